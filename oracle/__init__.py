@@ -1,0 +1,299 @@
+"""CPU ORACLE -- test infrastructure, NOT product code.
+
+ctypes front-end of ``oracle/librcg_oracle.so`` (``rcg_oracle.c``): a scalar plain-C
+restatement of rcognita's hot path (``System._state_dyn`` / ``closed_loop_rhs``, scipy's
+``RK45`` as driven by ``Simulator.sim_step``, ``CtrlOptPred.stage_obj`` / ``_critic`` /
+``_critic_cost`` / ``_actor_cost``) with reference file:line citations in the C source.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import this package.  ``rcognita_b200`` never does.
+
+Parity status: the reference has no tests or golden vectors of its own, so the oracle is
+pinned against outputs of the live reference captured by ``tests/golden/make_golden.py``
+(see ``tests/test_oracle_golden.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librcg_oracle.so")
+
+MAX_N, MAX_M, MAX_P, MAX_W = 5, 2, 7, 35
+
+SYS_IDS = {"3wrobotNI": 0, "3wrobot": 1, "2tank": 2}
+SYS_DIMS = {0: (3, 2), 1: (5, 2), 2: (2, 1)}
+MODES = {"MPC": 0, "RQL": 1, "SQL": 2}
+CRITIC_STRUCTS = {"quad-lin": 0, "quadratic": 1, "quad-nomix": 2, "quad-mix": 3}
+STAGE_STRUCTS = {"quadratic": 0, "biquadratic": 1}
+STATUS = {0: "running", 1: "finished", 2: "failed"}
+
+
+class SysT(C.Structure):
+    _fields_ = [("sys_id", C.c_int), ("n", C.c_int), ("m", C.c_int), ("has_bnds", C.c_int),
+                ("pars", C.c_double * 8), ("lo", C.c_double * MAX_M), ("hi", C.c_double * MAX_M)]
+
+
+class CtrlT(C.Structure):
+    _fields_ = [("mode", C.c_int), ("critic_struct", C.c_int), ("stage_struct", C.c_int),
+                ("has_target", C.c_int), ("Nactor", C.c_int), ("Ncritic", C.c_int),
+                ("gamma", C.c_double), ("pred_step_size", C.c_double),
+                ("R1", C.c_double * (MAX_P * MAX_P)), ("R2", C.c_double * (MAX_P * MAX_P)),
+                ("target", C.c_double * MAX_N)]
+
+
+class Rk45T(C.Structure):
+    _fields_ = [("t", C.c_double), ("t_bound", C.c_double), ("h_abs", C.c_double),
+                ("max_step", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+                ("y", C.c_double * MAX_N), ("f", C.c_double * MAX_N),
+                ("status", C.c_int), ("nfev", C.c_long)]
+
+
+def build(force: bool = False) -> str:
+    """Compile ``librcg_oracle.so`` (gcc; OpenMP if the toolchain has it)."""
+    src = os.path.join(_HERE, "rcg_oracle.c")
+    hdr = os.path.join(_HERE, "rcg_oracle.h")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return _LIB_PATH
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    base = [gcc, "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-shared",
+            "-o", _LIB_PATH, src, "-lm"]
+    for extra in (["-fopenmp"], []):
+        r = subprocess.run(base[:1] + extra + base[1:], capture_output=True, text=True)
+        if r.returncode == 0:
+            return _LIB_PATH
+    raise RuntimeError("oracle build failed:\n" + r.stderr)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.orc_dim_critic.restype = C.c_int
+        L.orc_state_dyn.argtypes = [C.POINTER(SysT), dp, dp, dp]
+        L.orc_closed_loop_rhs.argtypes = [C.POINTER(SysT), dp, dp, dp]
+        L.orc_rk45_init.argtypes = [C.POINTER(Rk45T), C.POINTER(SysT), dp, dp] + [C.c_double] * 6
+        L.orc_rk45_step.argtypes = [C.POINTER(Rk45T), C.POINTER(SysT), dp]
+        L.orc_rk45_step.restype = C.c_int
+        L.orc_stage_obj.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp]
+        L.orc_stage_obj.restype = C.c_double
+        L.orc_critic.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp, dp]
+        L.orc_critic.restype = C.c_double
+        L.orc_critic_cost.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp, dp, dp]
+        L.orc_critic_cost.restype = C.c_double
+        L.orc_actor_cost.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp]
+        L.orc_actor_cost.restype = C.c_double
+        L.orc_argmin.argtypes = [dp, C.c_int]
+        L.orc_argmin.restype = C.c_int
+        L.orc_actor_cost_table.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, dp, dp, dp, dp, ip]
+        L.orc_closed_loop.argtypes = ([C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, C.c_int, dp, C.c_int, dp, dp]
+                                      + [C.c_double] * 7 + [C.c_int, C.c_int, dp, dp, dp, ip, ip,
+                                                            C.POINTER(C.c_long), dp, C.c_int, ip,
+                                                            C.POINTER(C.c_longlong)])
+        L.orc_closed_loop.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    """float64 C-contiguous array + its double* (keeps the array alive via the tuple)."""
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    return arr, arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _null():
+    return C.POINTER(C.c_double)()
+
+
+def make_sys(name, pars=(), ctrl_bnds=None) -> SysT:
+    """``name`` is System.name of the reference: '3wrobotNI' | '3wrobot' | '2tank'."""
+    s = SysT()
+    s.sys_id = SYS_IDS[name]
+    s.n, s.m = SYS_DIMS[s.sys_id]
+    for i, p in enumerate(pars):
+        s.pars[i] = float(p)
+    b = np.zeros((0, 2)) if ctrl_bnds is None else np.asarray(ctrl_bnds, dtype=np.float64).reshape(-1, 2)
+    s.has_bnds = int(b.size > 0 and bool(b.any()))
+    for k in range(b.shape[0]):
+        s.lo[k], s.hi[k] = b[k, 0], b[k, 1]
+    return s
+
+
+def make_ctrl(n, m, mode="MPC", Nactor=1, pred_step_size=0.1, gamma=1.0, Ncritic=4, buffer_size=20,
+              critic_struct="quad-nomix", stage_obj_struct="quadratic", R1=None, R2=None,
+              observation_target=()) -> CtrlT:
+    c = CtrlT()
+    p = n + m
+    c.mode, c.critic_struct, c.stage_struct = MODES[mode], CRITIC_STRUCTS[critic_struct], STAGE_STRUCTS[stage_obj_struct]
+    c.Nactor = int(Nactor)
+    c.Ncritic = int(min(Ncritic, buffer_size - 1))
+    c.gamma, c.pred_step_size = float(gamma), float(pred_step_size)
+    for name, R in (("R1", R1), ("R2", R2)):
+        if R is not None:
+            R = np.asarray(R, dtype=np.float64)
+            if R.ndim == 1:
+                R = np.diag(R)
+            assert R.shape == (p, p)
+            flat = R.reshape(-1)
+            arr = getattr(c, name)
+            for i in range(p * p):
+                arr[i] = flat[i]
+    tgt = np.asarray(observation_target, dtype=np.float64).reshape(-1)
+    c.has_target = int(tgt.size > 0)
+    for i in range(tgt.size):
+        c.target[i] = tgt[i]
+    return c
+
+
+def dim_critic(critic_struct, n, m):
+    return lib().orc_dim_critic(CRITIC_STRUCTS[critic_struct], n, m)
+
+
+def state_dyn(s, state, action):
+    st, stp = _d(state)
+    ac, acp = _d(np.atleast_1d(action))
+    out = np.zeros(s.n)
+    lib().orc_state_dyn(C.byref(s), stp, acp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def closed_loop_rhs(s, y, action):
+    """Returns (rhs, clipped_action); the input ``action`` is not modified."""
+    yy, yp = _d(y)
+    ac = np.array(np.atleast_1d(action), dtype=np.float64)
+    out = np.zeros(s.n)
+    lib().orc_closed_loop_rhs(C.byref(s), yp, ac.ctypes.data_as(C.POINTER(C.c_double)),
+                              out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out, ac
+
+
+class RK45:
+    """One scipy-RK45-like solver lane bound to a system and a mutable action array."""
+
+    def __init__(self, s, y0, t0, t_bound, max_step, first_step=1e-6, rtol=1e-3, atol=1e-5, action=None):
+        self.s = s
+        self.r = Rk45T()
+        self.action = np.zeros(MAX_M) if action is None else np.array(action, dtype=np.float64)
+        y0a, y0p = _d(y0)
+        lib().orc_rk45_init(C.byref(self.r), C.byref(s), y0p, self._ap(), t0, t_bound, max_step,
+                            first_step, rtol, atol)
+
+    def _ap(self):
+        return self.action.ctypes.data_as(C.POINTER(C.c_double))
+
+    def receive_action(self, action):
+        a = np.atleast_1d(np.asarray(action, dtype=np.float64))
+        self.action[: a.size] = a
+
+    def step(self):
+        rc = lib().orc_rk45_step(C.byref(self.r), C.byref(self.s), self._ap())
+        if rc < 0:
+            raise RuntimeError("Attempt to step on a failed or finished solver.")
+        return rc
+
+    t = property(lambda self: self.r.t)
+    h_abs = property(lambda self: self.r.h_abs)
+    nfev = property(lambda self: self.r.nfev)
+    status = property(lambda self: STATUS[self.r.status])
+    y = property(lambda self: np.array(self.r.y[: self.s.n]))
+    f = property(lambda self: np.array(self.r.f[: self.s.n]))
+
+
+def stage_obj(c, n, m, obs, act):
+    o, op = _d(obs)
+    a, ap = _d(np.atleast_1d(act))
+    return lib().orc_stage_obj(C.byref(c), n, m, op, ap)
+
+
+def critic(c, n, m, obs, act, w):
+    o, op = _d(obs)
+    a, ap = _d(np.atleast_1d(act))
+    ww, wp = _d(w)
+    return lib().orc_critic(C.byref(c), n, m, op, ap, wp)
+
+
+def critic_cost(c, n, m, obs_buf, act_buf, w, w_prev):
+    ob, obp = _d(obs_buf)
+    ab, abp = _d(act_buf)
+    ww, wp = _d(w)
+    wv, wvp = _d(w_prev)
+    return lib().orc_critic_cost(C.byref(c), n, m, obp, abp, wp, wvp)
+
+
+def actor_cost(c, s, action_sqn, observation, state_sys, w_critic=None):
+    a, ap = _d(action_sqn)
+    o, op = _d(observation)
+    x, xp = _d(state_sys)
+    if w_critic is None:
+        w, wp = None, _null()
+    else:
+        w, wp = _d(w_critic)
+    return lib().orc_actor_cost(C.byref(c), C.byref(s), ap, op, xp, wp)
+
+
+def actor_cost_table(c, s, cand, observation, state_sys, w_critic=None):
+    """J[C] and np.argmin(J) for a candidate table [C, Nactor*m]."""
+    cd, cp = _d(cand)
+    o, op = _d(observation)
+    x, xp = _d(state_sys)
+    if w_critic is None:
+        w, wp = None, _null()
+    else:
+        w, wp = _d(w_critic)
+    ncand = cd.shape[0]
+    J = np.zeros(ncand)
+    am = C.c_int(-1)
+    lib().orc_actor_cost_table(C.byref(c), C.byref(s), ncand, cp, op, xp, wp,
+                               J.ctypes.data_as(C.POINTER(C.c_double)), C.byref(am))
+    return J, am.value
+
+
+def argmin(J):
+    j, jp = _d(J)
+    return lib().orc_argmin(jp, j.size)
+
+
+def closed_loop(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_step, first_step=1e-6,
+                rtol=1e-3, atol=1e-5, w_critic=None, max_steps_per_env=1 << 30, nthreads=0, traj_cap=0):
+    """Closed loop with the enumerate-and-argmin controller for E envs.
+
+    ``state_init`` [E, n]; ``cand`` [C, N*m] (shared) or [E, C, N*m] (per env).
+    Returns a dict of per-env results (+ ``traj`` of env 0 if ``traj_cap`` > 0).
+    """
+    x0, x0p = _d(np.atleast_2d(state_init))
+    E = x0.shape[0]
+    cd, cp = _d(cand)
+    per_env = int(cd.ndim == 3)
+    ncand = cd.shape[-2]
+    ai, aip = _d(np.atleast_1d(action_init))
+    if w_critic is None:
+        w, wp = None, _null()
+    else:
+        w, wp = _d(w_critic)
+    n, m = s.n, s.m
+    yf = np.zeros((E, n)); tf = np.zeros(E); acc = np.zeros(E)
+    nst = np.zeros(E, dtype=np.int32); nsa = np.zeros(E, dtype=np.int32); nfe = np.zeros(E, dtype=np.int64)
+    ncol = 1 + n + m + 3
+    traj = np.zeros((max(traj_cap, 1), ncol))
+    rows = C.c_int(0)
+    evals = C.c_longlong(0)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    total = lib().orc_closed_loop(
+        C.byref(c), C.byref(s), E, x0p, ncand, cp, per_env, wp, aip, sampling_time, t0, t1, max_step,
+        first_step, rtol, atol, int(max_steps_per_env), int(nthreads),
+        yf.ctypes.data_as(dp), tf.ctypes.data_as(dp), acc.ctypes.data_as(dp), nst.ctypes.data_as(ip),
+        nsa.ctypes.data_as(ip), nfe.ctypes.data_as(C.POINTER(C.c_long)),
+        traj.ctypes.data_as(dp) if traj_cap > 0 else _null(), int(traj_cap), C.byref(rows), C.byref(evals))
+    return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfev": nfe,
+            "traj": traj[: rows.value], "total_steps": int(total), "total_evals": int(evals.value)}
