@@ -1,0 +1,202 @@
+/*
+ * rcg.h -- C ABI of librcg_b200.so: the B200 (sm_100a) batched agent-environment engine
+ * for rcognita's data-parallel hot path.
+ *
+ * The reference (AIDynamicAction/rcognita v0.1.2) is pure Python and has no FFI seam; its
+ * boundary for this path is a set of Python methods.  Each entry point below replaces the
+ * per-environment arithmetic of one of those methods for E independent environments
+ * ("lanes") at once; the Python mirror classes in rcognita_b200/ (same names and
+ * signatures as the reference) are the only intended callers and bind these symbols with
+ * ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers (cudaMalloc / torch CUDA tensors); the two
+ *    descriptor structs are HOST pointers, read during the call.
+ *  - Struct-of-arrays, component-major: a per-lane vector quantity v of dimension d is
+ *    stored as v[i * E + e] (i < d component, e < E lane), so a warp reads 32 consecutive
+ *    lanes of one component with one coalesced 256-byte request.
+ *  - fp64 entry points have no suffix; "_f32" twins take float arrays for states, costs
+ *    and weights but keep every time-like quantity (t, h_abs, ctrl_clock) in fp64.
+ *  - All launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream).  Return value: 0 on success, otherwise a cudaError_t or a
+ *    negative RCG_E* code; rcg_last_error_string() describes the last failure of the
+ *    calling thread.
+ *  - Nothing here falls back to the CPU: without a CUDA device every compute entry point
+ *    returns an error.
+ */
+#ifndef RCG_H
+#define RCG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCG_VERSION 100          /* 0.1.0 */
+
+#define RCG_MAX_N 5              /* dim_state = dim_output <= 5 (Sys3WRobot)  */
+#define RCG_MAX_M 2              /* dim_input <= 2                            */
+#define RCG_MAX_P 7              /* n + m                                     */
+#define RCG_MAX_W 35             /* dim_critic <= 35 (quad-lin, p = 7)        */
+#define RCG_MAX_NACTOR 64        /* prediction horizon Nactor <= 64           */
+
+/* System.name of the reference (rcognita/systems.py:363, :301, :410). */
+enum { RCG_SYS_3WROBOT_NI = 0, RCG_SYS_3WROBOT = 1, RCG_SYS_2TANK = 2 };
+/* CtrlOptPred.mode (rcognita/controllers.py:1304-1326). */
+enum { RCG_MODE_MPC = 0, RCG_MODE_RQL = 1, RCG_MODE_SQL = 2 };
+/* CtrlOptPred.critic_struct (rcognita/controllers.py:1204-1212). */
+enum { RCG_CRITIC_QUAD_LIN = 0, RCG_CRITIC_QUADRATIC = 1, RCG_CRITIC_QUAD_NOMIX = 2, RCG_CRITIC_QUAD_MIX = 3 };
+/* CtrlOptPred.stage_obj_struct (rcognita/controllers.py:1076-1082). */
+enum { RCG_STAGE_QUADRATIC = 0, RCG_STAGE_BIQUADRATIC = 1 };
+/* scipy OdeSolver.status per lane ('running' | 'finished' | 'failed', scipy base.py:189-208). */
+enum { RCG_RUNNING = 0, RCG_FINISHED = 1, RCG_FAILED = 2 };
+
+enum { RCG_EINVAL = -1, RCG_ENODEV = -2 };
+
+/* The fields of rcognita.systems.System the path reads (rcognita/systems.py:69-145). */
+typedef struct rcg_system {
+    int32_t sys_id;              /* RCG_SYS_*                                              */
+    int32_t has_bnds;            /* ctrl_bnds.any()  (systems.py:241)                      */
+    double  pars[8];             /* Sys3WRobot [m, I]; Sys2Tank [tau1, tau2, K1, K2, K3]   */
+    double  lo[RCG_MAX_M];       /* ctrl_bnds[:, 0]                                        */
+    double  hi[RCG_MAX_M];       /* ctrl_bnds[:, 1]                                        */
+} rcg_system_t;
+
+/* The fields of rcognita.controllers.CtrlOptPred that stage_obj / _critic / _critic_cost /
+ * _actor_cost read (rcognita/controllers.py:811-1042). */
+typedef struct rcg_objective {
+    int32_t mode;                /* RCG_MODE_*                                             */
+    int32_t critic_struct;       /* RCG_CRITIC_*                                           */
+    int32_t stage_struct;        /* RCG_STAGE_*                                            */
+    int32_t r_is_diag;           /* 1: only the diagonals of R1/R2 are non-zero            */
+    int32_t has_target;          /* observation_target != []                               */
+    int32_t Nactor;              /* prediction horizon                                     */
+    int32_t Ncritic;             /* critic stack size, already min(Ncritic, buffer_size-1) */
+    int32_t buffer_size;         /* rows of the observation/action FIFO buffers            */
+    double  gamma;               /* discounting factor                                     */
+    double  pred_step_size;      /* Euler predictor step                                   */
+    double  gamma_pow[RCG_MAX_NACTOR];   /* gamma**k, k < Nactor, computed by the host with
+                                            libm pow() exactly like Python's float.__pow__ */
+    double  R1[RCG_MAX_P * RCG_MAX_P];   /* stage_obj_pars[0], row-major [p, p]            */
+    double  R2[RCG_MAX_P * RCG_MAX_P];   /* stage_obj_pars[1] (biquadratic only)           */
+    double  target[RCG_MAX_N];           /* observation_target                             */
+} rcg_objective_t;
+
+/* scipy RK45 settings as passed at rcognita/simulator.py:150. */
+typedef struct rcg_solver {
+    double t_bound;              /* t1                                                     */
+    double max_step;             /* dt / 2 (Simulator ignores its own max_step argument)   */
+    double rtol, atol;
+} rcg_solver_t;
+
+int         rcg_version(void);
+const char *rcg_last_error_string(void);
+/* Number of CUDA devices visible, or a negative RCG_E* code (never touches a kernel). */
+int         rcg_device_count(void);
+/* dim_state / dim_input / dim_critic helpers (controllers.py:1024-1039). */
+int         rcg_dim_state(int32_t sys_id);
+int         rcg_dim_input(int32_t sys_id);
+int         rcg_dim_critic(int32_t critic_struct, int32_t n, int32_t m);
+/* Kernels launched by this library since load / since the last reset (bench "gpu_launches"). */
+int64_t     rcg_launch_count(void);
+void        rcg_reset_launch_count(void);
+
+/* System.closed_loop_rhs (rcognita/systems.py:213-253), is_disturb = is_dyn_ctrl = 0:
+ * clips action[m][E] IN PLACE to ctrl_bnds, then f_out[n][E] = _state_dyn(y, action)
+ * (systems.py:308-323, :370-382, :412-419).  Used by Simulator.__init__ to seed the FSAL
+ * derivative f = fun(t0, y0) that scipy evaluates at construction (scipy rk.py:97). */
+int rcg_rhs(const rcg_system_t *sys, int64_t E, const double *y, double *action, double *f_out, void *stream);
+int rcg_rhs_f32(const rcg_system_t *sys, int64_t E, const float *y, float *action, float *f_out, void *stream);
+
+/* System._state_dyn alone (no clipping): dstate[n][E] = _state_dyn(state, action). */
+int rcg_state_dyn(const rcg_system_t *sys, int64_t E, const double *state, const double *action,
+                  double *dstate, void *stream);
+
+/* Simulator.sim_step, 'diff_eqn' branch (rcognita/simulator.py:161-168) = scipy
+ * RK45.step() (scipy base.py:179-212, rk.py:111-176, rk.py:61-71): exactly ONE accepted
+ * Dormand-Prince step per RUNNING lane, with per-lane adaptive step control, FSAL
+ * derivative f carried across calls (stale w.r.t. action changes, like scipy), in-place
+ * clipping of action.  Lanes that are not RUNNING are left untouched.  nfev[E] (may be
+ * NULL) is incremented by 6 per attempt. */
+int rcg_rk45_step(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E,
+                  double *y, double *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                  double *action, void *stream);
+int rcg_rk45_step_f32(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E,
+                      float *y, float *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                      float *action, void *stream);
+
+/* Fused main-loop body of presets/main_3wrobot_NI.py:415-440 between two controller
+ * samples: each RUNNING lane repeats { sim_step; receive_sys_state; upd_accum_obj } with
+ * the held action until its own sampling event `t - ctrl_clock >= sampling_time`
+ * (rcognita/controllers.py:1440-1442), for at most max_steps accepted steps.  On a sampling
+ * event the lane stops with sample_flag = 1, ctrl_clock = t and state_sys = the state BEFORE
+ * the last step (the one-step lag of receive_sys_state); the accumulated
+ * objective of that step is left to rcg_actor_cost's epilogue, which knows the new action.
+ * On non-sampling steps accum += stage_obj(y, action) * sampling_time (controllers.py:1093).
+ * nsteps[E] (may be NULL) counts accepted steps. */
+int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
+                     int64_t E, double *y, double *f, double *t, double *h_abs, int32_t *status,
+                     int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
+                     double sampling_time, int32_t max_steps, double *state_sys, double *accum,
+                     int32_t *sample_flag, void *stream);
+int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
+                         int64_t E, float *y, float *f, double *t, double *h_abs, int32_t *status,
+                         int32_t *nfev, int32_t *nsteps, float *action, double *ctrl_clock,
+                         double sampling_time, int32_t max_steps, float *state_sys, float *accum,
+                         int32_t *sample_flag, void *stream);
+
+/* CtrlOptPred._actor_cost (rcognita/controllers.py:1273-1328) for E environments x C
+ * candidate action sequences, one thread per (environment, candidate), plus np.argmin over
+ * the candidates of each environment (first minimal index wins, NaN counts as minimal).
+ *   state_sys[n][E], obs[n][E]  -- predictor start state and current observation.
+ *   cand                        -- cand_per_env = 0: one shared table [Nactor*m][C]
+ *                                  (component-major = transpose of the reference's
+ *                                  action_sqn rows); cand_per_env = 1: [Nactor*m][E*C],
+ *                                  element (k, j, e, c) at ((k*m + j) * E + e) * C + c.
+ *   w_critic                    -- w_per_env = 0: [dim_critic]; 1: [dim_critic][E]; may be
+ *                                  NULL in MPC mode.
+ *   mask[E] or NULL             -- environments with mask == 0 are skipped entirely.
+ *   J_out[E*C] or NULL          -- every cost (J_out[e*C + c]).
+ *   argmin_out[E], Jmin_out[E]  -- or NULL.
+ *   action_out[m][E] or NULL    -- first action of the arg-min sequence
+ *                                  (_actor_optimizer's return value, controllers.py:1427).
+ *   accum[E] or NULL            -- += stage_obj(obs, action_best) * sampling_time
+ *                                  (upd_accum_obj for the sampling step, controllers.py:1093). */
+int rcg_actor_cost(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t C,
+                   const double *state_sys, const double *obs, const double *cand, int32_t cand_per_env,
+                   const double *w_critic, int32_t w_per_env, const int32_t *mask,
+                   double *J_out, int32_t *argmin_out, double *Jmin_out, double *action_out,
+                   double *accum, double sampling_time, void *stream);
+int rcg_actor_cost_f32(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t C,
+                       const float *state_sys, const float *obs, const float *cand, int32_t cand_per_env,
+                       const float *w_critic, int32_t w_per_env, const int32_t *mask,
+                       float *J_out, int32_t *argmin_out, float *Jmin_out, float *action_out,
+                       float *accum, double sampling_time, void *stream);
+
+/* CtrlOptPred.stage_obj (rcognita/controllers.py:1063-1084): out[E] = stage_obj(obs, act);
+ * if accum != NULL additionally accum[E] += out * scale (upd_accum_obj, :1086-1093). */
+int rcg_stage_obj(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs,
+                  const double *act, double *out, double *accum, double scale, void *stream);
+
+/* CtrlOptPred._critic (rcognita/controllers.py:1192-1214): out[E] = w . phi(obs, act). */
+int rcg_critic(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs,
+               const double *act, const double *w, int32_t w_per_env, double *out, void *stream);
+
+/* CtrlOptPred._critic_cost (rcognita/controllers.py:1216-1245) for E environments x W weight
+ * vectors per environment.  obs_buf [buffer_size][n][E], act_buf [buffer_size][m][E] hold the
+ * FIFO buffers (row 0 = oldest, push_vec of rcognita/utilities.py:78-79); w [dimc][E*W]
+ * (element (i, e, k) at (i*E + e)*W + k), w_prev [dimc][E]; Jc_out [E*W]. */
+int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W,
+                    const double *obs_buf, const double *act_buf, const double *w, const double *w_prev,
+                    double *Jc_out, void *stream);
+
+/* utilities.push_vec on the controller FIFO buffers for the lanes with mask != 0
+ * (rcognita/controllers.py:1463-1464): rows shift up by one, the new row goes to the bottom. */
+int rcg_push_buffers(int32_t n, int32_t m, int32_t buffer_size, int64_t E, double *obs_buf, double *act_buf,
+                     const double *obs, const double *act, const int32_t *mask, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCG_H */

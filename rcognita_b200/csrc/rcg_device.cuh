@@ -1,0 +1,183 @@
+// rcg_device.cuh -- device-side building blocks shared by the sm_100a kernels:
+// the three environments' dynamics, the stage objective and the critic features.
+// Every function cites the reference line it reproduces (paths relative to the rcognita
+// v0.1.2 tree).  T is the arithmetic type of the path (double, or float for the _f32 twins).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rcg.h"
+
+namespace rcg {
+
+template <int SYS> struct SysDim;
+template <> struct SysDim<RCG_SYS_3WROBOT_NI> { static constexpr int n = 3, m = 2; };
+template <> struct SysDim<RCG_SYS_3WROBOT>    { static constexpr int n = 5, m = 2; };
+template <> struct SysDim<RCG_SYS_2TANK>      { static constexpr int n = 2, m = 1; };
+
+// Kernel-parameter copies of the host descriptors (passed by value -> constant bank).
+template <typename T>
+struct SysDev {
+    T pars[8];
+    T lo[RCG_MAX_M], hi[RCG_MAX_M];
+    int has_bnds;
+};
+
+template <typename T>
+struct ObjDev {
+    int stage_struct, has_target, Nactor, Ncritic, buffer_size;
+    T gamma, pred_step_size;
+    T gamma_pow[RCG_MAX_NACTOR];
+    T R1[RCG_MAX_P * RCG_MAX_P];
+    T R2[RCG_MAX_P * RCG_MAX_P];
+    T target[RCG_MAX_N];      // zeros when has_target == 0 (x - 0 == x exactly)
+};
+
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+
+// System._state_dyn, is_disturb = 0:
+//   Sys3WRobotNI rcognita/systems.py:370-382, Sys3WRobot :308-323, Sys2Tank :412-419.
+// Operation order follows the Python expressions literally.
+template <typename T, int SYS>
+__device__ __forceinline__ void state_dyn(const SysDev<T> &S, const T *x, const T *a, T *d)
+{
+    if constexpr (SYS == RCG_SYS_3WROBOT_NI) {
+        T s, c;
+        sincos_t(x[2], &s, &c);
+        d[0] = a[0] * c;
+        d[1] = a[0] * s;
+        d[2] = a[1];
+    } else if constexpr (SYS == RCG_SYS_3WROBOT) {
+        T s, c;
+        sincos_t(x[2], &s, &c);
+        d[0] = x[3] * c;
+        d[1] = x[3] * s;
+        d[2] = x[4];
+        d[3] = (T(1) / S.pars[0]) * a[0];          // 1/m * F
+        d[4] = (T(1) / S.pars[1]) * a[1];          // 1/I * M
+    } else {
+        const T tau1 = S.pars[0], tau2 = S.pars[1], K1 = S.pars[2], K2 = S.pars[3], K3 = S.pars[4];
+        d[0] = (T(1) / tau1) * (-x[0] + K1 * a[0]);
+        d[1] = (T(1) / tau2) * ((-x[1] + K2 * x[0]) + K3 * (x[1] * x[1]));
+    }
+}
+
+// The clipping of System.closed_loop_rhs (rcognita/systems.py:241-243): np.clip(a, lo, hi).
+template <typename T, int M>
+__device__ __forceinline__ void clip_action(const SysDev<T> &S, T *a)
+{
+    if (S.has_bnds) {
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            T v = a[k];
+            v = (v < S.lo[k]) ? S.lo[k] : v;        // NaN stays NaN, like np.clip
+            v = (v > S.hi[k]) ? S.hi[k] : v;
+            a[k] = v;
+        }
+    }
+}
+
+// x @ R @ x evaluated left to right like numpy: v = x @ R, then v @ x.
+template <typename T, int P, bool RDIAG>
+__device__ __forceinline__ T quad_form(const T *x, const T *R)
+{
+    T out = T(0);
+    if constexpr (RDIAG) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) out += (x[j] * R[j * P + j]) * x[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            T acc = T(0);
+#pragma unroll
+            for (int i = 0; i < P; ++i) acc += x[i] * R[i * P + j];
+            out += acc * x[j];
+        }
+    }
+    return out;
+}
+
+// CtrlOptPred.stage_obj (rcognita/controllers.py:1063-1084), a.k.a. rcost.
+template <typename T, int N, int M, bool RDIAG>
+__device__ __forceinline__ T stage_obj(const ObjDev<T> &O, const T *obs, const T *act)
+{
+    constexpr int P = N + M;
+    T chi[P];
+#pragma unroll
+    for (int i = 0; i < N; ++i) chi[i] = obs[i] - O.target[i];
+#pragma unroll
+    for (int j = 0; j < M; ++j) chi[N + j] = act[j];
+    if (O.stage_struct == RCG_STAGE_QUADRATIC) {
+        return quad_form<T, P, RDIAG>(chi, O.R1);
+    } else {
+        T chi2[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) chi2[i] = chi[i] * chi[i];
+        return quad_form<T, P, RDIAG>(chi2, O.R2) + quad_form<T, P, RDIAG>(chi, O.R1);
+    }
+}
+
+// CtrlOptPred._critic (rcognita/controllers.py:1192-1214): w . phi(obs, act).  Feature order:
+// uptria2vec is row-major i <= j (rcognita/utilities.py:81-96); np.kron(obs, act)[i*M + j] =
+// obs_i * act_j; quad-mix uses the RAW observation (controllers.py:1212).  `w(i)` is any
+// accessor of the i-th weight (shared memory, registers or a strided global load).
+template <typename T, int N, int M, int CS, class WAcc>
+__device__ __forceinline__ T critic(const ObjDev<T> &O, const T *obs, const T *act, WAcc w)
+{
+    constexpr int P = N + M;
+    T chi[P];
+#pragma unroll
+    for (int i = 0; i < N; ++i) chi[i] = obs[i] - O.target[i];
+#pragma unroll
+    for (int j = 0; j < M; ++j) chi[N + j] = act[j];
+    T q = T(0);
+    int k = 0;
+    if constexpr (CS == RCG_CRITIC_QUAD_LIN || CS == RCG_CRITIC_QUADRATIC) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = i; j < P; ++j) q += w(k++) * (chi[i] * chi[j]);
+        if constexpr (CS == RCG_CRITIC_QUAD_LIN) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) q += w(k++) * chi[i];
+        }
+    } else if constexpr (CS == RCG_CRITIC_QUAD_NOMIX) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) q += w(k++) * (chi[i] * chi[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) q += w(k++) * (obs[i] * obs[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) q += w(k++) * (obs[i] * act[j]);
+#pragma unroll
+        for (int j = 0; j < M; ++j) q += w(k++) * (act[j] * act[j]);
+    }
+    return q;
+}
+
+__host__ __device__ constexpr int dim_critic_c(int cs, int n, int m)
+{
+    const int p = n + m;
+    return cs == RCG_CRITIC_QUAD_LIN ? (p + 1) * p / 2 + p
+         : cs == RCG_CRITIC_QUADRATIC ? (p + 1) * p / 2
+         : cs == RCG_CRITIC_QUAD_NOMIX ? p
+         : n + n * m + m;
+}
+
+// (J, index) ordering of np.argmin: NaN is minimal, ties go to the lower index.
+template <typename T>
+__device__ __forceinline__ bool argmin_better(T Ja, int ia, T Jb, int ib)
+{
+    const bool na = Ja != Ja, nb = Jb != Jb;
+    if (na || nb) return (na && nb) ? (ia < ib) : na;
+    if (Ja < Jb) return true;
+    if (Ja > Jb) return false;
+    return ia < ib;
+}
+
+}  // namespace rcg

@@ -1,0 +1,367 @@
+// rk45.cu -- batched closed-loop integration: System.closed_loop_rhs and a per-lane
+// restatement of scipy.integrate.RK45 as Simulator.sim_step drives it
+// (rcognita/simulator.py:150, :161-168; scipy/integrate/_ivp/rk.py:14-71, :111-176,
+// base.py:179-212, common.py:63-65).
+//
+// One thread per environment ("lane"); y, f and the seven stage derivatives live in
+// registers; per-lane adaptive step control (accept/reject loop) exactly as scipy's,
+// including the FSAL derivative that is NOT refreshed when the action changes between
+// steps.  This translation unit is compiled with -fmad=false: the step
+// size feeds the fp64 time accumulation that decides on which solver step the controller
+// samples (section 3.3), so every multiply and add must round separately like numpy's.
+#include "rcg_host.h"
+
+namespace rcg {
+
+struct SolverDev {
+    double t_bound, max_step, rtol, atol;
+};
+
+// scipy rk.py:538-553 (class RK45)
+#define RK_A10 (1.0 / 5)
+#define RK_A20 (3.0 / 40)
+#define RK_A21 (9.0 / 40)
+#define RK_A30 (44.0 / 45)
+#define RK_A31 (-56.0 / 15)
+#define RK_A32 (32.0 / 9)
+#define RK_A40 (19372.0 / 6561)
+#define RK_A41 (-25360.0 / 2187)
+#define RK_A42 (64448.0 / 6561)
+#define RK_A43 (-212.0 / 729)
+#define RK_A50 (9017.0 / 3168)
+#define RK_A51 (-355.0 / 33)
+#define RK_A52 (46732.0 / 5247)
+#define RK_A53 (49.0 / 176)
+#define RK_A54 (-5103.0 / 18656)
+#define RK_B0 (35.0 / 384)
+#define RK_B1 (0.0)
+#define RK_B2 (500.0 / 1113)
+#define RK_B3 (125.0 / 192)
+#define RK_B4 (-2187.0 / 6784)
+#define RK_B5 (11.0 / 84)
+#define RK_E0 (-71.0 / 57600)
+#define RK_E1 (0.0)
+#define RK_E2 (71.0 / 16695)
+#define RK_E3 (-71.0 / 1920)
+#define RK_E4 (17253.0 / 339200)
+#define RK_E5 (-22.0 / 525)
+#define RK_E6 (1.0 / 40)
+
+// One scipy RK45.step() for one lane.  Returns false if the step failed (TOO_SMALL_STEP).
+// On success t, h_abs, y, f are advanced and *attempts holds the number of rk_step calls.
+template <typename T, int SYS>
+__device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDev &sol, const T *a,
+                                              double &t, double &h_abs, T *y, T *f, int &attempts)
+{
+    constexpr int N = SysDim<SYS>::n;
+    const double t0 = t;
+    const double min_step = 10 * fabs(nextafter(t0, (double)INFINITY) - t0);   // rk.py:118
+    double ha;
+    if (h_abs > sol.max_step) ha = sol.max_step;                               // rk.py:120-125
+    else if (h_abs < min_step) ha = min_step;
+    else ha = h_abs;
+
+    bool rejected = false;
+    T K[7][N], yn[N], yt[N];
+    double t_new;
+    attempts = 0;
+    for (;;) {
+        if (ha < min_step) return false;                                       // rk.py:131-132
+        double h = ha;
+        t_new = t0 + h;
+        if (t_new - sol.t_bound > 0) t_new = sol.t_bound;                      // rk.py:137-138
+        h = t_new - t0;
+        ha = fabs(h);
+        const T hT = (T)h;
+        ++attempts;
+
+        // rk_step (rk.py:61-71): dy = np.dot(K[:s].T, a[:s]) * h, sums left to right from 0.
+#pragma unroll
+        for (int i = 0; i < N; ++i) K[0][i] = f[i];                            // FSAL, never refreshed
+#pragma unroll
+        for (int i = 0; i < N; ++i) yt[i] = y[i] + (T(0) + K[0][i] * T(RK_A10)) * hT;
+        state_dyn<T, SYS>(S, yt, a, K[1]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yt[i] = y[i] + ((T(0) + K[0][i] * T(RK_A20)) + K[1][i] * T(RK_A21)) * hT;
+        state_dyn<T, SYS>(S, yt, a, K[2]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yt[i] = y[i] + (((T(0) + K[0][i] * T(RK_A30)) + K[1][i] * T(RK_A31)) + K[2][i] * T(RK_A32)) * hT;
+        state_dyn<T, SYS>(S, yt, a, K[3]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yt[i] = y[i] + ((((T(0) + K[0][i] * T(RK_A40)) + K[1][i] * T(RK_A41)) + K[2][i] * T(RK_A42)) +
+                            K[3][i] * T(RK_A43)) * hT;
+        state_dyn<T, SYS>(S, yt, a, K[4]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yt[i] = y[i] + (((((T(0) + K[0][i] * T(RK_A50)) + K[1][i] * T(RK_A51)) + K[2][i] * T(RK_A52)) +
+                             K[3][i] * T(RK_A53)) + K[4][i] * T(RK_A54)) * hT;
+        state_dyn<T, SYS>(S, yt, a, K[5]);
+        // y_new = y + h * np.dot(K[:-1].T, B)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yn[i] = y[i] + hT * ((((((T(0) + K[0][i] * T(RK_B0)) + K[1][i] * T(RK_B1)) + K[2][i] * T(RK_B2)) +
+                                   K[3][i] * T(RK_B3)) + K[4][i] * T(RK_B4)) + K[5][i] * T(RK_B5));
+        state_dyn<T, SYS>(S, yn, a, K[6]);
+
+        // error norm: rk.py:105-109, :146-147; common.py:63-65
+        T sq = T(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const T scale = (T)sol.atol + fmax(fabs(y[i]), fabs(yn[i])) * (T)sol.rtol;
+            const T acc = ((((((T(0) + K[0][i] * T(RK_E0)) + K[1][i] * T(RK_E1)) + K[2][i] * T(RK_E2)) +
+                             K[3][i] * T(RK_E3)) + K[4][i] * T(RK_E4)) + K[5][i] * T(RK_E5)) + K[6][i] * T(RK_E6);
+            const T e = acc * hT / scale;
+            sq += e * e;
+        }
+        const double err = (double)(sqrt(sq) / sqrt((T)N));
+
+        if (err < 1) {                                                         // rk.py:149-160
+            double factor;
+            if (err == 0) factor = 10;
+            else factor = fmin(10.0, 0.9 * pow(err, -0.2));
+            if (rejected) factor = fmin(1.0, factor);
+            ha *= factor;
+            break;
+        } else {                                                               // rk.py:161-164
+            ha *= fmax(0.2, 0.9 * pow(err, -0.2));
+            rejected = true;
+        }
+    }
+    t = t_new;
+    h_abs = ha;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y[i] = yn[i]; f[i] = K[6][i]; }
+    return true;
+}
+
+// CTRL = false: Simulator.sim_step (one accepted step per running lane).
+// CTRL = true : the fused loop body between two controller samples (see rcg_rk45_advance).
+template <typename T, int SYS, bool CTRL, bool RDIAG>
+__global__ void __launch_bounds__(128)
+rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
+            const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
+            double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
+            int32_t *__restrict__ nfev_g, int32_t *__restrict__ nsteps_g, T *__restrict__ action_g,
+            double *__restrict__ clock_g, double sampling_time, int max_steps, T *__restrict__ state_sys_g,
+            T *__restrict__ accum_g, int32_t *__restrict__ flag_g)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int st = status_g[e];
+    if (st != RCG_RUNNING) {
+        if (CTRL && flag_g) flag_g[e] = 0;
+        return;
+    }
+    T y[N], f[N], a[M], yprev[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y[i] = y_g[i * E + e]; f[i] = f_g[i * E + e]; yprev[i] = y[i]; }
+#pragma unroll
+    for (int j = 0; j < M; ++j) a[j] = action_g[j * E + e];
+    clip_action<T, M>(S, a);                       // systems.py:241-243, in place
+    double t = t_g[e], h_abs = h_g[e];
+    double clock = CTRL ? clock_g[e] : 0.0;
+    T acc = (CTRL && accum_g) ? accum_g[e] : T(0);
+    int nf = 0, ns = 0, flag = 0;
+
+    for (int it = 0; it < max_steps && st == RCG_RUNNING; ++it) {
+        if (t == sol.t_bound) { st = RCG_FINISHED; break; }                    // base.py:192-197
+#pragma unroll
+        for (int i = 0; i < N; ++i) yprev[i] = y[i];
+        int attempts;
+        const bool ok = rk45_one_step<T, SYS>(S, sol, a, t, h_abs, y, f, attempts);
+        nf += 6 * attempts;
+        if (!ok) { st = RCG_FAILED; break; }                                   // base.py:203-204
+        ++ns;
+        if (t - sol.t_bound >= 0) st = RCG_FINISHED;                           // base.py:207-208
+        if constexpr (CTRL) {
+            if (t - clock >= sampling_time) {                                  // controllers.py:1440-1442
+                clock = t;
+                flag = 1;
+                break;
+            }
+            // held action: compute_action returns action_curr (:1492-1493); upd_accum_obj (:1093)
+            acc += stage_obj<T, N, M, RDIAG>(O, y, a) * (T)sampling_time;
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y_g[i * E + e] = y[i]; f_g[i * E + e] = f[i]; }
+#pragma unroll
+    for (int j = 0; j < M; ++j) action_g[j * E + e] = a[j];
+    t_g[e] = t;
+    h_g[e] = h_abs;
+    status_g[e] = st;
+    if (nfev_g) nfev_g[e] += nf;
+    if (nsteps_g) nsteps_g[e] += ns;
+    if constexpr (CTRL) {
+        clock_g[e] = clock;
+        if (accum_g) accum_g[e] = acc;
+        if (flag_g) flag_g[e] = flag;
+        if (state_sys_g && ns > 0) {
+            // sampling lanes: the predictor starts from the state BEFORE the last step
+            // (receive_sys_state runs after compute_action, main_3wrobot_NI.py:421-424);
+            // other lanes: receive_sys_state(y) has already happened for this step.
+#pragma unroll
+            for (int i = 0; i < N; ++i) state_sys_g[i * E + e] = flag ? yprev[i] : y[i];
+        }
+    }
+}
+
+template <typename T, int SYS, bool CLIP>
+__global__ void __launch_bounds__(256)
+rhs_kernel(const __grid_constant__ SysDev<T> S, int64_t E, const T *__restrict__ y_g, T *action_g, T *__restrict__ f_g)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    T y[N], a[M], d[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = y_g[i * E + e];
+#pragma unroll
+    for (int j = 0; j < M; ++j) a[j] = action_g[j * E + e];
+    if constexpr (CLIP) {
+        clip_action<T, M>(S, a);
+#pragma unroll
+        for (int j = 0; j < M; ++j) action_g[j * E + e] = a[j];
+    }
+    state_dyn<T, SYS>(S, y, a, d);
+#pragma unroll
+    for (int i = 0; i < N; ++i) f_g[i * E + e] = d[i];
+}
+
+template <typename T, bool CLIP>
+static int launch_rhs(const rcg_system_t *sys, int64_t E, const T *y, T *action, T *f_out, void *stream)
+{
+    RCG_REQUIRE(sys && y && action && f_out, "rcg_rhs: null argument");
+    RCG_REQUIRE(sys_n(sys->sys_id) > 0, "rcg_rhs: unknown sys_id %d", sys->sys_id);
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    const SysDev<T> S = make_sys_dev<T>(sys);
+    const unsigned grid = (unsigned)((E + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (sys->sys_id) {
+    case RCG_SYS_3WROBOT_NI: rhs_kernel<T, RCG_SYS_3WROBOT_NI, CLIP><<<grid, 256, 0, s>>>(S, E, y, action, f_out); break;
+    case RCG_SYS_3WROBOT:    rhs_kernel<T, RCG_SYS_3WROBOT, CLIP><<<grid, 256, 0, s>>>(S, E, y, action, f_out); break;
+    default:                 rhs_kernel<T, RCG_SYS_2TANK, CLIP><<<grid, 256, 0, s>>>(S, E, y, action, f_out); break;
+    }
+    return check_launch("rcg_rhs");
+}
+
+template <typename T, int SYS, bool CTRL>
+static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const SysDev<T> &S, const SolverDev &sol,
+                            const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
+                            int32_t *nfev, int32_t *nsteps, T *action, double *clock, double sampling_time,
+                            int max_steps, T *state_sys, T *accum, int32_t *flag)
+{
+    if (rdiag)
+        rk45_kernel<T, SYS, CTRL, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
+                                                             clock, sampling_time, max_steps, state_sys, accum, flag);
+    else
+        rk45_kernel<T, SYS, CTRL, false><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
+                                                              clock, sampling_time, max_steps, state_sys, accum, flag);
+}
+
+template <typename T, bool CTRL>
+static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solver_t *sol_h, const rcg_objective_t *obj,
+                       int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                       int32_t *nsteps, T *action, double *clock, double sampling_time, int max_steps,
+                       T *state_sys, T *accum, int32_t *flag, void *stream)
+{
+    RCG_REQUIRE(sys && sol_h && y && f && t && h_abs && status && action, "%s: null argument", what);
+    const int n = sys_n(sys->sys_id), m = sys_m(sys->sys_id);
+    RCG_REQUIRE(n > 0, "%s: unknown sys_id %d", what, sys->sys_id);
+    RCG_REQUIRE(sol_h->max_step > 0, "%s: `max_step` must be positive.", what);    // scipy common.py:18-23
+    if (CTRL) {
+        RCG_REQUIRE(obj && clock, "%s: objective and ctrl_clock are required", what);
+        RCG_REQUIRE(max_steps > 0, "%s: max_steps must be positive", what);
+    }
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    const SysDev<T> S = make_sys_dev<T>(sys);
+    const SolverDev sol{sol_h->t_bound, sol_h->max_step, sol_h->rtol, sol_h->atol};
+    ObjDev<T> O;
+    bool rdiag = true;
+    if (CTRL) {
+        O = make_obj_dev<T>(obj, n, m);
+        rdiag = obj->r_is_diag && is_diag(obj->R1, n + m) &&
+                (obj->stage_struct == RCG_STAGE_QUADRATIC || is_diag(obj->R2, n + m));
+    } else {
+        memset(&O, 0, sizeof(O));
+    }
+    const unsigned grid = (unsigned)((E + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (sys->sys_id) {
+    case RCG_SYS_3WROBOT_NI:
+        launch_rk45_sys<T, RCG_SYS_3WROBOT_NI, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag);
+        break;
+    case RCG_SYS_3WROBOT:
+        launch_rk45_sys<T, RCG_SYS_3WROBOT, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag);
+        break;
+    default:
+        launch_rk45_sys<T, RCG_SYS_2TANK, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag);
+        break;
+    }
+    return check_launch(what);
+}
+
+}  // namespace rcg
+
+extern "C" {
+
+int rcg_rhs(const rcg_system_t *sys, int64_t E, const double *y, double *action, double *f_out, void *stream)
+{
+    return rcg::launch_rhs<double, true>(sys, E, y, action, f_out, stream);
+}
+
+int rcg_rhs_f32(const rcg_system_t *sys, int64_t E, const float *y, float *action, float *f_out, void *stream)
+{
+    return rcg::launch_rhs<float, true>(sys, E, y, action, f_out, stream);
+}
+
+int rcg_state_dyn(const rcg_system_t *sys, int64_t E, const double *state, const double *action, double *dstate,
+                  void *stream)
+{
+    return rcg::launch_rhs<double, false>(sys, E, state, const_cast<double *>(action), dstate, stream);
+}
+
+int rcg_rk45_step(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E, double *y, double *f, double *t,
+                  double *h_abs, int32_t *status, int32_t *nfev, double *action, void *stream)
+{
+    return rcg::launch_rk45<double, false>("rcg_rk45_step", sys, sol, nullptr, E, y, f, t, h_abs, status, nfev, nullptr,
+                                           action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, stream);
+}
+
+int rcg_rk45_step_f32(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E, float *y, float *f, double *t,
+                      double *h_abs, int32_t *status, int32_t *nfev, float *action, void *stream)
+{
+    return rcg::launch_rk45<float, false>("rcg_rk45_step_f32", sys, sol, nullptr, E, y, f, t, h_abs, status, nfev,
+                                          nullptr, action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, stream);
+}
+
+int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,
+                     double *y, double *f, double *t, double *h_abs, int32_t *status, int32_t *nfev, int32_t *nsteps,
+                     double *action, double *ctrl_clock, double sampling_time, int32_t max_steps, double *state_sys,
+                     double *accum, int32_t *sample_flag, void *stream)
+{
+    return rcg::launch_rk45<double, true>("rcg_rk45_advance", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
+                                          action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
+                                          stream);
+}
+
+int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,
+                         float *y, float *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                         int32_t *nsteps, float *action, double *ctrl_clock, double sampling_time, int32_t max_steps,
+                         float *state_sys, float *accum, int32_t *sample_flag, void *stream)
+{
+    return rcg::launch_rk45<float, true>("rcg_rk45_advance_f32", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
+                                         action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
+                                         stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""Batched closed loop: E independent environments stepped by the fused kernels.
+
+This is the device-resident form of the reference's headless main loop
+(presets/main_3wrobot_NI.py:415-440) with ``_actor_optimizer`` replaced by
+enumerate-and-argmin over candidate action sequences: per control
+interval one ``rcg_rk45_advance`` launch (every lane integrates to its own next sampling
+event) and one ``rcg_actor_cost`` launch (E x C ``_actor_cost`` evaluations, per-env arg-min,
+action hand-over and ``upd_accum_obj``).  All state stays in HBM as ``[component, lane]``
+tensors; nothing returns to the host until results are requested.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _C, ops
+
+
+def _as_dev(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), dtype=dtype, device=device)
+
+
+class ClosedLoopEngine:
+    """Closed loop of ``Simulator`` + ``CtrlOptPred`` (MPC, or RQL/SQL with fixed critic weights)
+    for ``E`` environments with a candidate/arg-min actor.
+
+    Parameters mirror the reference objects: ``system`` is ``System.name``; ``pars`` /
+    ``ctrl_bnds`` as in ``System``; ``dt`` is both ``Simulator.dt`` (``max_step = dt/2``,
+    rcognita/simulator.py:150) and ``CtrlOptPred.sampling_time``; ``candidates`` is a shared
+    table ``[C, Nactor*m]`` (rows = action sequences like the reference's ``action_sqn``) or a
+    per-environment set ``[E, C, Nactor*m]``.
+    """
+
+    def __init__(self, system, state_init, candidates, *, pars=(), ctrl_bnds=None, mode="MPC", Nactor=6, dt=0.01,
+                 pred_step_size=None, t0=0.0, t1=10.0, first_step=1e-6, atol=1e-5, rtol=1e-3, gamma=1.0, R1=None,
+                 R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
+                 w_critic=None, action_init=(), device=None, dtype=torch.float64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = dtype
+        self.sysd = _C.make_system(system, pars, ctrl_bnds)
+        self.n, self.m = _C.SYS_DIMS[self.sysd.sys_id]
+        n, m = self.n, self.m
+        self.sampling_time = float(dt)
+        self.t0, self.t1 = float(t0), float(t1)
+        self.first_step = float(first_step)
+        if first_step <= 0:
+            raise ValueError("`first_step` must be positive.")            # scipy common.py:10-16
+        if first_step > abs(t1 - t0):
+            raise ValueError("`first_step` exceeds bounds.")
+        self.sol = _C.make_solver(t1, dt / 2, rtol, atol)
+        self.obj = _C.make_objective(n, m, mode=mode, Nactor=Nactor,
+                                     pred_step_size=dt if pred_step_size is None else pred_step_size, gamma=gamma,
+                                     critic_struct=critic_struct, stage_obj_struct=stage_obj_struct, R1=R1, R2=R2,
+                                     observation_target=observation_target)
+        with torch.cuda.device(self.device):
+            x0 = _as_dev(state_init, dtype, self.device)
+            if x0.dim() == 1:
+                x0 = x0[None, :]
+            if x0.shape[1] != n:
+                raise ValueError(f"state_init must be [E, {n}]")
+            self.E = E = x0.shape[0]
+            self.y0 = x0.t().contiguous()                                  # [n, E]
+            L = Nactor * m
+            cand = _as_dev(candidates, dtype, self.device)
+            if cand.dim() == 2:
+                if cand.shape[1] != L:
+                    raise ValueError(f"candidates must be [C, {L}]")
+                self.C = cand.shape[0]
+                self.cand_per_env = False
+                self.cand = cand.t().contiguous()                          # [L, C]
+            elif cand.dim() == 3:
+                if cand.shape[0] != E or cand.shape[2] != L:
+                    raise ValueError(f"candidates must be [E, C, {L}]")
+                self.C = cand.shape[1]
+                self.cand_per_env = True
+                self.cand = cand.permute(2, 0, 1).reshape(L, E * self.C).contiguous()   # [L, E*C]
+            else:
+                raise ValueError("candidates must be [C, N*m] or [E, C, N*m]")
+            if mode != "MPC":
+                if w_critic is None:
+                    raise ValueError("w_critic is required for RQL/SQL")
+                w = _as_dev(w_critic, dtype, self.device)
+                dimc = _C.dim_critic(critic_struct, n, m)
+                if w.dim() == 1:
+                    self.w, self.w_per_env = w.contiguous(), False
+                else:
+                    self.w, self.w_per_env = w.t().contiguous(), True      # [E, dimc] -> [dimc, E]
+                assert self.w.shape[0] == dimc
+            else:
+                self.w, self.w_per_env = None, False
+            lo = np.array([self.sysd.lo[k] for k in range(m)])
+            a0 = lo / 10 if len(action_init) == 0 else np.asarray(action_init, dtype=np.float64).reshape(m)
+            self.action_init = _as_dev(a0, dtype, self.device)             # controllers.py:973-978
+            self._alloc()
+            self.reset()
+
+    def _alloc(self):
+        n, m, E, dt, dev = self.n, self.m, self.E, self.dtype, self.device
+        self.y = torch.empty((n, E), dtype=dt, device=dev)
+        self.f = torch.empty((n, E), dtype=dt, device=dev)
+        self.state_sys = torch.empty((n, E), dtype=dt, device=dev)
+        self.action = torch.empty((m, E), dtype=dt, device=dev)
+        self.t = torch.empty((E,), dtype=torch.float64, device=dev)
+        self.h_abs = torch.empty((E,), dtype=torch.float64, device=dev)
+        self.ctrl_clock = torch.empty((E,), dtype=torch.float64, device=dev)
+        self.accum = torch.empty((E,), dtype=dt, device=dev)
+        self.status = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.nfev = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.nsteps = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.nsamples = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.sample_flag = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.argmin = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.Jmin = torch.empty((E,), dtype=dt, device=dev)
+
+    def reset(self):
+        """Documented intent of ``Simulator.reset`` + ``CtrlOptPred.reset``: restore y0, t0,
+        f(t0, y0) with zero action, h_abs = first_step, clocks and accumulators."""
+        self.y.copy_(self.y0)
+        self.state_sys.copy_(self.y0)
+        self.action.zero_()                                # System.action = zeros (systems.py:134)
+        self.t.fill_(self.t0)
+        self.h_abs.fill_(self.first_step)
+        self.ctrl_clock.fill_(self.t0)
+        self.accum.zero_()
+        self.status.fill_(_C.RUNNING)
+        self.nfev.fill_(1)
+        self.nsteps.zero_()
+        self.nsamples.zero_()
+        self.sample_flag.zero_()
+        self.argmin.fill_(-1)
+        self.Jmin.fill_(float("nan"))
+        ops.rhs(self.sysd, self.y, self.action, out=self.f)               # RK45.__init__: f = fun(t0, y0)
+        self.intervals = 0
+        self._first_done = False
+
+    # -- the very first solver step runs with System.action = 0; only afterwards does the
+    #    system receive the controller's initial action (main_3wrobot_NI.py:417-424).
+    def _first_step(self):
+        ops.rk45_step(self.sysd, self.sol, self.y, self.f, self.t, self.h_abs, self.status, self.action, nfev=self.nfev)
+        self.nsteps += 1
+        flag = (self.t - self.ctrl_clock >= self.sampling_time).to(torch.int32)
+        self.sample_flag.copy_(flag)
+        self.action.copy_(self.action_init[:, None].expand(self.m, self.E))
+        hold = torch.empty((self.E,), dtype=self.dtype, device=self.device)
+        if self.dtype == torch.float64:
+            ops.stage_obj(self.obj, self.n, self.m, self.y, self.action, out=hold)
+        else:
+            hold = ops.stage_obj(self.obj, self.n, self.m, self.y.double(), self.action.double()).to(self.dtype)
+        self.accum += hold * self.sampling_time * (1 - flag).to(self.dtype)
+        if bool(flag.any()):
+            self.ctrl_clock.copy_(torch.where(flag.bool(), self.t, self.ctrl_clock))
+            self._actor()                                   # state_sys is still y0 here
+        self.state_sys.copy_(self.y)
+        self._first_done = True
+
+    def _actor(self):
+        ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
+                       w_critic=self.w, w_per_env=self.w_per_env, mask=self.sample_flag, want_J=False,
+                       argmin_out=self.argmin, Jmin_out=self.Jmin, action_out=self.action, accum=self.accum,
+                       sampling_time=self.sampling_time)
+        self.nsamples += self.sample_flag
+
+    def run_interval(self, max_steps=1 << 30):
+        """One control interval for every running lane: advance to the next sampling event,
+        evaluate all candidates, pick the arg-min action."""
+        if not self._first_done:
+            self._first_step()
+        ops.rk45_advance(self.sysd, self.sol, self.obj, self.y, self.f, self.t, self.h_abs, self.status, self.action,
+                         self.ctrl_clock, self.sampling_time, max_steps, state_sys=self.state_sys, accum=self.accum,
+                         sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps)
+        self._actor()
+        self.intervals += 1
+
+    def all_done(self) -> bool:
+        return not bool((self.status == _C.RUNNING).any())
+
+    def run(self, max_intervals=None, check_every=32):
+        """Run until every lane is finished/failed (or ``max_intervals``). Returns intervals run."""
+        k = 0
+        while max_intervals is None or k < max_intervals:
+            self.run_interval()
+            k += 1
+            if k % check_every == 0 and self.all_done():
+                break
+        if max_intervals is None:
+            while not self.all_done():
+                self.run_interval()
+                k += 1
+        return k
+
+    def results(self):
+        """Host copies in the reference's row layout: y [E,n], action [E,m], etc."""
+        return {
+            "y": self.y.t().contiguous().cpu().numpy(), "t": self.t.cpu().numpy(),
+            "action": self.action.t().contiguous().cpu().numpy(), "accum": self.accum.cpu().numpy(),
+            "status": self.status.cpu().numpy(), "nfev": self.nfev.cpu().numpy(),
+            "nsteps": self.nsteps.cpu().numpy(), "nsamples": self.nsamples.cpu().numpy(),
+            "argmin": self.argmin.cpu().numpy(), "Jmin": self.Jmin.cpu().numpy(),
+        }

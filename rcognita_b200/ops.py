@@ -1,0 +1,170 @@
+"""Tensor-level launchers: CUDA tensors in struct-of-arrays layout -> ``librcg_b200.so``.
+
+Layout: a per-lane vector quantity of dimension d is a contiguous ``[d, E]`` tensor
+(component-major).  PyTorch only provides device memory and the stream; all arithmetic
+happens in the library's hand-written sm_100a kernels.  No fallback exists: non-CUDA
+tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _C
+
+_F64, _F32, _I32 = torch.float64, torch.float32, torch.int32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, shape=None, name="tensor", optional=False):
+    if t is None:
+        if optional:
+            return C.c_void_p(0)
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (rcognita_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _suffix(dtype):
+    if dtype == _F64:
+        return ""
+    if dtype == _F32:
+        return "_f32"
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def rhs(sysd, y, action, out=None):
+    """``System.closed_loop_rhs``: clips ``action`` [m,E] in place, returns f [n,E]."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = y.shape[1]
+    out = torch.empty_like(y) if out is None else out
+    fn = getattr(_C.lib, "rcg_rhs" + _suffix(y.dtype))
+    _C.check(fn(C.byref(sysd), E, _ptr(y, None, (n, E), "y"), _ptr(action, y.dtype, (m, E), "action"),
+                _ptr(out, y.dtype, (n, E), "out"), _stream()), "rcg_rhs")
+    return out
+
+
+def state_dyn(sysd, state, action, out=None):
+    """``System._state_dyn`` (no clipping)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = state.shape[1]
+    out = torch.empty_like(state) if out is None else out
+    _C.check(_C.lib.rcg_state_dyn(C.byref(sysd), E, _ptr(state, _F64, (n, E), "state"),
+                                  _ptr(action, _F64, (m, E), "action"), _ptr(out, _F64, (n, E), "out"), _stream()),
+             "rcg_state_dyn")
+    return out
+
+
+def rk45_step(sysd, sol, y, f, t, h_abs, status, action, nfev=None):
+    """``Simulator.sim_step``: one accepted RK45 step per running lane, in place."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = y.shape[1]
+    fn = getattr(_C.lib, "rcg_rk45_step" + _suffix(y.dtype))
+    _C.check(fn(C.byref(sysd), C.byref(sol), E, _ptr(y, None, (n, E), "y"), _ptr(f, y.dtype, (n, E), "f"),
+                _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),
+                _ptr(nfev, _I32, (E,), "nfev", optional=True), _ptr(action, y.dtype, (m, E), "action"), _stream()),
+             "rcg_rk45_step")
+
+
+def rk45_advance(sysd, sol, obj, y, f, t, h_abs, status, action, ctrl_clock, sampling_time, max_steps,
+                 state_sys=None, accum=None, sample_flag=None, nfev=None, nsteps=None):
+    """Fused loop body between two controller samples (see ``rcg_rk45_advance`` in rcg.h)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = y.shape[1]
+    dt = y.dtype
+    fn = getattr(_C.lib, "rcg_rk45_advance" + _suffix(dt))
+    _C.check(fn(C.byref(sysd), C.byref(sol), C.byref(obj), E, _ptr(y, None, (n, E), "y"), _ptr(f, dt, (n, E), "f"),
+                _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),
+                _ptr(nfev, _I32, (E,), "nfev", optional=True), _ptr(nsteps, _I32, (E,), "nsteps", optional=True),
+                _ptr(action, dt, (m, E), "action"), _ptr(ctrl_clock, _F64, (E,), "ctrl_clock"),
+                float(sampling_time), int(max_steps), _ptr(state_sys, dt, (n, E), "state_sys", optional=True),
+                _ptr(accum, dt, (E,), "accum", optional=True), _ptr(sample_flag, _I32, (E,), "sample_flag", optional=True),
+                _stream()), "rcg_rk45_advance")
+
+
+def actor_cost(sysd, obj, state_sys, obs, cand, cand_per_env, C_, w_critic=None, w_per_env=False, mask=None,
+               want_J=True, J_out=None, argmin_out=None, Jmin_out=None, action_out=None, accum=None,
+               sampling_time=0.0):
+    """``CtrlOptPred._actor_cost`` over E x C candidates + per-env ``np.argmin``.
+
+    ``cand``: ``[N*m, C]`` (shared) or ``[N*m, E*C]`` (per env, element (k,j,e,c) at column e*C+c).
+    Returns ``(J [E,C] or None, argmin [E] int32, Jmin [E])``.
+    """
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = obs.shape[1]
+    dt = obs.dtype
+    L = obj.Nactor * m
+    ncol = E * C_ if cand_per_env else C_
+    if want_J and J_out is None:
+        J_out = torch.empty((E, C_), dtype=dt, device=obs.device)
+    if argmin_out is None:
+        argmin_out = torch.full((E,), -1, dtype=_I32, device=obs.device)
+    if Jmin_out is None:
+        Jmin_out = torch.full((E,), float("nan"), dtype=dt, device=obs.device)
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    wshape = None if w_critic is None else ((dimc, E) if w_per_env else (dimc,))
+    fn = getattr(_C.lib, "rcg_actor_cost" + _suffix(dt))
+    _C.check(fn(C.byref(sysd), C.byref(obj), E, int(C_), _ptr(state_sys, dt, (n, E), "state_sys"),
+                _ptr(obs, dt, (n, E), "obs"), _ptr(cand, dt, (L, ncol), "cand"), int(bool(cand_per_env)),
+                _ptr(w_critic, dt, wshape, "w_critic", optional=True), int(bool(w_per_env)),
+                _ptr(mask, _I32, (E,), "mask", optional=True),
+                _ptr(J_out, dt, (E, C_), "J_out", optional=True), _ptr(argmin_out, _I32, (E,), "argmin_out"),
+                _ptr(Jmin_out, dt, (E,), "Jmin_out"), _ptr(action_out, dt, (m, E), "action_out", optional=True),
+                _ptr(accum, dt, (E,), "accum", optional=True), float(sampling_time), _stream()), "rcg_actor_cost")
+    return J_out, argmin_out, Jmin_out
+
+
+def stage_obj(obj, n, m, obs, act, out=None, accum=None, scale=0.0, want_out=True):
+    """``CtrlOptPred.stage_obj`` (+ fused ``upd_accum_obj`` when ``accum`` is given)."""
+    E = obs.shape[1]
+    if want_out and out is None:
+        out = torch.empty((E,), dtype=_F64, device=obs.device)
+    _C.check(_C.lib.rcg_stage_obj(C.byref(obj), n, m, E, _ptr(obs, _F64, (n, E), "obs"), _ptr(act, _F64, (m, E), "act"),
+                                  _ptr(out, _F64, (E,), "out", optional=True),
+                                  _ptr(accum, _F64, (E,), "accum", optional=True), float(scale), _stream()),
+             "rcg_stage_obj")
+    return out
+
+
+def critic(obj, n, m, obs, act, w, w_per_env=False, out=None):
+    """``CtrlOptPred._critic``."""
+    E = obs.shape[1]
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    out = torch.empty((E,), dtype=_F64, device=obs.device) if out is None else out
+    _C.check(_C.lib.rcg_critic(C.byref(obj), n, m, E, _ptr(obs, _F64, (n, E), "obs"), _ptr(act, _F64, (m, E), "act"),
+                               _ptr(w, _F64, (dimc, E) if w_per_env else (dimc,), "w"), int(bool(w_per_env)),
+                               _ptr(out, _F64, (E,), "out"), _stream()), "rcg_critic")
+    return out
+
+
+def critic_cost(obj, n, m, obs_buf, act_buf, w, w_prev, out=None):
+    """``CtrlOptPred._critic_cost`` for W weight vectors per env: ``w`` [dimc, E, W] -> Jc [E, W]."""
+    L, _, E = obs_buf.shape
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    W = w.shape[2]
+    out = torch.empty((E, W), dtype=_F64, device=obs_buf.device) if out is None else out
+    _C.check(_C.lib.rcg_critic_cost(C.byref(obj), n, m, E, W, _ptr(obs_buf, _F64, (L, n, E), "obs_buf"),
+                                    _ptr(act_buf, _F64, (L, m, E), "act_buf"), _ptr(w, _F64, (dimc, E, W), "w"),
+                                    _ptr(w_prev, _F64, (dimc, E), "w_prev"), _ptr(out, _F64, (E, W), "out"), _stream()),
+             "rcg_critic_cost")
+    return out
+
+
+def push_buffers(n, m, obs_buf, act_buf, obs, act, mask=None):
+    """``utilities.push_vec`` on the controller FIFO buffers for the masked lanes."""
+    L, _, E = obs_buf.shape
+    _C.check(_C.lib.rcg_push_buffers(n, m, L, E, _ptr(obs_buf, _F64, (L, n, E), "obs_buf"),
+                                     _ptr(act_buf, _F64, (L, m, E), "act_buf"), _ptr(obs, _F64, (n, E), "obs"),
+                                     _ptr(act, _F64, (m, E), "act"), _ptr(mask, _I32, (E,), "mask", optional=True),
+                                     _stream()), "rcg_push_buffers")
