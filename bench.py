@@ -1,0 +1,331 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of rcognita's hot path on B200 (and of its CPU restatement).
+
+Workload (BASELINE.json configs[1]): 3wrobot_NI, MPC, Nactor=6, dt=0.01; 65,536 environments
+PER GPU x 256 candidate action sequences per environment, RK45 closed loop.  One bench "step"
+= one control interval of the whole batch: `rcg_rk45_advance` integrates every environment
+to its next controller sample (scipy-faithful RK45, ~2-3 accepted steps) and `rcg_actor_cost`
+evaluates E x C `_actor_cost` rollouts, takes the per-environment arg-min and hands the action
+over.  `value` = `_actor_cost` evaluations per second over the whole closed loop (all GPUs),
+`env_steps_per_s` the accepted RK45 steps per second of the same timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA)
+    python bench.py --impl reference ...                           # CPU arm: the oracle port, all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SYSTEM = "3wrobotNI"
+BNDS = [[-25.0, 25.0], [-5.0, 5.0]]
+R1_DIAG = [1.0, 10.0, 1.0, 0.0, 0.0]
+DT = 0.01
+ACTION_INIT = [-2.5, -0.5]
+METRIC = "closed-loop actor-cost evals/s (+ env-steps/s), 3wrobot_NI MPC Nactor=6"
+BYTES_PER_EVAL_PER_ENV_CAND = lambda N, m: N * m * 8 + 8      # candidate read + J (folded into arg-min) -- DESIGN.md
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--cands", type=int, default=256)
+    ap.add_argument("--nactor", type=int, default=6)
+    ap.add_argument("--shared-cands", action="store_true", help="one shared candidate table instead of per-env sets")
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="environments in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    kind = "shared candidate table" if args.shared_cands else "per-env candidates"
+    return (f"3wrobot_NI MPC Nactor={args.nactor} dt={DT}: {args.envs} envs/GPU x {args.cands} candidate action "
+            f"sequences ({kind}), RK45 closed loop")
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_start=None, t_end=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if t_start is not None and not (t_start - 0.05 <= ts <= t_end + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms (oracle port)
+
+def cpu_closed_loop(args, sample_envs, steps, warmup, budget_s=None):
+    """Times the CPU restatement of the same closed loop (oracle/, C + OpenMP on all host threads)
+    on a bounded sample of the workload: `sample_envs` environments with the same distributions.
+    Returns (evals/s, env-steps/s, ms/step, threads, steps run)."""
+    import oracle
+    from bench_workload import make_workload
+    x0, cand = make_workload(args, 0, sample_envs)
+    s = oracle.make_sys(SYSTEM, [], BNDS)
+    c = oracle.make_ctrl(3, 2, mode="MPC", Nactor=args.nactor, pred_step_size=DT, R1=R1_DIAG)
+    t1 = max(10.0, (steps + warmup + 16) * 3 * DT)
+    batch = oracle.EnvBatch(c, s, x0, cand, ACTION_INIT, DT, 0.0, t1, DT / 2)
+    threads = oracle.num_threads()
+    for _ in range(warmup):
+        batch.interval()
+    tot_steps = tot_evals = done = 0
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        st, ev = batch.interval()
+        tot_steps += st; tot_evals += ev; done += 1
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    el = time.perf_counter() - t_begin
+    return tot_evals / el, tot_steps / el, 1e3 * el / done, threads, done
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the path (oracle port -- the reference is
+    pure Python and cannot travel to the GPU box) on all host threads, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.num_threads()
+    sample = args.cpu_sample_envs or 256 * threads
+    evals_s, steps_s, ms, threads, done = cpu_closed_loop(args, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": evals_s, "unit": "evals/s", "env_steps_per_s": steps_s,
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "t1": 10.0},
+        "cpu_baseline": {"value": evals_s, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {args.envs} envs x {args.cands} candidates, one control interval per step "
+                                   f"(oracle/rcg_oracle.c, OpenMP)"},
+        "e2e": {"value": evals_s, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import rcognita_b200
+    from rcognita_b200 import shard
+    from rcognita_b200.engine import ClosedLoopEngine
+    from bench_workload import make_workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rcognita_b200 has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    K, W = args.steps, max(args.warmup, 3)
+    E, C, N = args.envs, args.cands, args.nactor
+    lo, hi = shard.shard_range(E * world, rank, world)
+    x0, cand = make_workload(args, lo, hi)
+    t1 = max(10.0, (2 * (K + W) + 32) * 3 * DT)             # long enough that no lane finishes mid-bench
+    eng = ClosedLoopEngine(SYSTEM, x0, cand, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
+                           action_init=ACTION_INIT, device=dev)
+    del cand
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident closed loop: warm-up, then exactly K timed steps
+    for _ in range(W):
+        eng.run_interval()
+    barrier()
+    steps0, samples0 = int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0.0)
+    barrier()
+    rcognita_b200.reset_launch_count()
+    eng.actor_events = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(K):
+        eng.run_interval()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = rcognita_b200.launch_count()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_total = ev0.elapsed_time(ev1)
+    actor_ms = [a.elapsed_time(b) for a, b in eng.actor_events]
+    eng.actor_events = None
+    d_steps = int(eng.nsteps.sum().item()) - steps0
+    d_evals = (int(eng.nsamples.sum().item()) - samples0) * C
+
+    red = torch.tensor([ms_total, float(np.mean(actor_ms))], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([d_steps, d_evals, launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    # end-of-run collectives (the only ones on the path): gather per-env returns, sum the counters
+    returns, cnt = shard.gather_returns(eng.accum, cnt)
+    ms_total, actor_ms_avg = float(red[0].item()), float(red[1].item())
+    tot_steps, tot_evals, tot_launches = (int(v) for v in cnt.tolist())
+    value = tot_evals / (ms_total * 1e-3)
+    steps_per_s = tot_steps / (ms_total * 1e-3)
+
+    # ---- end to end: lane state owned by the HOST (pinned), copied in and out every step
+    e2e = None
+    if not args.no_e2e:
+        host = eng.make_host_state()
+        for _ in range(3):
+            eng.run_interval_host(host)
+        barrier()
+        s0 = int(host["nsamples"].sum().item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            h2d, d2h = eng.run_interval_host(host)
+        e1.record()
+        barrier()
+        ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ev_e2e = torch.tensor([(int(host["nsamples"].sum().item()) - s0) * C], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ev_e2e, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(ev_e2e.item()) / (float(ms_e2e.item()) * 1e-3), "unit": "evals/s",
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "ms_per_step": float(ms_e2e.item()) / K,
+               "api": "ClosedLoopEngine.run_interval_host (pinned host lane state in/out every step; candidates resident)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (actor_cost_kernel), measured live with CUDA events
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    evals_per_launch = E * C                                   # per rank; every env samples in (almost) every interval
+    evals_per_launch = d_evals / max(1, K)
+    bytes_per_eval = (N * 2 * 8 + 8) if not args.shared_cands else 8
+    achieved = evals_per_launch * bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "actor_cost_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
+                "kernel_ms_avg": actor_ms_avg, "kernel_share_of_step": actor_ms_avg * K / ms_total,
+                "kernel_evals_per_s": evals_per_launch / (actor_ms_avg * 1e-3)}
+    prof = os.path.join(ROOT, "profiles", "actor_cost_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as fh:
+                roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        threads = oracle.num_threads()
+        sample = args.cpu_sample_envs or 256 * threads
+        ev_s, st_s, ms, threads, done = cpu_closed_loop(args, sample, 400, 3, budget_s=15.0)
+        cpu = {"value": ev_s, "unit": "evals/s", "cores": threads, "kind": "port", "env_steps_per_s": st_s,
+               "sample": f"{sample} of {E} envs x {C} candidates, {done} control intervals "
+                         f"(oracle/rcg_oracle.c, C + OpenMP, {threads} threads)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "env_steps_per_s": steps_per_s, "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "envs_total": E * world, "candidates": C, "Nactor": N, "t1": t1,
+                   "l2": f"per-launch candidate stream {E * C * N * 2 * 8 / 1e9:.2f} GB > 126 MB L2 (no flush needed)"
+                         if not args.shared_cands else "shared table: cache-resident by design",
+                   "sharding": f"{world} x contiguous env blocks, no per-step communication"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": tot_launches, "roofline": roofline, "cpu_baseline": cpu,
+        "mean_return_so_far": float(returns.mean().item()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.envs % 1024:
+        raise SystemExit("--envs must be a multiple of 1024")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

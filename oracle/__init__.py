@@ -54,6 +54,13 @@ class Rk45T(C.Structure):
                 ("status", C.c_int), ("nfev", C.c_long)]
 
 
+class EnvT(C.Structure):
+    _fields_ = [("r", Rk45T), ("sys_action", C.c_double * MAX_M), ("action_curr", C.c_double * MAX_M),
+                ("state_sys", C.c_double * MAX_N), ("ctrl_clock", C.c_double), ("accum", C.c_double),
+                ("Jbest", C.c_double), ("steps", C.c_int), ("samples", C.c_int), ("best", C.c_int),
+                ("done", C.c_int)]
+
+
 def build(force: bool = False) -> str:
     """Compile ``librcg_oracle.so`` (gcc; OpenMP if the toolchain has it)."""
     src = os.path.join(_HERE, "rcg_oracle.c")
@@ -102,6 +109,12 @@ def lib():
                                                             C.POINTER(C.c_long), dp, C.c_int, ip,
                                                             C.POINTER(C.c_longlong)])
         L.orc_closed_loop.restype = C.c_longlong
+        L.orc_env_init.argtypes = [C.POINTER(EnvT), C.POINTER(SysT), C.c_int, dp, dp] + [C.c_double] * 6
+        L.orc_env_init.restype = None
+        L.orc_env_interval.argtypes = [C.POINTER(EnvT), C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, C.c_int, dp,
+                                       C.c_int, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_longlong)]
+        L.orc_env_interval.restype = C.c_longlong
+        L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
 
@@ -297,3 +310,53 @@ def closed_loop(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_
         traj.ctypes.data_as(dp) if traj_cap > 0 else _null(), int(traj_cap), C.byref(rows), C.byref(evals))
     return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfev": nfe,
             "traj": traj[: rows.value], "total_steps": int(total), "total_evals": int(evals.value)}
+
+
+def num_threads() -> int:
+    """Threads the OpenMP loops of the oracle will use (1 without OpenMP)."""
+    return int(lib().orc_num_threads())
+
+
+class EnvBatch:
+    """E resumable closed-loop environments (``orc_env_t``): ``interval()`` advances every live
+    environment up to and including its next controller sample, like one
+    ``ClosedLoopEngine.run_interval`` of the product -- used interval by interval in tests and as
+    the timed unit of bench.py's CPU arms."""
+
+    def __init__(self, c, s, state_init, cand, action_init, sampling_time, t0, t1, max_step, first_step=1e-6,
+                 rtol=1e-3, atol=1e-5, w_critic=None):
+        self.c, self.s = c, s
+        self.x0, x0p = _d(np.atleast_2d(state_init))
+        self.E = self.x0.shape[0]
+        self.cand, self._cp = _d(cand)
+        self.per_env = int(self.cand.ndim == 3)
+        self.C = self.cand.shape[-2]
+        ai, aip = _d(np.atleast_1d(action_init))
+        self.w, self._wp = (None, _null()) if w_critic is None else _d(w_critic)
+        self.sampling_time, self.t1 = float(sampling_time), float(t1)
+        self.envs = (EnvT * self.E)()
+        lib().orc_env_init(self.envs, C.byref(s), self.E, x0p, aip, t0, t1, max_step, first_step, rtol, atol)
+
+    def interval(self, nthreads=0):
+        """Returns (accepted solver steps, _actor_cost evaluations) of this interval."""
+        ev = C.c_longlong(0)
+        steps = lib().orc_env_interval(self.envs, C.byref(self.c), C.byref(self.s), self.E, self.C, self._cp,
+                                       self.per_env, self._wp, self.sampling_time, self.t1, int(nthreads),
+                                       C.byref(ev))
+        return int(steps), int(ev.value)
+
+    def snapshot(self):
+        n, m = self.s.n, self.s.m
+        v = self.envs
+        return {
+            "t": np.array([v[e].r.t for e in range(self.E)]),
+            "y": np.array([[v[e].r.y[i] for i in range(n)] for e in range(self.E)]),
+            "action": np.array([[v[e].action_curr[j] for j in range(m)] for e in range(self.E)]),
+            "accum": np.array([v[e].accum for e in range(self.E)]),
+            "argmin": np.array([v[e].best for e in range(self.E)], dtype=np.int32),
+            "Jmin": np.array([v[e].Jbest for e in range(self.E)]),
+            "nsteps": np.array([v[e].steps for e in range(self.E)], dtype=np.int32),
+            "nsamples": np.array([v[e].samples for e in range(self.E)], dtype=np.int32),
+            "nfev": np.array([v[e].r.nfev for e in range(self.E)], dtype=np.int64),
+            "done": np.array([v[e].done for e in range(self.E)], dtype=np.int32),
+        }

@@ -339,9 +339,106 @@ void orc_actor_cost_table(const orc_ctrl_t *c, const orc_sys_t *s, int C, const 
     if (argmin_out) *argmin_out = orc_argmin(J_out, C);
 }
 
-/* ref: presets/main_3wrobot_NI.py:415-440 (headless loop) + controllers.py:1429-1493
- * (compute_action, MPC / fixed-critic RQL,SQL) + :1056 receive_sys_state + :1086 upd_accum_obj,
- * with _actor_optimizer replaced by enumerate-and-argmin. */
+/* ------------------------------------------------- resumable per-environment closed loop */
+
+/* Construction of the reference objects for one environment: Simulator.__init__
+ * (ref: rcognita/simulator.py:150 -> RK45 ctor with System.action = zeros, systems.py:134) and
+ * CtrlOptPred.__init__ (action_curr = action_init, ctrl_clock = t0, controllers.py:973-990). */
+void orc_env_init(orc_env_t *envs, const orc_sys_t *s, int E, const double *state_init,
+                  const double *action_init, double t0, double t1, double max_step, double first_step,
+                  double rtol, double atol)
+{
+    for (int e = 0; e < E; ++e) {
+        orc_env_t *v = envs + e;
+        memset(v, 0, sizeof(*v));
+        for (int j = 0; j < s->m; ++j) v->action_curr[j] = action_init[j];
+        for (int i = 0; i < s->n; ++i) v->state_sys[i] = state_init[(long)e * s->n + i];
+        orc_rk45_init(&v->r, s, state_init + (long)e * s->n, v->sys_action, t0, t1, max_step, first_step, rtol, atol);
+        v->ctrl_clock = t0;
+        v->best = -1;
+        v->Jbest = NAN;
+    }
+}
+
+/* ONE iteration of the headless main loop for one environment.
+ * ref: presets/main_3wrobot_NI.py:415-440 + controllers.py:1429-1493 (compute_action, MPC /
+ * fixed-critic RQL,SQL) + :1056 receive_sys_state + :1086 upd_accum_obj, with
+ * _actor_optimizer replaced by enumerate-and-argmin.
+ * Returns 1 if the controller sampled in this iteration, 0 if it held, -1 if the env is done. */
+static int env_iterate(orc_env_t *v, const orc_ctrl_t *c, const orc_sys_t *s, int C, const double *tab,
+                       const double *w_critic, double sampling_time, double t1)
+{
+    const int n = s->n, m = s->m, L = c->Nactor * m;
+    int sampled = 0;
+    double Jtab[4096];
+    if (v->done) return -1;
+    if (orc_rk45_step(&v->r, s, v->sys_action) != 0) { v->done = 1; return -1; }   /* sim_step */
+    ++v->steps;
+    const double t = v->r.t;
+    const double *obs = v->r.y;                                /* out() = identity            */
+    if (t - v->ctrl_clock >= sampling_time) {                  /* controllers.py:1440-1442    */
+        v->ctrl_clock = t;
+        for (int i0 = 0; i0 < C; i0 += 4096) {
+            int cnt = C - i0 < 4096 ? C - i0 : 4096;
+            int bi;
+            orc_actor_cost_table(c, s, cnt, tab + (long)i0 * L, obs, v->state_sys, w_critic, Jtab, &bi);
+            /* strict '<' keeps the first minimum across chunks; NaN wins once */
+            if (i0 == 0 || (!isnan(v->Jbest) && (isnan(Jtab[bi]) || Jtab[bi] < v->Jbest))) {
+                v->Jbest = Jtab[bi];
+                v->best = i0 + bi;
+            }
+        }
+        for (int j = 0; j < m; ++j) v->action_curr[j] = tab[(long)v->best * L + j];
+        ++v->samples;
+        sampled = 1;
+    }
+    for (int j = 0; j < m; ++j) v->sys_action[j] = v->action_curr[j];     /* receive_action       */
+    for (int i = 0; i < n; ++i) v->state_sys[i] = v->r.y[i];              /* receive_sys_state    */
+    v->accum += orc_stage_obj(c, n, m, obs, v->action_curr) * sampling_time;   /* upd_accum_obj   */
+    if (t >= t1) v->done = 1;                                  /* main_3wrobot_NI.py:440      */
+    return sampled;
+}
+
+/* Every environment that is not done iterates the main loop up to and including its next
+ * controller sample (or its end).  Returns the accepted solver steps taken; *evals (may be
+ * NULL) receives the number of _actor_cost evaluations. */
+long long orc_env_interval(orc_env_t *envs, const orc_ctrl_t *c, const orc_sys_t *s, int E, int C,
+                           const double *cand, int cand_per_env, const double *w_critic,
+                           double sampling_time, double t1, int nthreads, long long *evals_out)
+{
+    const int L = c->Nactor * s->m;
+    long long total_steps = 0, evals = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total_steps, evals)
+    for (int e = 0; e < E; ++e) {
+        orc_env_t *v = envs + e;
+        const double *tab = cand_per_env ? cand + (long)e * C * L : cand;
+        for (;;) {
+            int rc = env_iterate(v, c, s, C, tab, w_critic, sampling_time, t1);
+            if (rc < 0) break;
+            ++total_steps;
+            if (rc == 1) { evals += C; break; }
+            if (v->done) break;
+        }
+    }
+    if (evals_out) *evals_out = evals;
+    return total_steps;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* Whole episodes (the closed loop above run to t1) for E environments, OpenMP-parallel. */
 long long orc_closed_loop(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *state_init,
                           int C, const double *cand, int cand_per_env, const double *w_critic,
                           const double *action_init, double sampling_time,
@@ -359,60 +456,32 @@ long long orc_closed_loop(const orc_ctrl_t *c, const orc_sys_t *s, int E, const 
 #endif
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_steps, evals)
     for (int e = 0; e < E; ++e) {
-        orc_rk45_t r;
-        double sys_action[ORC_MAX_M] = {0, 0};          /* System.action = zeros, systems.py:134 */
-        double action_curr[ORC_MAX_M], state_sys[ORC_MAX_N];
-        double ctrl_clock = t0, acc = 0.0;
-        int steps = 0, samples = 0, best = -1;
-        double Jbest = NAN;
-        double Jtab[4096];
+        orc_env_t v;
         const double *tab = cand_per_env ? cand + (long)e * C * L : cand;
-        for (int j = 0; j < m; ++j) action_curr[j] = action_init[j];
-        for (int i = 0; i < n; ++i) state_sys[i] = state_init[(long)e * n + i];
-        orc_rk45_init(&r, s, state_init + (long)e * n, sys_action, t0, t1, max_step, first_step, rtol, atol);
-        while (steps < max_steps_per_env) {
-            if (orc_rk45_step(&r, s, sys_action) != 0) break;     /* sim_step                    */
-            ++steps;
-            const double t = r.t;
-            const double *obs = r.y;                               /* out() = identity            */
-            if (t - ctrl_clock >= sampling_time) {                 /* controllers.py:1440-1442    */
-                ctrl_clock = t;
-                for (int i0 = 0; i0 < C; i0 += 4096) {
-                    int cnt = C - i0 < 4096 ? C - i0 : 4096;
-                    int bi;
-                    orc_actor_cost_table(c, s, cnt, tab + (long)i0 * L, obs, state_sys, w_critic, Jtab, &bi);
-                    /* strict '<' keeps the first minimum across chunks; NaN wins once */
-                    if (i0 == 0 || (!isnan(Jbest) && (isnan(Jtab[bi]) || Jtab[bi] < Jbest))) {
-                        Jbest = Jtab[bi];
-                        best = i0 + bi;
-                    }
-                }
-                for (int j = 0; j < m; ++j) action_curr[j] = tab[(long)best * L + j];
-                ++samples;
-                evals += C;
+        orc_env_init(&v, s, 1, state_init + (long)e * n, action_init, t0, t1, max_step, first_step, rtol, atol);
+        while (v.steps < max_steps_per_env) {
+            int rc = env_iterate(&v, c, s, C, tab, w_critic, sampling_time, t1);
+            if (rc < 0) break;
+            if (rc == 1) evals += C;
+            if (e == 0 && traj && v.steps <= traj_cap) {
+                double *row = traj + (long)(v.steps - 1) * (1 + n + m + 3);
+                row[0] = v.r.t;
+                for (int i = 0; i < n; ++i) row[1 + i] = v.r.y[i];
+                for (int j = 0; j < m; ++j) row[1 + n + j] = v.action_curr[j];
+                row[1 + n + m] = v.accum;
+                row[2 + n + m] = (double)v.best;
+                row[3 + n + m] = v.Jbest;
+                if (traj_rows) *traj_rows = v.steps;
             }
-            for (int j = 0; j < m; ++j) sys_action[j] = action_curr[j];   /* receive_action       */
-            for (int i = 0; i < n; ++i) state_sys[i] = r.y[i];            /* receive_sys_state    */
-            acc += orc_stage_obj(c, n, m, obs, action_curr) * sampling_time;   /* upd_accum_obj   */
-            if (e == 0 && traj && steps <= traj_cap) {
-                double *row = traj + (long)(steps - 1) * (1 + n + m + 3);
-                row[0] = t;
-                for (int i = 0; i < n; ++i) row[1 + i] = r.y[i];
-                for (int j = 0; j < m; ++j) row[1 + n + j] = action_curr[j];
-                row[1 + n + m] = acc;
-                row[2 + n + m] = (double)best;
-                row[3 + n + m] = Jbest;
-                if (traj_rows) *traj_rows = steps;
-            }
-            if (t >= t1) break;                                    /* main_3wrobot_NI.py:440      */
+            if (v.done) break;
         }
-        if (y_final) for (int i = 0; i < n; ++i) y_final[(long)e * n + i] = r.y[i];
-        if (t_final) t_final[e] = r.t;
-        if (accum) accum[e] = acc;
-        if (nsteps) nsteps[e] = steps;
-        if (nsamples) nsamples[e] = samples;
-        if (nfev) nfev[e] = r.nfev;
-        total_steps += steps;
+        if (y_final) for (int i = 0; i < n; ++i) y_final[(long)e * n + i] = v.r.y[i];
+        if (t_final) t_final[e] = v.r.t;
+        if (accum) accum[e] = v.accum;
+        if (nsteps) nsteps[e] = v.steps;
+        if (nsamples) nsamples[e] = v.samples;
+        if (nfev) nfev[e] = v.r.nfev;
+        total_steps += v.steps;
     }
     if (total_evals) *total_evals = evals;
     return total_steps;

@@ -67,6 +67,17 @@ typedef struct {
     long nfev;
 } orc_rk45_t;
 
+/* One environment of the headless closed loop (presets/main_3wrobot_NI.py:415-440): the solver,
+ * System.action, and the CtrlOptPred fields the loop mutates. */
+typedef struct {
+    orc_rk45_t r;
+    double sys_action[ORC_MAX_M];   /* System.action (clipped in place by closed_loop_rhs) */
+    double action_curr[ORC_MAX_M];  /* CtrlOptPred.action_curr                              */
+    double state_sys[ORC_MAX_N];    /* CtrlOptPred.state_sys (one solver step behind)       */
+    double ctrl_clock, accum, Jbest;
+    int steps, samples, best, done;
+} orc_env_t;
+
 int    orc_dim_critic(int critic_struct, int n, int m);
 void   orc_state_dyn(const orc_sys_t *s, const double *state, const double *action, double *dstate);
 void   orc_closed_loop_rhs(const orc_sys_t *s, const double *y, double *action, double *rhs);
@@ -100,6 +111,17 @@ long long orc_closed_loop(const orc_ctrl_t *c, const orc_sys_t *s, int E, const 
                           double *y_final, double *t_final, double *accum, int *nsteps,
                           int *nsamples, long *nfev, double *traj, int traj_cap, int *traj_rows,
                           long long *total_evals);
+
+/* Resumable form of the same loop (bench cpu_baseline / reference arm, interval-level tests):
+ * orc_env_init builds E environments; orc_env_interval advances every live environment up to
+ * and including its next controller sample. */
+void      orc_env_init(orc_env_t *envs, const orc_sys_t *s, int E, const double *state_init,
+                       const double *action_init, double t0, double t1, double max_step, double first_step,
+                       double rtol, double atol);
+long long orc_env_interval(orc_env_t *envs, const orc_ctrl_t *c, const orc_sys_t *s, int E, int C,
+                           const double *cand, int cand_per_env, const double *w_critic,
+                           double sampling_time, double t1, int nthreads, long long *evals_out);
+int       orc_num_threads(void);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,7 @@ class ClosedLoopEngine:
         ops.rhs(self.sysd, self.y, self.action, out=self.f)               # RK45.__init__: f = fun(t0, y0)
         self.intervals = 0
         self._first_done = False
+        self.actor_events = None        # set to a list to record (start, end) CUDA events per actor launch
 
     # -- the very first solver step runs with System.action = 0; only afterwards does the
     #    system receive the controller's initial action (main_3wrobot_NI.py:417-424).
@@ -158,11 +159,21 @@ class ClosedLoopEngine:
         self._first_done = True
 
     def _actor(self):
+        ev = None
+        if self.actor_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        self._actor_launch()
+        if ev is not None:
+            ev[1].record()
+            self.actor_events.append(ev)
+        self.nsamples += self.sample_flag
+
+    def _actor_launch(self):
         ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
                        w_critic=self.w, w_per_env=self.w_per_env, mask=self.sample_flag, want_J=False,
                        argmin_out=self.argmin, Jmin_out=self.Jmin, action_out=self.action, accum=self.accum,
                        sampling_time=self.sampling_time)
-        self.nsamples += self.sample_flag
 
     def run_interval(self, max_steps=1 << 30):
         """One control interval for every running lane: advance to the next sampling event,
@@ -201,3 +212,30 @@ class ClosedLoopEngine:
             "nsteps": self.nsteps.cpu().numpy(), "nsamples": self.nsamples.cpu().numpy(),
             "argmin": self.argmin.cpu().numpy(), "Jmin": self.Jmin.cpu().numpy(),
         }
+
+
+    # -- host-buffer form of one control interval: the lane state lives in PINNED HOST memory
+    #    between calls (a caller that owns its environments on the host, like the reference's
+    #    Python loop does); every call copies it in, runs the two kernels and copies it back.
+    LANE_FIELDS = ("y", "f", "t", "h_abs", "status", "action", "ctrl_clock", "state_sys", "accum")
+    RESULT_FIELDS = ("argmin", "Jmin", "sample_flag", "nsteps", "nfev", "nsamples")
+
+    def make_host_state(self):
+        """Pinned host mirrors of the lane state (initialised from the current device state)."""
+        if not self._first_done:
+            self._first_step()
+        return {k: getattr(self, k).cpu().pin_memory() for k in self.LANE_FIELDS + self.RESULT_FIELDS}
+
+    def run_interval_host(self, host):
+        """H2D lane state -> rk45_advance + actor_cost -> D2H lane state and results; returns the
+        bytes moved (h2d, d2h).  Synchronises: the host buffers are valid on return."""
+        h2d = d2h = 0
+        for k in self.LANE_FIELDS:
+            getattr(self, k).copy_(host[k], non_blocking=True)
+            h2d += host[k].numel() * host[k].element_size()
+        self.run_interval()
+        for k in self.LANE_FIELDS + self.RESULT_FIELDS:
+            host[k].copy_(getattr(self, k), non_blocking=True)
+            d2h += host[k].numel() * host[k].element_size()
+        torch.cuda.current_stream().synchronize()
+        return h2d, d2h

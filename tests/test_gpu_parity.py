@@ -1,0 +1,490 @@
+"""GPU parity tests: librcg_b200.so (through its C ABI / the torch launchers) against the CPU
+oracle and the committed live-reference golden vectors.
+
+Tolerances (BASELINE.json north_star): _actor_cost / _critic_cost 1e-9 relative in fp64;
+RK45 closed-loop trajectories 1e-6 relative (we assert 1e-9, and exact step times / counts);
+arg-min indices bit-exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from golden_util import DIMS, PRESET, load, mixed_err, rel_err  # noqa: E402
+
+COST_RTOL = 1e-9
+SYSTEMS = ["3wrobotNI", "3wrobot", "2tank"]
+X0 = {"3wrobotNI": [5, 5, -3 * np.pi / 4], "3wrobot": [5, 5, -3 * np.pi / 4, 0.3, -0.2], "2tank": [2, -2]}
+
+
+@pytest.fixture(scope="module")
+def rb():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    import rcognita_b200
+    from rcognita_b200 import _C, ops
+    torch.cuda.set_device(0)
+    return rcognita_b200, _C, ops
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return load("functions.json")
+
+
+def dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda", dtype=dtype or torch.float64)
+
+
+def soa(rows):
+    """[E, d] row layout (reference) -> [d, E] component-major device tensor."""
+    return dev(np.asarray(rows, dtype=np.float64).T.copy())
+
+
+def random_states(name, E, seed=0):
+    rng = np.random.default_rng(seed)
+    if name == "3wrobotNI":
+        return np.stack([rng.uniform(-10, 10, E), rng.uniform(-10, 10, E), rng.uniform(-np.pi, np.pi, E)], 1)
+    if name == "3wrobot":
+        return np.stack([rng.uniform(-10, 10, E), rng.uniform(-10, 10, E), rng.uniform(-np.pi, np.pi, E),
+                         rng.uniform(-1, 1, E), rng.uniform(-1, 1, E)], 1)
+    return np.stack([rng.uniform(-2, 2, E), rng.uniform(-2, 2, E)], 1)
+
+
+def random_cands(name, shape_prefix, N, seed=1):
+    b = np.array(PRESET[name]["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+    return np.random.default_rng(seed).uniform(lo, hi, size=tuple(shape_prefix) + (N * b.shape[0],))
+
+
+# ------------------------------------------------------------------ function level vs golden
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_state_dyn_and_rhs_golden(rb, fn, name):
+    _, _C, ops = rb
+    d = fn[name]
+    sysd = _C.make_system(name, d["pars"], d["bnds"])
+    cases = d["cases"]["state_dyn"]
+    out = ops.state_dyn(sysd, soa([c["state"] for c in cases]), soa([c["action"] for c in cases]))
+    assert rel_err(out.T.cpu().numpy(), [c["out"] for c in cases]) <= 1e-14
+    cases = d["cases"]["closed_loop_rhs"]
+    act = soa([c["action"] for c in cases])
+    out = ops.rhs(sysd, soa([c["state"] for c in cases]), act)
+    assert rel_err(out.T.cpu().numpy(), [c["out"] for c in cases]) <= 1e-14
+    assert np.array_equal(act.T.cpu().numpy(), np.array([c["action_clipped"] for c in cases]))   # in-place clip
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_stage_obj_critic_golden(rb, fn, name):
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    for c in fn[name]["cases"]["stage_obj"]:
+        obj = _C.make_objective(n, m, R1=c["R1"], R2=c["R2"], stage_obj_struct=c["struct"], observation_target=c["target"])
+        got = ops.stage_obj(obj, n, m, soa([c["obs"]]), soa([c["act"]])).item()
+        assert rel_err(got, c["out"]) <= COST_RTOL
+    for c in fn[name]["cases"]["critic"]:
+        obj = _C.make_objective(n, m, critic_struct=c["critic_struct"], observation_target=c["target"])
+        assert _C.dim_critic(c["critic_struct"], n, m) == c["dim_critic"]
+        got = ops.critic(obj, n, m, soa([c["obs"]]), soa([c["act"]]), dev(c["w"])).item()
+        assert rel_err(got, c["out"]) <= COST_RTOL
+        got = ops.critic(obj, n, m, soa([c["obs"]] * 3), soa([c["act"]] * 3), soa([c["w"]] * 3), w_per_env=True)
+        assert rel_err(got.cpu().numpy(), [c["out"]] * 3) <= COST_RTOL
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_critic_cost_golden(rb, fn, name):
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    for c in fn[name]["cases"]["critic_cost"]:
+        obj = _C.make_objective(n, m, mode="RQL", critic_struct=c["critic_struct"], gamma=c["gamma"], Ncritic=4,
+                                buffer_size=10, R1=c["R1_diag"], observation_target=c["target"])
+        E, W = 3, 2
+        ob = dev(np.repeat(np.asarray(c["obs_buf"])[:, :, None], E, axis=2))          # [L, n, E]
+        ab = dev(np.repeat(np.asarray(c["act_buf"])[:, :, None], E, axis=2))
+        w = dev(np.broadcast_to(np.asarray(c["w"])[:, None, None], (len(c["w"]), E, W)).copy())
+        wp = dev(np.repeat(np.asarray(c["w_prev"])[:, None], E, axis=1))
+        got = ops.critic_cost(obj, n, m, ob, ab, w, wp).cpu().numpy()
+        assert rel_err(got, np.full((E, W), c["out"])) <= COST_RTOL
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+@pytest.mark.parametrize("per_env", [False, True])
+def test_actor_cost_golden(rb, fn, name, per_env):
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    d = fn[name]
+    sysd = _C.make_system(name, d["pars"], d["bnds"])
+    for c in d["cases"]["actor_cost"]:
+        obj = _C.make_objective(n, m, mode=c["mode"], Nactor=c["N"], pred_step_size=c["pred_step"], gamma=c["gamma"],
+                                critic_struct=c["critic_struct"], R1=c["R1"], observation_target=c["target"])
+        cand = np.asarray(c["cand"])                                                  # [C, N*m]
+        C_ = cand.shape[0]
+        E = 2 if per_env else 1
+        if per_env:
+            cdev = dev(np.tile(cand.T[:, None, :], (1, E, 1)).reshape(cand.shape[1], E * C_))
+        else:
+            cdev = dev(cand.T.copy())
+        w = None if c["w"] is None else dev(c["w"])
+        J, am, Jmin = ops.actor_cost(sysd, obj, soa([c["state_sys"]] * E), soa([c["obs"]] * E), cdev, per_env, C_,
+                                     w_critic=w)
+        J = J.cpu().numpy()
+        for e in range(E):
+            assert rel_err(J[e], c["J"]) <= COST_RTOL, (c["mode"], c["critic_struct"], c["N"])
+            assert int(am[e]) == c["argmin"]
+            assert J[e, 4] == J[e, 1]                                                # duplicated candidate: exact tie
+            assert Jmin[e].item() == J[e, c["argmin"]]
+
+
+# ------------------------------------------------------------------ vs the oracle, seeded random lanes
+
+@pytest.mark.parametrize("name,mode,cs,N", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6), ("3wrobotNI", "RQL", "quad-lin", 5), ("3wrobotNI", "SQL", "quad-mix", 7),
+    ("3wrobot", "RQL", "quadratic", 10), ("3wrobot", "SQL", "quad-nomix", 4), ("3wrobot", "MPC", "quad-nomix", 12),
+    ("2tank", "SQL", "quad-nomix", 8), ("2tank", "RQL", "quad-mix", 3), ("2tank", "MPC", "quad-nomix", 1),
+])
+@pytest.mark.parametrize("C_,per_env,w_per_env", [(256, False, False), (48, True, True), (1000, False, True), (7, True, False)])
+def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E = 37
+    gamma = 0.95
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    R1 = np.diag(p["R1_diag"]).astype(float)
+    if cs == "quad-mix":                                     # also exercise a dense R1
+        R1 = R1 + 0.01 * np.arange((n + m) ** 2).reshape(n + m, n + m)
+    kw = dict(mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], gamma=gamma, critic_struct=cs, R1=R1,
+              observation_target=p["target"])
+    obj = _C.make_objective(n, m, **kw)
+    s = oracle.make_sys(name, p["pars"], p["bnds"])
+    c = oracle.make_ctrl(n, m, **kw)
+    obs = random_states(name, E, 3)
+    xs = obs + 0.01 * np.random.default_rng(4).normal(size=obs.shape)
+    cand = random_cands(name, (E, C_) if per_env else (C_,), N, 5)
+    dimc = _C.dim_critic(cs, n, m)
+    w = np.random.default_rng(6).uniform(0, 2, size=(E, dimc) if w_per_env else (dimc,))
+    mask = np.ones(E, dtype=np.int32)
+    mask[5] = 0
+    mask[E - 1] = 0
+    if per_env:
+        cdev = dev(np.transpose(cand, (2, 0, 1)).reshape(N * m, E * C_))
+    else:
+        cdev = dev(cand.T.copy())
+    action_out = torch.full((m, E), -777.0, device="cuda", dtype=torch.float64)
+    accum = torch.full((E,), 0.5, device="cuda", dtype=torch.float64)
+    J, am, Jmin = ops.actor_cost(sysd, obj, soa(xs), soa(obs), cdev, per_env, C_,
+                                 w_critic=dev(w.T.copy() if w_per_env else w), w_per_env=w_per_env,
+                                 mask=dev(mask, torch.int32), action_out=action_out, accum=accum, sampling_time=0.01)
+    J, am, Jmin = J.cpu().numpy(), am.cpu().numpy(), Jmin.cpu().numpy()
+    action_out, accum = action_out.T.cpu().numpy(), accum.cpu().numpy()
+    for e in range(E):
+        if not mask[e]:
+            assert am[e] == -1 and np.isnan(Jmin[e]) and np.all(action_out[e] == -777.0) and accum[e] == 0.5
+            continue
+        tab = cand[e] if per_env else cand
+        Jr, ar = oracle.actor_cost_table(c, s, tab, obs[e], xs[e], w[e] if w_per_env else w)
+        assert rel_err(J[e], Jr) <= COST_RTOL
+        assert am[e] == int(np.argmin(J[e]))                 # bit-exact arg-min of the GPU's own costs
+        if am[e] != ar:                                      # oracle may differ only on a sub-tolerance near-tie
+            assert abs(Jr[am[e]] - Jr[ar]) <= COST_RTOL * abs(Jr[ar])
+        assert Jmin[e] == J[e, am[e]]
+        assert np.array_equal(action_out[e], tab[am[e], :m])
+        assert rel_err(accum[e], 0.5 + oracle.stage_obj(c, n, m, obs[e], tab[am[e], :m]) * 0.01) <= COST_RTOL
+
+
+def test_argmin_ties_and_nan(rb):
+    """np.argmin semantics: first minimum wins; NaN counts as minimal (first NaN wins)."""
+    _, _C, ops = rb
+    p = PRESET["3wrobotNI"]
+    sysd = _C.make_system("3wrobotNI", p["pars"], p["bnds"])
+    N, C_ = 6, 700
+    obj = _C.make_objective(3, 2, mode="MPC", Nactor=N, pred_step_size=0.01, R1=p["R1_diag"])
+    base = random_cands("3wrobotNI", (1,), N, 9)[0]
+    cand = np.tile(base, (C_, 1))
+    # R1 puts zero weight on actions and a[N-1] never enters the dynamics: candidates differing only
+    # in the last action tie EXACTLY -> index 0 must win.
+    cand[:, -2:] = np.random.default_rng(2).uniform(-1, 1, size=(C_, 2))
+    x = soa([X0["3wrobotNI"]])
+    J, am, _ = ops.actor_cost(sysd, obj, x, x, dev(cand.T.copy()), False, C_)
+    assert np.unique(J.cpu().numpy()).size == 1 and int(am[0]) == 0
+    cand2 = random_cands("3wrobotNI", (C_,), N, 10)
+    cand2[300:, :] = cand2[299, :]                       # the minimum's duplicates come later
+    J, am, _ = ops.actor_cost(sysd, obj, x, x, dev(cand2.T.copy()), False, C_)
+    assert int(am[0]) == int(np.argmin(J.cpu().numpy()[0]))
+    cand3 = cand2.copy()
+    cand3[613, 0] = np.nan
+    cand3[401, 2] = np.nan
+    J, am, Jmin = ops.actor_cost(sysd, obj, x, x, dev(cand3.T.copy()), False, C_)
+    assert int(am[0]) == 401 and np.isnan(Jmin[0].item())
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_critic_cost_vs_oracle(rb, name):
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E, W, L = 19, 5, 10
+    rng = np.random.default_rng(11)
+    for cs in ["quad-lin", "quadratic", "quad-nomix", "quad-mix"]:
+        kw = dict(mode="RQL", critic_struct=cs, gamma=0.9, Ncritic=4, buffer_size=L, R1=p["R1_diag"],
+                  observation_target=p["target"])
+        obj = _C.make_objective(n, m, **kw)
+        c = oracle.make_ctrl(n, m, **kw)
+        dimc = _C.dim_critic(cs, n, m)
+        ob = rng.normal(size=(E, L, n)); ab = rng.uniform(-1, 1, size=(E, L, m))
+        w = rng.uniform(0, 3, size=(E, W, dimc)); wp = rng.uniform(0, 3, size=(E, dimc))
+        got = ops.critic_cost(obj, n, m, dev(np.transpose(ob, (1, 2, 0)).copy()), dev(np.transpose(ab, (1, 2, 0)).copy()),
+                              dev(np.transpose(w, (2, 0, 1)).copy()), dev(wp.T.copy())).cpu().numpy()
+        for e in range(E):
+            for k in range(W):
+                assert rel_err(got[e, k], oracle.critic_cost(c, n, m, ob[e], ab[e], w[e, k], wp[e])) <= COST_RTOL
+
+
+def test_push_buffers(rb):
+    _, _C, ops = rb
+    n, m, L, E = 3, 2, 10, 9
+    rng = np.random.default_rng(0)
+    ob = rng.normal(size=(L, n, E)); ab = rng.normal(size=(L, m, E))
+    o = rng.normal(size=(n, E)); a = rng.normal(size=(m, E))
+    mask = (np.arange(E) % 3 != 0).astype(np.int32)
+    obd, abd = dev(ob), dev(ab)
+    ops.push_buffers(n, m, obd, abd, dev(o), dev(a), dev(mask, torch.int32))
+    exp_o = ob.copy(); exp_a = ab.copy()
+    for e in range(E):
+        if mask[e]:                                                # utilities.push_vec
+            exp_o[:, :, e] = np.vstack([ob[1:, :, e], o[:, e]])
+            exp_a[:, :, e] = np.vstack([ab[1:, :, e], a[:, e]])
+    assert np.array_equal(obd.cpu().numpy(), exp_o) and np.array_equal(abd.cpu().numpy(), exp_a)
+
+
+# ------------------------------------------------------------------ RK45 integrator
+
+def _sim_state(ops, _C, sysd, x0_rows, t0=0.0, first_step=1e-6):
+    E = len(x0_rows)
+    y = soa(x0_rows)
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    action = torch.zeros((m, E), device="cuda", dtype=torch.float64)
+    f = ops.rhs(sysd, y, action)
+    t = torch.full((E,), t0, device="cuda", dtype=torch.float64)
+    h = torch.full((E,), first_step, device="cuda", dtype=torch.float64)
+    status = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    nfev = torch.ones((E,), device="cuda", dtype=torch.int32)
+    return y, f, t, h, status, nfev, action
+
+
+@pytest.mark.parametrize("key", ["3wrobotNI:inbounds", "3wrobotNI:outofbounds", "3wrobot:inbounds",
+                                 "3wrobot:outofbounds", "2tank:inbounds", "2tank:outofbounds"])
+def test_rk45_step_golden_traces(rb, key):
+    """SURVEY.md App. A.3 protocol against the live reference's recorded solver traces, with 33
+    identical lanes (a full warp + 1): every lane must reproduce t, y, f, h_abs and nfev per step."""
+    _, _C, ops = rb
+    g = load("integrator.json")[key]
+    name = g["system"]
+    n, m = DIMS[name]
+    d = PRESET[name]
+    E = 33
+    sysd = _C.make_system(name, d["pars"], d["bnds"])
+    sol = _C.make_solver(g["t1"], d["dt"] / 2)
+    y, f, t, h, status, nfev, action = _sim_state(ops, _C, sysd, [X0[name]] * E)
+    sched = np.array(g["sched"]); rows = np.array(g["rows"])
+    for k in range(1, len(rows) + 1):
+        ops.rk45_step(sysd, sol, y, f, t, h, status, action, nfev=nfev)
+        action.copy_(dev(sched[(k // 5) % 4])[:, None].expand(m, E))
+        ref = rows[k - 1]
+        tt = t.cpu().numpy()
+        assert np.all(tt == tt[0])
+        assert abs(tt[0] - ref[0]) <= 1e-13 * max(abs(ref[0]), 1e-6), (k, tt[0], ref[0])
+        yy = y.cpu().numpy(); ff = f.cpu().numpy()
+        assert np.all(yy == yy[:, :1]) and np.all(ff == ff[:, :1])
+        assert mixed_err(yy[:, 0], ref[1:1 + n], floor=1e-3) <= 1e-9, k
+        assert mixed_err(ff[:, 0], ref[1 + n:1 + 2 * n], floor=1e-3) <= 1e-9, k
+        assert rel_err(h.cpu().numpy()[0], ref[1 + 2 * n]) <= 1e-9, k
+        assert np.all(nfev.cpu().numpy() == int(ref[2 + 2 * n])), k
+    st = status.cpu().numpy()
+    assert np.all(st == {"running": 0, "finished": 1, "failed": 2}[g["status"]])
+    # stepping a finished lane is a no-op (scipy raises; the batched kernel skips non-running lanes)
+    y_before = y.clone()
+    ops.rk45_step(sysd, sol, y, f, t, h, status, action, nfev=nfev)
+    assert torch.equal(y, y_before)
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_rk45_step_vs_oracle_random_lanes(rb, name):
+    """Different lanes, lane-specific action jumps (-> lane-specific rejections): every lane must
+    match its own scalar oracle solver, including nfev and exact t."""
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    d = PRESET[name]
+    E, steps = 70, 60
+    x0 = random_states(name, E, 21)
+    sysd = _C.make_system(name, d["pars"], d["bnds"])
+    s = oracle.make_sys(name, d["pars"], d["bnds"])
+    t1 = d["dt"] * 12
+    sol = _C.make_solver(t1, d["dt"] / 2)
+    y, f, t, h, status, nfev, action = _sim_state(ops, _C, sysd, x0)
+    solvers = [oracle.RK45(s, x0[e], 0.0, t1, d["dt"] / 2) for e in range(E)]
+    b = np.array(d["bnds"], dtype=float)
+    rng = np.random.default_rng(22)
+    for k in range(steps):
+        ops.rk45_step(sysd, sol, y, f, t, h, status, action, nfev=nfev)
+        for r in solvers:
+            if r.status == "running":
+                r.step()
+        if k % 4 == 3:                                       # new (partly out-of-bounds) actions per lane
+            a = rng.uniform(1.5 * b[:, 0], 1.5 * b[:, 1], size=(E, m))
+            action.copy_(soa(a))
+            for e, r in enumerate(solvers):
+                r.receive_action(a[e])
+        tt, yy, hh, nn, ss = t.cpu().numpy(), y.cpu().numpy(), h.cpu().numpy(), nfev.cpu().numpy(), status.cpu().numpy()
+        for e, r in enumerate(solvers):
+            assert tt[e] == r.t, (k, e)
+            assert mixed_err(yy[:, e], r.y, floor=1e-3) <= 1e-9, (k, e)
+            assert rel_err(hh[e], r.h_abs) <= 1e-9
+            assert nn[e] == r.nfev
+            assert _C.STATUS_NAMES[int(ss[e])] == r.status
+    assert np.all(status.cpu().numpy() == _C.FINISHED)
+
+
+# ------------------------------------------------------------------ closed loop (engine)
+
+def _engine_for(g, name, x0_rows, cand, dtype=None):
+    from rcognita_b200.engine import ClosedLoopEngine
+    d = PRESET[name]
+    return ClosedLoopEngine(name, x0_rows, cand, pars=d["pars"], ctrl_bnds=d["bnds"], mode=g["mode"], Nactor=g["Nactor"],
+                            dt=d["dt"], pred_step_size=d["dt"] * d["psm"], t1=g["t1"], gamma=g["gamma"],
+                            R1=d["R1_diag"], observation_target=d["target"], critic_struct=g["critic_struct"],
+                            w_critic=g["w_fixed"], action_init=g["action_init"],
+                            dtype=dtype or torch.float64)
+
+
+@pytest.mark.parametrize("key", ["NI_MPC_N6", "NI_MPC_N6_x1", "3wrobot_RQL_N10", "2tank_SQL_N8"])
+def test_closed_loop_golden(rb, key):
+    """the live reference's closed loop with its own _actor_cost on a candidate
+    table + np.argmin, vs the fused GPU loop (rk45_advance + actor_cost), sampled at every
+    controller sample: t, state, picked index, J_min; and the episode totals."""
+    _, _C, ops = rb
+    g = load("closed_loop.json")[key]
+    name = g["system"]
+    n, m = DIMS[name]
+    rows = np.array(g["rows"]); picks = np.array(g["picks"])
+    E = 5
+    eng = _engine_for(g, name, [g["x0"]] * E, np.array(g["cand"]))
+    sampled_rows = rows[rows[:, -1] > 0]
+    k = 0
+    while not eng.all_done():
+        eng.run_interval()
+        fl = eng.sample_flag.cpu().numpy()
+        assert np.all(fl == fl[0])
+        if fl[0]:
+            ref = sampled_rows[k]
+            assert np.all(eng.t.cpu().numpy() == ref[0]) or abs(eng.t[0].item() - ref[0]) <= 1e-15 * g["t1"]
+            yy = eng.y.cpu().numpy()
+            assert np.all(yy == yy[:, :1])
+            assert mixed_err(yy[:, 0], ref[1:1 + n], floor=1e-2) <= 1e-9, k
+            assert np.all(eng.argmin.cpu().numpy() == int(picks[k, 0])), k
+            assert rel_err(eng.Jmin.cpu().numpy(), np.full(E, picks[k, 1])) <= COST_RTOL
+            assert np.array_equal(eng.action.cpu().numpy()[:, 0], ref[1 + n:1 + n + m])
+            assert rel_err(eng.accum[0].item(), ref[1 + n + m]) <= 1e-9
+            k += 1
+    res = eng.results()
+    assert k == len(picks)
+    assert np.all(res["nsteps"] == len(rows)) and np.all(res["nsamples"] == len(picks)) and np.all(res["nfev"] == g["nfev"])
+    assert mixed_err(res["y"][0], rows[-1, 1:1 + n], floor=1e-2) <= 1e-9
+    assert rel_err(res["accum"], np.full(E, rows[-1, 1 + n + m])) <= 1e-9
+    assert np.all(res["status"] == _C.FINISHED)
+
+
+@pytest.mark.parametrize("name,mode,cs,N,t1,per_env", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 0.5, True), ("3wrobotNI", "MPC", "quad-nomix", 6, 0.5, False),
+    ("3wrobot", "RQL", "quadratic", 10, 0.3, False), ("2tank", "SQL", "quad-nomix", 8, 5.0, True),
+])
+def test_closed_loop_vs_oracle_many_envs(rb, name, mode, cs, N, t1, per_env):
+    """Different environments desynchronise (lane-specific sampling events, rejections): every
+    env must match its own scalar oracle episode: exact step/sample counts and final time,
+    state and accumulated objective to 1e-9."""
+    _, _C, ops = rb
+    from rcognita_b200.engine import ClosedLoopEngine
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E, C_ = 200, 64
+    x0 = random_states(name, E, 31)
+    cand = random_cands(name, (E, C_) if per_env else (C_,), N, 32)
+    dimc = _C.dim_critic(cs, n, m)
+    w = None if mode == "MPC" else np.random.default_rng(33).uniform(0, 2, size=dimc)
+    b = np.array(p["bnds"], dtype=float)
+    a0 = b[:, 0] / 10 if name != "2tank" else np.array([0.5])
+    eng = ClosedLoopEngine(name, x0, cand, pars=p["pars"], ctrl_bnds=p["bnds"], mode=mode, Nactor=N, dt=p["dt"],
+                           pred_step_size=p["dt"] * p["psm"], t1=t1, R1=p["R1_diag"], observation_target=p["target"],
+                           critic_struct=cs, w_critic=w, action_init=a0)
+    eng.run()
+    got = eng.results()
+    s = oracle.make_sys(name, p["pars"], p["bnds"])
+    c = oracle.make_ctrl(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], critic_struct=cs, R1=p["R1_diag"],
+                         observation_target=p["target"])
+    ref = oracle.closed_loop(c, s, x0, cand, a0, p["dt"], 0.0, t1, p["dt"] / 2, w_critic=w)
+    assert np.array_equal(got["nsteps"], ref["nsteps"])
+    assert np.array_equal(got["nsamples"], ref["nsamples"])
+    assert np.array_equal(got["nfev"], ref["nfev"])
+    assert np.array_equal(got["t"], ref["t"])
+    assert mixed_err(got["y"], ref["y"], floor=1e-2) <= 1e-9
+    assert rel_err(got["accum"], ref["accum"]) <= 1e-9
+    assert np.all(got["status"] == _C.FINISHED)
+
+
+def test_lane_permutation_and_batch_size_invariance(rb):
+    """No cross-environment arithmetic: permuting lanes permutes results bit-exactly, and a lane run
+    alone (E=1) gives the same bits as inside a big batch (the basis of shard-count invariance)."""
+    _, _C, ops = rb
+    from rcognita_b200.engine import ClosedLoopEngine
+    name, N, C_, E = "3wrobotNI", 6, 256, 4096 + 17
+    p = PRESET[name]
+    x0 = random_states(name, E, 41)
+    cand = random_cands(name, (C_,), N, 42)
+    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=0.01, t1=0.15, R1=p["R1_diag"])
+    a = ClosedLoopEngine(name, x0, cand, **kw); a.run(); ra = a.results()
+    perm = np.random.default_rng(43).permutation(E)
+    b = ClosedLoopEngine(name, x0[perm], cand, **kw); b.run(); rb_ = b.results()
+    for k in ("y", "t", "accum", "nsteps", "nsamples", "argmin", "Jmin"):
+        assert np.array_equal(ra[k][perm], rb_[k], equal_nan=True), k
+    one = ClosedLoopEngine(name, x0[1234:1235], cand, **kw); one.run(); r1 = one.results()
+    for k in ("y", "t", "accum", "nsteps", "nsamples", "argmin", "Jmin"):
+        assert np.array_equal(ra[k][1234:1235], r1[k], equal_nan=True), k
+
+
+def test_fp32_twin_tolerance(rb):
+    """_f32 kernels: costs within 2e-5 relative of the fp64 oracle; arg-min equal or a near-tie."""
+    _, _C, ops = rb
+    name, N, C_, E = "2tank", 8, 256, 64
+    n, m = DIMS[name]
+    p = PRESET[name]
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    kw = dict(mode="SQL", Nactor=N, pred_step_size=0.2, critic_struct="quad-nomix", R1=p["R1_diag"],
+              observation_target=p["target"])
+    obj = _C.make_objective(n, m, **kw)
+    s = oracle.make_sys(name, p["pars"], p["bnds"]); c = oracle.make_ctrl(n, m, **kw)
+    obs = random_states(name, E, 51); cand = random_cands(name, (C_,), N, 52); w = np.array([11.0, 11.0, 1.0])
+    f32 = torch.float32
+    J, am, Jmin = ops.actor_cost(sysd, obj, soa(obs).to(f32), soa(obs).to(f32), dev(cand.T.copy()).to(f32), False, C_,
+                                 w_critic=dev(w).to(f32))
+    J, am = J.cpu().numpy().astype(np.float64), am.cpu().numpy()
+    for e in range(E):
+        Jr, ar = oracle.actor_cost_table(c, s, cand, obs[e], obs[e], w)
+        assert rel_err(J[e], Jr) <= 2e-5
+        assert am[e] == ar or abs(Jr[am[e]] - Jr[ar]) <= 2e-5 * abs(Jr[ar])
+
+
+def test_errors_are_loud(rb):
+    rcognita_b200, _C, ops = rb
+    p = PRESET["3wrobotNI"]
+    sysd = _C.make_system("3wrobotNI", p["pars"], p["bnds"])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.state_dyn(sysd, torch.zeros((3, 4), dtype=torch.float64), torch.zeros((2, 4), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        _C.make_system("pendulum")
+    sol = _C.make_solver(1.0, -1.0)
+    y, f, t, h, status, nfev, action = _sim_state(ops, _C, sysd, [X0["3wrobotNI"]])
+    with pytest.raises(RuntimeError, match="max_step"):
+        ops.rk45_step(sysd, sol, y, f, t, h, status, action)
