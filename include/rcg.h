@@ -134,17 +134,17 @@ int rcg_rk45_step_f32(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t 
  * the last step (the one-step lag of receive_sys_state); the accumulated
  * objective of that step is left to rcg_actor_cost's epilogue, which knows the new action.
  * On non-sampling steps accum += stage_obj(y, action) * sampling_time (controllers.py:1093).
- * nsteps[E] (may be NULL) counts accepted steps. */
+ * nsteps[E] (may be NULL) counts accepted steps, nsamples[E] (may be NULL) sampling events. */
 int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
                      int64_t E, double *y, double *f, double *t, double *h_abs, int32_t *status,
                      int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
                      double sampling_time, int32_t max_steps, double *state_sys, double *accum,
-                     int32_t *sample_flag, void *stream);
+                     int32_t *sample_flag, int32_t *nsamples, void *stream);
 int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
                          int64_t E, float *y, float *f, double *t, double *h_abs, int32_t *status,
                          int32_t *nfev, int32_t *nsteps, float *action, double *ctrl_clock,
                          double sampling_time, int32_t max_steps, float *state_sys, float *accum,
-                         int32_t *sample_flag, void *stream);
+                         int32_t *sample_flag, int32_t *nsamples, void *stream);
 
 /* CtrlOptPred._actor_cost (rcognita/controllers.py:1273-1328) for E environments x C
  * candidate action sequences, one thread per (environment, candidate), plus np.argmin over
@@ -190,6 +190,13 @@ int rcg_critic(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, cons
 int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W,
                     const double *obs_buf, const double *act_buf, const double *w, const double *w_prev,
                     double *Jc_out, void *stream);
+
+/* The sampling-clock test of CtrlOptPred.compute_action (rcognita/controllers.py:1440-1442;
+ * the critic clock of :1459-1468 uses the same form): for every lane with in_mask != 0 (all
+ * lanes if in_mask is NULL) mask_out = (t - clock >= period) and clock = t where it fired;
+ * other lanes get mask_out = 0. */
+int rcg_ctrl_sample(int64_t E, const double *t, double *clock, double period, const int32_t *in_mask,
+                    int32_t *mask_out, void *stream);
 
 /* utilities.push_vec on the controller FIFO buffers for the lanes with mask != 0
  * (rcognita/controllers.py:1463-1464): rows shift up by one, the new row goes to the bottom. */

@@ -115,6 +115,10 @@ def lib():
                                        C.c_int, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_longlong)]
         L.orc_env_interval.restype = C.c_longlong
         L.orc_num_threads.restype = C.c_int
+        L.orc_sincos.argtypes = [C.c_double, dp, dp]
+        L.orc_sincos.restype = None
+        L.orc_pow_m02.argtypes = [C.c_double]
+        L.orc_pow_m02.restype = C.c_double
         _lib = L
     return _lib
 
@@ -310,6 +314,18 @@ def closed_loop(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_
         traj.ctypes.data_as(dp) if traj_cap > 0 else _null(), int(traj_cap), C.byref(rows), C.byref(evals))
     return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfev": nfe,
             "traj": traj[: rows.value], "total_steps": int(total), "total_evals": int(evals.value)}
+
+
+def sincos(x):
+    """The oracle's deterministic (sin, cos) -- the spec the CUDA fp64 path reproduces bit for bit."""
+    s, c = C.c_double(), C.c_double()
+    lib().orc_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def pow_m02(x):
+    """The oracle's correctly rounded x ** -0.2 (scipy rk.py:153, :162 ERROR_EXPONENT)."""
+    return lib().orc_pow_m02(float(x))
 
 
 def num_threads() -> int:

@@ -17,6 +17,80 @@
 #include <omp.h>
 #endif
 
+/* ------------------------------------------------- deterministic elementary functions
+ *
+ * The reference takes sin/cos from numpy (a SIMD kernel or libm, depending on the CPU) and
+ * err ** -0.2 from libm's pow; their last bits differ between libm builds, and through the
+ * adaptive step size they decide the bits of the solver time t, hence on which solver step the
+ * controller samples.  So that the CPU oracle and the CUDA kernels agree BIT FOR
+ * BIT (same accepted-step times, same sampling pattern, on every lane), both implement the SAME
+ * fully specified functions from IEEE +,-,*,fma only:
+ *
+ *  - orc_sincos: argument reduction by q = rint(x * 2/pi) with pi/2 split into three doubles,
+ *    carried out in double-double (head rh, tail rl), then the published fdlibm / FreeBSD msun
+ *    kernels k_sin.c / k_cos.c (Sun Microsystems, freely redistributable; < 1 ulp).
+ *  - orc_pow_m02: x ** -0.2 as libm pow() followed by one correction step from the
+ *    double-double residual y^5 * x - 1 (plus the term for 0.2 != 1/5 in binary): the correctly
+ *    rounded result independent of libm's last bits (up to astronomically rare hard cases),
+ *    which is also what glibc's pow returns in all but ~1e-5 of the calls.
+ *
+ * Both are pinned, like everything else here, by the live-reference golden vectors.
+ */
+static const double PIO2_1 = 1.5707963267948966e+00;   /* double(pi/2)                    */
+static const double PIO2_2 = 6.123233995736766e-17;    /* double(pi/2 - PIO2_1)           */
+static const double PIO2_3 = -1.4973849048591698e-33;  /* double(pi/2 - PIO2_1 - PIO2_2)  */
+static const double TWO_OVER_PI = 6.36619772367581382433e-01;
+
+void orc_sincos(double x, double *sn, double *cs)
+{
+    static const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                        S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                        S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    static const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                        C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                        C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    if (!(fabs(x) <= 1.0e5)) {           /* huge, inf, NaN: outside the regime of the path */
+        *sn = sin(x);
+        *cs = cos(x);
+        return;
+    }
+    const double q = rint(x * TWO_OVER_PI);
+    /* r = x - q*pi/2 in double-double */
+    const double ph = q * PIO2_1, pl = fma(q, PIO2_1, -ph);
+    const double r = x - ph;
+    double t = fma(-q, PIO2_2, -pl);
+    t = fma(-q, PIO2_3, t);
+    const double rh = r + t;
+    const double bb = rh - r;
+    const double rl = (r - (rh - bb)) + (t - bb);           /* two-sum */
+    /* kernels on [-pi/4, pi/4] */
+    const double z = rh * rh, w = z * z, v = z * rh;
+    const double ps = S2 + z * (S3 + z * S4) + z * w * (S5 + z * S6);
+    const double ks = rh - ((z * (0.5 * rl - v * ps) - rl) - v * S1);
+    const double pc = z * (C1 + z * (C2 + z * C3)) + (w * w) * (C4 + z * (C5 + z * C6));
+    const double hz = 0.5 * z, w1 = 1.0 - hz;
+    const double kc = w1 + (((1.0 - w1) - hz) + (z * pc - rh * rl));
+    switch (((long long)q) & 3) {
+    case 0:  *sn = ks;  *cs = kc;  break;
+    case 1:  *sn = kc;  *cs = -ks; break;
+    case 2:  *sn = -ks; *cs = -kc; break;
+    default: *sn = -kc; *cs = ks;  break;
+    }
+}
+
+double orc_pow_m02(double x)
+{
+    if (!(x > 0.0 && x < INFINITY)) return pow(x, -0.2);
+    const double y = pow(x, -0.2);
+    const double ah = y * y, al = fma(y, y, -ah);                       /* y^2          */
+    const double bh = ah * ah, bl = fma(ah, ah, -bh) + 2.0 * (ah * al); /* y^4          */
+    const double ch = bh * y, cl = fma(bh, y, -ch) + bl * y;            /* y^5          */
+    const double dh = ch * x, dl = fma(ch, x, -dh) + cl * x;            /* y^5 * x ~ 1  */
+    const double g = (dh - 1.0) + dl;
+    /* exponent is the double 0.2 = 1/5 + 1.1102230246251565e-17 */
+    return y + (-y) * (0.2 * g + 1.1102230246251565e-17 * log(x));
+}
+
 /* ------------------------------------------------------------------ systems */
 
 /* ref: rcognita/systems.py:308-323 (Sys3WRobot), :370-382 (Sys3WRobotNI),
@@ -25,15 +99,20 @@
 void orc_state_dyn(const orc_sys_t *s, const double *state, const double *action, double *d)
 {
     switch (s->sys_id) {
-    case ORC_SYS_3WROBOT_NI:
-        d[0] = action[0] * cos(state[2]);
-        d[1] = action[0] * sin(state[2]);
+    case ORC_SYS_3WROBOT_NI: {
+        double sn, cs;
+        orc_sincos(state[2], &sn, &cs);
+        d[0] = action[0] * cs;
+        d[1] = action[0] * sn;
         d[2] = action[1];
         break;
+    }
     case ORC_SYS_3WROBOT: {
         double m = s->pars[0], I = s->pars[1];
-        d[0] = state[3] * cos(state[2]);
-        d[1] = state[3] * sin(state[2]);
+        double sn, cs;
+        orc_sincos(state[2], &sn, &cs);
+        d[0] = state[3] * cs;
+        d[1] = state[3] * sn;
         d[2] = state[4];
         d[3] = 1 / m * action[0];      /* Python: (1/m) * F */
         d[4] = 1 / I * action[1];
@@ -163,12 +242,12 @@ int orc_rk45_step(orc_rk45_t *r, const orc_sys_t *s, double *action)
         if (err < 1) {                                     /* rk.py:149-160          */
             double factor;
             if (err == 0) factor = 10;
-            else factor = fmin(10, 0.9 * pow(err, -0.2));
+            else factor = fmin(10, 0.9 * orc_pow_m02(err));
             if (step_rejected) factor = fmin(1, factor);
             h_abs *= factor;
             break;
         } else {                                           /* rk.py:161-164          */
-            h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+            h_abs *= fmax(0.2, 0.9 * orc_pow_m02(err));
             step_rejected = 1;
         }
     }

@@ -78,6 +78,9 @@ typedef struct {
     int steps, samples, best, done;
 } orc_env_t;
 
+/* Deterministic sin/cos and x ** -0.2 shared (as a specification) with the CUDA kernels. */
+void   orc_sincos(double x, double *sn, double *cs);
+double orc_pow_m02(double x);
 int    orc_dim_critic(int critic_struct, int n, int m);
 void   orc_state_dyn(const orc_sys_t *s, const double *state, const double *action, double *dstate);
 void   orc_closed_loop_rhs(const orc_sys_t *s, const double *y, double *action, double *rhs);

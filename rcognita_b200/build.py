@@ -24,9 +24,11 @@ SOURCES = {
     "api.cu": [],
     "rk45.cu": ["-fmad=false"],
     "actor.cu": [],
+    "actor_ni_f64.cu": [], "actor_3w_f64.cu": [], "actor_2t_f64.cu": [],
+    "actor_ni_f32.cu": [], "actor_3w_f32.cu": [], "actor_2t_f32.cu": [],
     "critic.cu": ["-fmad=false"],
 }
-HEADERS = ["rcg_device.cuh", "rcg_host.h", os.path.join(INCLUDE, "rcg.h")]
+HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", os.path.join(INCLUDE, "rcg.h")]
 
 
 def _nvcc() -> str:
@@ -61,7 +63,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         return name, r
 
-    with ThreadPoolExecutor(max_workers=max(1, min(4, len(jobs)))) as ex:
+    with ThreadPoolExecutor(max_workers=max(1, min(os.cpu_count() or 4, len(jobs)))) as ex:
         for name, r in ex.map(run, jobs):
             if verbose or r.returncode != 0:
                 sys.stderr.write(f"--- nvcc {name}\n{r.stdout}{r.stderr}\n")
@@ -79,4 +81,4 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

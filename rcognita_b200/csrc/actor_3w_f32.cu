@@ -1,0 +1,6 @@
+// actor_3w_f32.cu -- instantiates the actor-cost kernels of actor_impl.cuh for one (system, dtype).
+#include "actor_impl.cuh"
+
+namespace rcg {
+int launch_actor_3w(const ActorLaunch<float> &L) { return launch_actor_sys<float, RCG_SYS_3WROBOT>(L); }
+}  // namespace rcg

@@ -1,0 +1,331 @@
+// actor_impl.cuh -- CtrlOptPred._actor_cost (rcognita/controllers.py:1273-1328) for E environments
+// x C candidate action sequences with a fused per-environment np.argmin.
+//
+// Mapping: one WARP per environment (or, for C < 32, one power-of-two lane segment per
+// environment).  Each lane evaluates candidates lane, lane+32, ... in order: the Euler rollout
+// state, the running cost and the whole action sequence of the candidate live in registers,
+// and the horizon runs in order inside the thread, so the cost is accumulated in the
+// reference's order (k = 0..Nactor-1).  Candidate components are read straight from HBM in
+// component-major order (consecutive lanes = consecutive candidates -> 256-byte coalesced
+// requests); with a compile-time horizon (NA > 0) all Nactor*m loads of a candidate are issued
+// before the first use.  The arg-min never leaves the warp: per-lane running best, then
+// lexicographic (J, index) xor-shuffles (first minimum wins, NaN counts as minimal, like
+// np.argmin) -- no shared memory, no block barrier.  Environment-uniform data (state_sys,
+// observation, critic weights, sin/cos of the initial heading) are loaded once per environment.
+//
+// Heading trigonometry of the two robots: the predictor needs sin/cos of theta_k for every
+// stage.  theta_{k+1} = theta_k + delta with delta = h * omega_k, so (sin, cos) are advanced by
+// the angle-addition formulas with a reduction-free polynomial sincos(delta) (|delta| <= pi/4,
+// the usual case: h = 0.01..0.02 s); otherwise a full sincos(theta_{k+1}).  Each rotation adds
+// <= 2 ulp, i.e. ~1e-15 over the longest horizon -- against the 1e-9 cost tolerance.
+#pragma once
+
+#include "rcg_host.h"
+
+namespace rcg {
+
+constexpr int kActorThreads = 256;
+constexpr int kActorWarps = kActorThreads / 32;
+
+// sin/cos on [-pi/4, pi/4] without range reduction (fdlibm __kernel_sin / __kernel_cos minimax
+// coefficients, |error| < 2^-57).  The coefficients sit in constant memory so that every DFMA
+// takes its coefficient as a c[bank][offset] operand (no immediate-materialising moves).
+static __constant__ double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+static __constant__ double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
+__device__ __forceinline__ void sincos_small(double x, double *s, double *c)
+{
+    const double z = x * x;
+    double ps = kSinC[0], pc = kCosC[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        ps = fma(ps, z, kSinC[i]);
+        pc = fma(pc, z, kCosC[i]);
+    }
+    *s = fma(x * z, ps, x);
+    *c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+
+static __device__ __noinline__ double2 sincos_full(double x)
+{
+    double2 r;
+    sincos(x, &r.x, &r.y);
+    return r;
+}
+
+// (s, c) = (sin, cos)(theta_old) on entry; (sin, cos)(theta_new) on exit, theta_new = theta_old + delta.
+__device__ __forceinline__ void rotate_trig(double theta_new, double delta, double &s, double &c)
+{
+    if (fabs(delta) <= 0.78539816339744830962) {
+        double sd, cd;
+        sincos_small(delta, &sd, &cd);
+        const double cn = fma(c, cd, -(s * sd));
+        const double sn = fma(s, cd, c * sd);
+        s = sn;
+        c = cn;
+    } else {
+        const double2 r = sincos_full(theta_new);   // also the NaN / inf path
+        s = r.x;
+        c = r.y;
+    }
+}
+__device__ __forceinline__ void rotate_trig(float theta_new, float, float &s, float &c) { sincosf(theta_new, &s, &c); }
+
+// One explicit-Euler predictor step, state += h * _state_dyn(state, a)  (controllers.py:1294 with
+// sys_rhs = System._state_dyn, unclipped).  (s, c) caches sin/cos of the heading state[2].
+template <typename T, int SYS>
+__device__ __forceinline__ void euler_step(const SysDev<T> &S, T h, T *x, const T *a, T &s, T &c)
+{
+    if constexpr (SYS == RCG_SYS_3WROBOT_NI) {           // systems.py:370-382
+        const T d = h * a[1];
+        x[0] = x[0] + h * (a[0] * c);
+        x[1] = x[1] + h * (a[0] * s);
+        x[2] = x[2] + d;
+        rotate_trig(x[2], d, s, c);
+    } else if constexpr (SYS == RCG_SYS_3WROBOT) {       // systems.py:308-323
+        const T d = h * x[4];
+        x[0] = x[0] + h * (x[3] * c);
+        x[1] = x[1] + h * (x[3] * s);
+        x[2] = x[2] + d;
+        x[3] = x[3] + h * ((T(1) / S.pars[0]) * a[0]);
+        x[4] = x[4] + h * ((T(1) / S.pars[1]) * a[1]);
+        rotate_trig(x[2], d, s, c);
+    } else {                                             // systems.py:412-419
+        T d[2];
+        state_dyn<T, SYS>(S, x, a, d);
+        x[0] = x[0] + h * d[0];
+        x[1] = x[1] + h * d[1];
+    }
+}
+
+template <typename T, int DIMC>
+struct RegW {
+    const T *w;
+    __device__ __forceinline__ T operator()(int i) const { return w[i]; }
+};
+
+// Template flag RDIAG of the actor kernels = "R1 diagonal AND stage_obj_struct == 'quadratic'" (every
+// preset); the general kernels (RDIAG = false) take dense R1/R2 and branch on the structure.
+// One _actor_cost evaluation.  `cp` points at component 0 of this lane's candidate, `ld` is the
+// distance between consecutive components.  NA > 0: compile-time horizon, fully unrolled.
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+__device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T> &O, const T *x0, const T *ob0, T s0,
+                                             T c0, const T *__restrict__ cp, int64_t ld, const T *w_r)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    constexpr int DIMC = dim_critic_c(CS, N, M);
+    const RegW<T, DIMC> w{w_r};
+    T state[N], obs[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { state[i] = x0[i]; obs[i] = ob0[i]; }    // controllers.py:1290-1291
+    T s = s0, c = c0, J = T(0);
+    const T h = O.pred_step_size;
+
+    auto stage = [&](int k, bool last, const T *a) {
+        if constexpr (MODE == RCG_MODE_MPC) {
+            J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);          // :1305-1306
+        } else if constexpr (MODE == RCG_MODE_RQL) {
+            if (!last) J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);   // :1308-1309
+            else J += critic<T, N, M, CS>(O, obs, a, w);                                // :1310
+        } else {
+            J += critic<T, N, M, CS>(O, obs, a, w);                                     // :1312-1326
+        }
+        if (!last) {
+            euler_step<T, SYS>(S, h, state, a, s, c);                                   // :1292-1296
+#pragma unroll
+            for (int i = 0; i < N; ++i) obs[i] = state[i];                              // sys_out = identity
+        }
+    };
+
+    if constexpr (NA > 0) {
+        T a[NA][M];
+#pragma unroll
+        for (int k = 0; k < NA; ++k)
+#pragma unroll
+            for (int j = 0; j < M; ++j) a[k][j] = __ldg(cp + (int64_t)(k * M + j) * ld);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) stage(k, k + 1 == NA, a[k]);
+    } else {
+        // runtime horizon: chunks of CH stages, the next chunk's actions are in flight while the
+        // current chunk is evaluated
+        constexpr int CH = 4;
+        const int na = O.Nactor;
+        T a[CH][M], an[CH][M];
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) a[i][j] = (i < na) ? __ldg(cp + (int64_t)(i * M + j) * ld) : T(0);
+        for (int k0 = 0; k0 < na; k0 += CH) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    an[i][j] = (k0 + CH + i < na) ? __ldg(cp + ((int64_t)(k0 + CH + i) * M + j) * ld) : T(0);
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (k0 + i < na) stage(k0 + i, k0 + i + 1 == na, a[i]);
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+#pragma unroll
+                for (int j = 0; j < M; ++j) a[i][j] = an[i][j];
+        }
+    }
+    return J;
+}
+
+struct ActorArgs {
+    int64_t E;
+    int C, seg, seg_shift;          // lanes per environment (32, or the power of two >= C), log2(seg)
+    int64_t num_groups;             // warps' worth of environments: ceil(E / (32 / seg))
+    int cand_per_env, w_per_env;
+};
+
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+__global__ void __launch_bounds__(kActorThreads)
+actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ ObjDev<T> O,
+                  const __grid_constant__ ActorArgs A, const T *__restrict__ state_sys_g, const T *__restrict__ obs_g,
+                  const T *__restrict__ cand_g, const T *__restrict__ w_g, const int32_t *__restrict__ mask_g,
+                  T *__restrict__ J_g, int32_t *__restrict__ argmin_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
+                  T *__restrict__ accum_g, T sampling_time)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    constexpr int DIMC = (MODE == RCG_MODE_MPC) ? 1 : dim_critic_c(CS, N, M);
+    constexpr int kNone = 0x7fffffff;            // "no candidate": loses against any real index
+    const int64_t E = A.E;
+    const int C = A.C, seg = A.seg;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane >> A.seg_shift, cl = lane & (seg - 1);
+    const int epw = 32 >> A.seg_shift;           // environments per warp
+    const int64_t ld = A.cand_per_env ? E * (int64_t)C : (int64_t)C;
+    const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kActorWarps;
+
+    for (int64_t g = warp0; g < A.num_groups; g += nwarps) {
+        const int64_t e = g * epw + slot;
+        const bool active = e < E && (mask_g == nullptr || mask_g[e] != 0);
+        T bestJ = T(0);
+        int bestI = kNone;
+        if (active) {
+            T x0[N], ob[N], w[DIMC];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { x0[i] = state_sys_g[i * E + e]; ob[i] = obs_g[i * E + e]; }
+            if constexpr (MODE != RCG_MODE_MPC) {
+#pragma unroll
+                for (int i = 0; i < DIMC; ++i) w[i] = A.w_per_env ? w_g[i * E + e] : w_g[i];
+            }
+            T s0 = T(0), c0 = T(1);
+            if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
+            const T *cbase = cand_g + (A.cand_per_env ? e * (int64_t)C : 0);
+            for (int c = cl; c < C; c += seg) {
+                const T J = actor_cost_lane<T, SYS, MODE, CS, RDIAG, NA>(S, O, x0, ob, s0, c0, cbase + c, ld, w);
+                if (J_g) J_g[e * (int64_t)C + c] = J;
+                if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
+            }
+        }
+        // arg-min across the lanes of this environment's segment (all 32 lanes take part in the shuffles)
+        for (int off = seg >> 1; off > 0; off >>= 1) {
+            const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
+            const int oI = __shfl_xor_sync(0xffffffffu, bestI, off);
+            if (oI != kNone && (bestI == kNone || argmin_better(oJ, oI, bestJ, bestI))) { bestJ = oJ; bestI = oI; }
+        }
+        if (active && cl == 0 && bestI != kNone) {
+            if (argmin_g) argmin_g[e] = bestI;
+            if (Jmin_g) Jmin_g[e] = bestJ;
+            if (action_g || accum_g) {
+                // first action of the best sequence (_actor_optimizer returns action_sqn[:dim_input])
+                T act[M], obs_e[N];
+                const T *cb = cand_g + (A.cand_per_env ? e * (int64_t)C : 0) + bestI;
+#pragma unroll
+                for (int j = 0; j < M; ++j) act[j] = cb[j * ld];
+                if (action_g) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
+                }
+                if (accum_g) {            // upd_accum_obj of the sampling step (controllers.py:1093)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) obs_e[i] = obs_g[i * E + e];
+                    accum_g[e] += stage_obj<T, N, M, RDIAG, RDIAG>(O, obs_e, act) * sampling_time;
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+struct ActorLaunch {
+    SysDev<T> S;
+    ObjDev<T> O;
+    ActorArgs A;
+    const T *state_sys, *obs, *cand, *w;
+    const int32_t *mask;
+    T *J;
+    int32_t *argmin;
+    T *Jmin, *action, *accum;
+    T sampling_time;
+    bool rdiag;
+    int mode, cs;
+    unsigned grid;
+    cudaStream_t stream;
+};
+
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+static void launch_actor_one(const ActorLaunch<T> &L)
+{
+    actor_cost_kernel<T, SYS, MODE, CS, RDIAG, NA><<<L.grid, kActorThreads, 0, L.stream>>>(
+        L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J, L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
+}
+
+// Horizon specialisations (diagonal R, the presets' case): the Nactor values of BASELINE.json's
+// configs (6, 10, 8) and of the presets' defaults (3, 5, 10); everything else runs the runtime loop.
+template <typename T, int SYS, int MODE, int CS>
+static void launch_actor_mc(const ActorLaunch<T> &L)
+{
+    if (!L.rdiag) { launch_actor_one<T, SYS, MODE, CS, false, 0>(L); return; }
+    if constexpr (sizeof(T) == 8) {
+        switch (L.O.Nactor) {
+        case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3>(L); return;
+        case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5>(L); return;
+        case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6>(L); return;
+        case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8>(L); return;
+        case 10: launch_actor_one<T, SYS, MODE, CS, true, 10>(L); return;
+        default: break;
+        }
+    }
+    launch_actor_one<T, SYS, MODE, CS, true, 0>(L);
+}
+
+template <typename T, int SYS>
+static int launch_actor_sys(const ActorLaunch<T> &L)
+{
+#define RCG_CASE_CS(MODE)                                                                      \
+    switch (L.cs) {                                                                            \
+    case RCG_CRITIC_QUAD_LIN:   launch_actor_mc<T, SYS, MODE, RCG_CRITIC_QUAD_LIN>(L); break;   \
+    case RCG_CRITIC_QUADRATIC:  launch_actor_mc<T, SYS, MODE, RCG_CRITIC_QUADRATIC>(L); break;  \
+    case RCG_CRITIC_QUAD_NOMIX: launch_actor_mc<T, SYS, MODE, RCG_CRITIC_QUAD_NOMIX>(L); break; \
+    case RCG_CRITIC_QUAD_MIX:   launch_actor_mc<T, SYS, MODE, RCG_CRITIC_QUAD_MIX>(L); break;   \
+    default: return RCG_EINVAL;                                                                \
+    }
+    if (L.mode == RCG_MODE_MPC) {
+        launch_actor_mc<T, SYS, RCG_MODE_MPC, RCG_CRITIC_QUAD_NOMIX>(L);
+    } else if (L.mode == RCG_MODE_RQL) {
+        RCG_CASE_CS(RCG_MODE_RQL)
+    } else if (L.mode == RCG_MODE_SQL) {
+        RCG_CASE_CS(RCG_MODE_SQL)
+    } else {
+        return RCG_EINVAL;
+    }
+#undef RCG_CASE_CS
+    return 0;
+}
+
+// one translation unit per (system, dtype): actor_ni.cu, actor_3w.cu, actor_2t.cu
+int launch_actor_ni(const ActorLaunch<double> &L);
+int launch_actor_ni(const ActorLaunch<float> &L);
+int launch_actor_3w(const ActorLaunch<double> &L);
+int launch_actor_3w(const ActorLaunch<float> &L);
+int launch_actor_2t(const ActorLaunch<double> &L);
+int launch_actor_2t(const ActorLaunch<float> &L);
+
+}  // namespace rcg

@@ -6,7 +6,7 @@
 namespace rcg {
 
 template <typename T>
-struct GlobalW {                 // weight i of lane `idx` in a [dimc][stride] array (stride 0: shared)
+struct GlobalW {                 // weight i of lane `idx` in a [dimc][stride] array (shared vector: stride 1, idx 0)
     const T *w;
     int64_t stride, idx;
     __device__ __forceinline__ T operator()(int i) const { return w[i * stride + idx]; }
@@ -41,7 +41,7 @@ critic_kernel(const __grid_constant__ ObjDev<T> O, int64_t E, const T *__restric
     for (int i = 0; i < N; ++i) obs[i] = obs_g[i * E + e];
 #pragma unroll
     for (int j = 0; j < M; ++j) act[j] = act_g[j * E + e];
-    const GlobalW<T> w{w_g, w_per_env ? E : 0, w_per_env ? e : 0};
+    const GlobalW<T> w{w_g, w_per_env ? E : 1, w_per_env ? e : 0};
     out_g[e] = critic<T, N, M, CS>(O, obs, act, w);
 }
 
@@ -94,6 +94,20 @@ push_buffers_kernel(int n, int m, int L, int64_t E, T *__restrict__ obs_buf, T *
     }
     for (int i = 0; i < n; ++i) obs_buf[((int64_t)(L - 1) * n + i) * E + e] = obs[i * E + e];
     for (int j = 0; j < m; ++j) act_buf[((int64_t)(L - 1) * m + j) * E + e] = act[j * E + e];
+}
+
+// The clock test of CtrlOptPred.compute_action (controllers.py:1440-1442, and :1459-1468 for
+// the critic clock): mask = (t - clock >= period) [& in_mask]; clock = t where mask.
+__global__ void __launch_bounds__(256)
+ctrl_sample_kernel(int64_t E, const double *__restrict__ t, double *__restrict__ clock, double period,
+                   const int32_t *__restrict__ in_mask, int32_t *__restrict__ mask_out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const double te = t[e];
+    const bool fire = (in_mask == nullptr || in_mask[e] != 0) && (te - clock[e] >= period);
+    if (fire) clock[e] = te;
+    mask_out[e] = fire ? 1 : 0;
 }
 
 static bool obj_rdiag(const rcg_objective_t *obj, int p)
@@ -188,6 +202,17 @@ int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E,
 #undef CALL
 #undef CC
     return check_launch("rcg_critic_cost");
+}
+
+int rcg_ctrl_sample(int64_t E, const double *t, double *clock, double period, const int32_t *in_mask, int32_t *mask_out,
+                    void *stream)
+{
+    using namespace rcg;
+    RCG_REQUIRE(t && clock && mask_out, "rcg_ctrl_sample: null argument");
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    ctrl_sample_kernel<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(E, t, clock, period, in_mask, mask_out);
+    return check_launch("rcg_ctrl_sample");
 }
 
 int rcg_push_buffers(int32_t n, int32_t m, int32_t buffer_size, int64_t E, double *obs_buf, double *act_buf,

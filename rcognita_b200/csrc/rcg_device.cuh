@@ -35,7 +35,70 @@ struct ObjDev {
     T target[RCG_MAX_N];      // zeros when has_target == 0 (x - 0 == x exactly)
 };
 
-__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+// ---- deterministic elementary functions (fp64 path) -------------------------------------------
+// sin/cos and err ** -0.2 decide, through the adaptive step size, the last bits of the solver time
+// t and with them the step on which the controller samples.  libm results differ
+// in the last bit between implementations (CUDA's sincos: <= 2 ulp; numpy's: CPU dependent), so the
+// fp64 path uses fully specified functions built from IEEE +,-,*,fma only -- the same operation
+// sequence the CPU checker uses, so that both agree bit for bit on every lane:
+//  - det_sincos: q = rint(x * 2/pi); r = x - q*pi/2 in double-double with pi/2 split into three
+//    doubles; then the fdlibm / FreeBSD msun k_sin / k_cos kernels on (rh, rl)  (< 1 ulp).
+//  - det_pow_m02: x ** -0.2 = libm pow() + one correction from the double-double residual
+//    y^5 * x - 1 and the term for 0.2 != 1/5: correctly rounded (up to astronomically rare cases).
+// Translation units that need bit-reproducibility (rk45.cu) are compiled with -fmad=false, so the
+// plain * and + below are never contracted; the fma() calls are explicit.
+__device__ __forceinline__ void det_sincos(double x, double *sn, double *cs)
+{
+    if (!(fabs(x) <= 1.0e5)) {                  // huge, inf, NaN: outside the regime of the path
+        sincos(x, sn, cs);
+        return;
+    }
+    const double q = rint(__dmul_rn(x, 6.36619772367581382433e-01));
+    const double P1 = 1.5707963267948966e+00, P2 = 6.123233995736766e-17, P3 = -1.4973849048591698e-33;
+    const double ph = __dmul_rn(q, P1), pl = fma(q, P1, -ph);
+    const double r = __dadd_rn(x, -ph);
+    double t = fma(-q, P2, -pl);
+    t = fma(-q, P3, t);
+    const double rh = __dadd_rn(r, t);
+    const double bb = __dadd_rn(rh, -r);
+    const double rl = __dadd_rn(__dadd_rn(r, -__dadd_rn(rh, -bb)), __dadd_rn(t, -bb));     // two-sum
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double z = __dmul_rn(rh, rh), w = __dmul_rn(z, z), v = __dmul_rn(z, rh);
+    // every product and sum rounded separately (intrinsics: immune to -fmad contraction)
+    const double ps = __dadd_rn(__dadd_rn(S2, __dmul_rn(z, __dadd_rn(S3, __dmul_rn(z, S4)))),
+                                __dmul_rn(__dmul_rn(z, w), __dadd_rn(S5, __dmul_rn(z, S6))));
+    const double ks = __dadd_rn(rh, -__dadd_rn(__dadd_rn(__dmul_rn(z, __dadd_rn(__dmul_rn(0.5, rl), -__dmul_rn(v, ps))), -rl),
+                                               -__dmul_rn(v, S1)));
+    const double pc = __dadd_rn(__dmul_rn(z, __dadd_rn(C1, __dmul_rn(z, __dadd_rn(C2, __dmul_rn(z, C3))))),
+                                __dmul_rn(__dmul_rn(w, w), __dadd_rn(C4, __dmul_rn(z, __dadd_rn(C5, __dmul_rn(z, C6))))));
+    const double hz = __dmul_rn(0.5, z), w1 = __dadd_rn(1.0, -hz);
+    const double kc = __dadd_rn(w1, __dadd_rn(__dadd_rn(__dadd_rn(1.0, -w1), -hz),
+                                              __dadd_rn(__dmul_rn(z, pc), -__dmul_rn(rh, rl))));
+    const int n = (int)((long long)q & 3);
+    *sn = (n == 0) ? ks : (n == 1) ? kc : (n == 2) ? -ks : -kc;
+    *cs = (n == 0) ? kc : (n == 1) ? -ks : (n == 2) ? -kc : ks;
+}
+
+__device__ __forceinline__ double det_pow_m02(double x)
+{
+    const double y = pow(x, -0.2);
+    if (!(x > 0.0 && x < (double)INFINITY)) return y;
+    const double ah = __dmul_rn(y, y), al = fma(y, y, -ah);                                                  // y^2
+    const double bh = __dmul_rn(ah, ah), bl = __dadd_rn(fma(ah, ah, -bh), __dmul_rn(2.0, __dmul_rn(ah, al)));   // y^4
+    const double ch = __dmul_rn(bh, y), cl = __dadd_rn(fma(bh, y, -ch), __dmul_rn(bl, y));                   // y^5
+    const double dh = __dmul_rn(ch, x), dl = __dadd_rn(fma(ch, x, -dh), __dmul_rn(cl, x));                   // y^5 x ~ 1
+    const double g = __dadd_rn(__dadd_rn(dh, -1.0), dl);
+    // the exponent is the double 0.2 = 1/5 + 1.1102230246251565e-17
+    return __dadd_rn(y, __dmul_rn(-y, __dadd_rn(__dmul_rn(0.2, g), __dmul_rn(1.1102230246251565e-17, log(x)))));
+}
+__device__ __forceinline__ float det_pow_m02(float x) { return powf(x, -0.2f); }
+
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { det_sincos(x, s, c); }
 __device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
 
 // System._state_dyn, is_disturb = 0:
@@ -101,7 +164,7 @@ __device__ __forceinline__ T quad_form(const T *x, const T *R)
 }
 
 // CtrlOptPred.stage_obj (rcognita/controllers.py:1063-1084), a.k.a. rcost.
-template <typename T, int N, int M, bool RDIAG>
+template <typename T, int N, int M, bool RDIAG, bool QUAD_ONLY = false>
 __device__ __forceinline__ T stage_obj(const ObjDev<T> &O, const T *obs, const T *act)
 {
     constexpr int P = N + M;
@@ -110,7 +173,7 @@ __device__ __forceinline__ T stage_obj(const ObjDev<T> &O, const T *obs, const T
     for (int i = 0; i < N; ++i) chi[i] = obs[i] - O.target[i];
 #pragma unroll
     for (int j = 0; j < M; ++j) chi[N + j] = act[j];
-    if (O.stage_struct == RCG_STAGE_QUADRATIC) {
+    if (QUAD_ONLY || O.stage_struct == RCG_STAGE_QUADRATIC) {
         return quad_form<T, P, RDIAG>(chi, O.R1);
     } else {
         T chi2[P];

@@ -120,12 +120,12 @@ __device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDe
         if (err < 1) {                                                         // rk.py:149-160
             double factor;
             if (err == 0) factor = 10;
-            else factor = fmin(10.0, 0.9 * pow(err, -0.2));
+            else factor = fmin(10.0, 0.9 * det_pow_m02(err));
             if (rejected) factor = fmin(1.0, factor);
             ha *= factor;
             break;
         } else {                                                               // rk.py:161-164
-            ha *= fmax(0.2, 0.9 * pow(err, -0.2));
+            ha *= fmax(0.2, 0.9 * det_pow_m02(err));
             rejected = true;
         }
     }
@@ -145,7 +145,7 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
             int32_t *__restrict__ nfev_g, int32_t *__restrict__ nsteps_g, T *__restrict__ action_g,
             double *__restrict__ clock_g, double sampling_time, int max_steps, T *__restrict__ state_sys_g,
-            T *__restrict__ accum_g, int32_t *__restrict__ flag_g)
+            T *__restrict__ accum_g, int32_t *__restrict__ flag_g, int32_t *__restrict__ nsamples_g)
 {
     constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,6 +200,7 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
         clock_g[e] = clock;
         if (accum_g) accum_g[e] = acc;
         if (flag_g) flag_g[e] = flag;
+        if (nsamples_g && flag) nsamples_g[e] += 1;
         if (state_sys_g && ns > 0) {
             // sampling lanes: the predictor starts from the state BEFORE the last step
             // (receive_sys_state runs after compute_action, main_3wrobot_NI.py:421-424);
@@ -254,21 +255,23 @@ template <typename T, int SYS, bool CTRL>
 static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const SysDev<T> &S, const SolverDev &sol,
                             const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
                             int32_t *nfev, int32_t *nsteps, T *action, double *clock, double sampling_time,
-                            int max_steps, T *state_sys, T *accum, int32_t *flag)
+                            int max_steps, T *state_sys, T *accum, int32_t *flag, int32_t *nsamples)
 {
     if (rdiag)
         rk45_kernel<T, SYS, CTRL, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
-                                                             clock, sampling_time, max_steps, state_sys, accum, flag);
+                                                             clock, sampling_time, max_steps, state_sys, accum, flag,
+                                                             nsamples);
     else
         rk45_kernel<T, SYS, CTRL, false><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
-                                                              clock, sampling_time, max_steps, state_sys, accum, flag);
+                                                              clock, sampling_time, max_steps, state_sys, accum, flag,
+                                                              nsamples);
 }
 
 template <typename T, bool CTRL>
 static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solver_t *sol_h, const rcg_objective_t *obj,
                        int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
                        int32_t *nsteps, T *action, double *clock, double sampling_time, int max_steps,
-                       T *state_sys, T *accum, int32_t *flag, void *stream)
+                       T *state_sys, T *accum, int32_t *flag, int32_t *nsamples, void *stream)
 {
     RCG_REQUIRE(sys && sol_h && y && f && t && h_abs && status && action, "%s: null argument", what);
     const int n = sys_n(sys->sys_id), m = sys_m(sys->sys_id);
@@ -296,15 +299,15 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
     switch (sys->sys_id) {
     case RCG_SYS_3WROBOT_NI:
         launch_rk45_sys<T, RCG_SYS_3WROBOT_NI, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag);
+                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
         break;
     case RCG_SYS_3WROBOT:
         launch_rk45_sys<T, RCG_SYS_3WROBOT, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag);
+                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
         break;
     default:
         launch_rk45_sys<T, RCG_SYS_2TANK, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag);
+                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
         break;
     }
     return check_launch(what);
@@ -334,34 +337,34 @@ int rcg_rk45_step(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E, d
                   double *h_abs, int32_t *status, int32_t *nfev, double *action, void *stream)
 {
     return rcg::launch_rk45<double, false>("rcg_rk45_step", sys, sol, nullptr, E, y, f, t, h_abs, status, nfev, nullptr,
-                                           action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, stream);
+                                           action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int rcg_rk45_step_f32(const rcg_system_t *sys, const rcg_solver_t *sol, int64_t E, float *y, float *f, double *t,
                       double *h_abs, int32_t *status, int32_t *nfev, float *action, void *stream)
 {
     return rcg::launch_rk45<float, false>("rcg_rk45_step_f32", sys, sol, nullptr, E, y, f, t, h_abs, status, nfev,
-                                          nullptr, action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, stream);
+                                          nullptr, action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,
                      double *y, double *f, double *t, double *h_abs, int32_t *status, int32_t *nfev, int32_t *nsteps,
                      double *action, double *ctrl_clock, double sampling_time, int32_t max_steps, double *state_sys,
-                     double *accum, int32_t *sample_flag, void *stream)
+                     double *accum, int32_t *sample_flag, int32_t *nsamples, void *stream)
 {
     return rcg::launch_rk45<double, true>("rcg_rk45_advance", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
                                           action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
-                                          stream);
+                                          nsamples, stream);
 }
 
 int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,
                          float *y, float *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
                          int32_t *nsteps, float *action, double *ctrl_clock, double sampling_time, int32_t max_steps,
-                         float *state_sys, float *accum, int32_t *sample_flag, void *stream)
+                         float *state_sys, float *accum, int32_t *sample_flag, int32_t *nsamples, void *stream)
 {
     return rcg::launch_rk45<float, true>("rcg_rk45_advance_f32", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
                                          action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
-                                         stream);
+                                         nsamples, stream);
 }
 
 }  // extern "C"

@@ -154,6 +154,7 @@ class ClosedLoopEngine:
         self.accum += hold * self.sampling_time * (1 - flag).to(self.dtype)
         if bool(flag.any()):
             self.ctrl_clock.copy_(torch.where(flag.bool(), self.t, self.ctrl_clock))
+            self.nsamples += self.sample_flag
             self._actor()                                   # state_sys is still y0 here
         self.state_sys.copy_(self.y)
         self._first_done = True
@@ -167,7 +168,6 @@ class ClosedLoopEngine:
         if ev is not None:
             ev[1].record()
             self.actor_events.append(ev)
-        self.nsamples += self.sample_flag
 
     def _actor_launch(self):
         ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
@@ -182,7 +182,7 @@ class ClosedLoopEngine:
             self._first_step()
         ops.rk45_advance(self.sysd, self.sol, self.obj, self.y, self.f, self.t, self.h_abs, self.status, self.action,
                          self.ctrl_clock, self.sampling_time, max_steps, state_sys=self.state_sys, accum=self.accum,
-                         sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps)
+                         sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps, nsamples=self.nsamples)
         self._actor()
         self.intervals += 1
 

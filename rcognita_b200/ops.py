@@ -78,7 +78,7 @@ def rk45_step(sysd, sol, y, f, t, h_abs, status, action, nfev=None):
 
 
 def rk45_advance(sysd, sol, obj, y, f, t, h_abs, status, action, ctrl_clock, sampling_time, max_steps,
-                 state_sys=None, accum=None, sample_flag=None, nfev=None, nsteps=None):
+                 state_sys=None, accum=None, sample_flag=None, nfev=None, nsteps=None, nsamples=None):
     """Fused loop body between two controller samples (see ``rcg_rk45_advance`` in rcg.h)."""
     n, m = _C.SYS_DIMS[sysd.sys_id]
     E = y.shape[1]
@@ -90,7 +90,7 @@ def rk45_advance(sysd, sol, obj, y, f, t, h_abs, status, action, ctrl_clock, sam
                 _ptr(action, dt, (m, E), "action"), _ptr(ctrl_clock, _F64, (E,), "ctrl_clock"),
                 float(sampling_time), int(max_steps), _ptr(state_sys, dt, (n, E), "state_sys", optional=True),
                 _ptr(accum, dt, (E,), "accum", optional=True), _ptr(sample_flag, _I32, (E,), "sample_flag", optional=True),
-                _stream()), "rcg_rk45_advance")
+                _ptr(nsamples, _I32, (E,), "nsamples", optional=True), _stream()), "rcg_rk45_advance")
 
 
 def actor_cost(sysd, obj, state_sys, obs, cand, cand_per_env, C_, w_critic=None, w_per_env=False, mask=None,
@@ -159,6 +159,17 @@ def critic_cost(obj, n, m, obs_buf, act_buf, w, w_prev, out=None):
                                     _ptr(w_prev, _F64, (dimc, E), "w_prev"), _ptr(out, _F64, (E, W), "out"), _stream()),
              "rcg_critic_cost")
     return out
+
+
+def ctrl_sample(t, clock, period, in_mask=None, mask_out=None):
+    """Clock test of ``CtrlOptPred.compute_action``: returns mask [E] int32, updates ``clock`` in place."""
+    E = t.shape[0]
+    if mask_out is None:
+        mask_out = torch.empty((E,), dtype=_I32, device=t.device)
+    _C.check(_C.lib.rcg_ctrl_sample(E, _ptr(t, _F64, (E,), "t"), _ptr(clock, _F64, (E,), "clock"), float(period),
+                                    _ptr(in_mask, _I32, (E,), "in_mask", optional=True),
+                                    _ptr(mask_out, _I32, (E,), "mask_out"), _stream()), "rcg_ctrl_sample")
+    return mask_out
 
 
 def push_buffers(n, m, obs_buf, act_buf, obs, act, mask=None):

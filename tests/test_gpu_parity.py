@@ -77,6 +77,23 @@ def test_state_dyn_and_rhs_golden(rb, fn, name):
     assert np.array_equal(act.T.cpu().numpy(), np.array([c["action_clipped"] for c in cases]))   # in-place clip
 
 
+def test_deterministic_sincos_bit_exact(rb):
+    """The fp64 kernels' sin/cos must equal the oracle's deterministic sincos BIT FOR BIT (it feeds
+    the adaptive step size and with it the controller's sampling pattern).  Sys3WRobotNI with
+    action (1, 0): _state_dyn = (cos theta, sin theta, 0)."""
+    _, _C, ops = rb
+    rng = np.random.default_rng(5)
+    th = np.concatenate([rng.uniform(-30, 30, 60000), rng.uniform(-1e4, 1e4, 20000), rng.normal(size=20000) * 1e-3,
+                         np.arange(-16, 17) * (np.pi / 4), [0.0, 1e-300, 99999.0, 1.0e5]])
+    E = th.size
+    sysd = _C.make_system("3wrobotNI", [], [])
+    state = np.zeros((3, E)); state[2] = th
+    act = np.zeros((2, E)); act[0] = 1.0
+    out = ops.state_dyn(sysd, dev(state), dev(act)).cpu().numpy()
+    ref = np.array([oracle.sincos(x) for x in th])
+    assert np.array_equal(out[0], ref[:, 1]) and np.array_equal(out[1], ref[:, 0]) and np.all(out[2] == 0.0)
+
+
 @pytest.mark.parametrize("name", SYSTEMS)
 def test_stage_obj_critic_golden(rb, fn, name):
     _, _C, ops = rb

@@ -74,6 +74,31 @@ def test_actor_cost_and_argmin(fn, name):
         assert one == J[2]
 
 
+def test_deterministic_elementary_functions():
+    """orc_sincos / orc_pow_m02 (the functions the CUDA fp64 path reproduces bit for bit): < 1 ulp
+    against libm over the path's argument range, quadrant logic, special values; x ** -0.2
+    equal to libm's pow except on rare last-bit cases (where libm is the one mis-rounding)."""
+    import math
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-30, 30, 20000), rng.uniform(-1e4, 1e4, 5000), rng.normal(size=5000) * 1e-4,
+                         np.arange(-16, 17) * (np.pi / 4), [0.0, -0.0, 1e-300, 99999.0]])
+    for x in xs:
+        s, c = oracle.sincos(x)
+        assert abs(s - math.sin(x)) <= 1.0 * np.spacing(abs(math.sin(x))) + 1e-300, x
+        assert abs(c - math.cos(x)) <= 1.0 * np.spacing(abs(math.cos(x))) + 1e-300, x
+    assert oracle.sincos(0.0) == (0.0, 1.0)
+    assert all(np.isnan(v) for v in oracle.sincos(float("nan"))) and all(np.isnan(v) for v in oracle.sincos(float("inf")))
+    assert oracle.sincos(3e7) == (math.sin(3e7), math.cos(3e7))          # huge arguments: libm fallback
+    es = np.concatenate([rng.uniform(0, 1, 20000) ** 3 * 5 + 1e-12, [1.0, 0.59049, 1e-30, 1e30]])
+    mism = 0
+    for e in es:
+        got, ref = oracle.pow_m02(e), float(e) ** -0.2
+        assert abs(got - ref) <= np.spacing(ref), e
+        mism += got != ref
+    assert mism <= 0.005 * len(es)
+    assert oracle.pow_m02(1.0) == 1.0 and oracle.pow_m02(float("inf")) == 0.0 and np.isnan(oracle.pow_m02(float("nan")))
+
+
 def test_argmin_semantics():
     assert oracle.argmin([3.0, 1.0, 1.0, 2.0]) == 1           # first minimum
     assert oracle.argmin([3.0, np.nan, 0.0, np.nan]) == 1     # np.argmin: first NaN wins

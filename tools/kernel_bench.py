@@ -1,0 +1,132 @@
+#!/usr/bin/env python3
+"""Kernel-level timings (CUDA events) of the hot-path kernels on one GPU: the actor-cost sweep
+(BASELINE.json configs[4]) and the RK45 step/advance kernels under a held action.  Prints one
+JSON line per point; used for profiles/ and DESIGN.md, not for the bench contract."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rcognita_b200 import _C, ops  # noqa: E402
+
+PRESET = {
+    "3wrobotNI": dict(pars=[], bnds=[[-25, 25], [-5, 5]], R1=[1, 10, 1, 0, 0], dt=0.01, psm=1.0, target=[]),
+    "3wrobot": dict(pars=[10, 1], bnds=[[-300, 300], [-100, 100]], R1=[1, 10, 1, 0, 0, 0, 0], dt=0.01, psm=2.0, target=[]),
+    "2tank": dict(pars=[18.4, 24.4, 1.3, 1, 0.2], bnds=[[0, 1]], R1=[10, 10, 1], dt=0.1, psm=2.0, target=[0.5, 0.5]),
+}
+BOX = {"3wrobotNI": ([-10, -10, -np.pi], [10, 10, np.pi]), "3wrobot": ([-10, -10, -np.pi, -1, -1], [10, 10, np.pi, 1, 1]),
+       "2tank": ([-2, -2], [2, 2])}
+
+
+def time_it(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def actor_point(system, mode, cs, N, E, C, per_env, dtype=torch.float64, iters=10):
+    p = PRESET[system]
+    n, m = _C.SYS_DIMS[_C.SYS_IDS[system]]
+    sysd = _C.make_system(system, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], critic_struct=cs, R1=p["R1"],
+                            observation_target=p["target"])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = (torch.tensor(v, device="cuda", dtype=torch.float64) for v in BOX[system])
+    x = (lo[:, None] + (hi - lo)[:, None] * torch.rand((n, E), device="cuda", dtype=torch.float64, generator=g)).to(dtype)
+    b = torch.tensor(p["bnds"], device="cuda", dtype=torch.float64)
+    ncol = E * C if per_env else C
+    cand = torch.empty((N * m, ncol), device="cuda", dtype=dtype)
+    for k in range(N * m):
+        j = k % m
+        cand[k] = (b[j, 0] + (b[j, 1] - b[j, 0]) * torch.rand((ncol,), device="cuda", dtype=torch.float64, generator=g)).to(dtype)
+    dimc = _C.dim_critic(cs, n, m)
+    w = None if mode == "MPC" else torch.rand((dimc,), device="cuda", dtype=torch.float64, generator=g).to(dtype)
+    am = torch.empty((E,), device="cuda", dtype=torch.int32)
+    jm = torch.empty((E,), device="cuda", dtype=dtype)
+    act = torch.empty((m, E), device="cuda", dtype=dtype)
+    fn = lambda: ops.actor_cost(sysd, obj, x, x, cand, per_env, C, w_critic=w, want_J=False, argmin_out=am, Jmin_out=jm,
+                                action_out=act)
+    ms = time_it(fn, iters)
+    evals = E * C
+    bytes_eval = (N * m * cand.element_size() + cand.element_size()) if per_env else cand.element_size()
+    return {"kernel": "actor_cost", "system": system, "mode": mode, "critic": cs, "Nactor": N, "E": E, "C": C,
+            "per_env_cands": bool(per_env), "dtype": str(dtype).split(".")[-1], "ms": ms, "evals_per_s": evals / ms * 1e3,
+            "alg_GBps": evals * bytes_eval / ms * 1e-6}
+
+
+def rk45_point(system, E, steps_per_launch, iters=5):
+    p = PRESET[system]
+    n, m = _C.SYS_DIMS[_C.SYS_IDS[system]]
+    sysd = _C.make_system(system, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode="MPC", Nactor=1, R1=p["R1"], observation_target=p["target"])
+    sol = _C.make_solver(1e9, p["dt"] / 2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = (torch.tensor(v, device="cuda", dtype=torch.float64) for v in BOX[system])
+    y = lo[:, None] + (hi - lo)[:, None] * torch.rand((n, E), device="cuda", dtype=torch.float64, generator=g)
+    b = torch.tensor(p["bnds"], device="cuda", dtype=torch.float64)
+    action = b[:, :1] + (b[:, 1:] - b[:, :1]) * torch.rand((m, E), device="cuda", dtype=torch.float64, generator=g)
+    f = ops.rhs(sysd, y, action)
+    t = torch.zeros((E,), device="cuda", dtype=torch.float64)
+    h = torch.full((E,), 1e-6, device="cuda", dtype=torch.float64)
+    status = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    nsteps = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    clock = torch.zeros((E,), device="cuda", dtype=torch.float64)
+    accum = torch.zeros((E,), device="cuda", dtype=torch.float64)
+    ssys = y.clone()
+    flag = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    if steps_per_launch == 1:
+        fn = lambda: ops.rk45_step(sysd, sol, y, f, t, h, status, action)
+    else:   # sampling_time huge: every lane takes exactly steps_per_launch accepted steps per launch
+        fn = lambda: ops.rk45_advance(sysd, sol, obj, y, f, t, h, status, action, clock, 1e18, steps_per_launch,
+                                      state_sys=ssys, accum=accum, sample_flag=flag, nsteps=nsteps)
+    for _ in range(8):
+        fn()                                                   # reach the max_step regime
+    ms = time_it(fn, iters)
+    steps = E * steps_per_launch
+    bytes_step = ((2 * n + 2 + m) * 8 + (2 * n + 2) * 8)
+    return {"kernel": "rk45_step" if steps_per_launch == 1 else "rk45_advance", "system": system, "E": E,
+            "steps_per_launch": steps_per_launch, "ms": ms, "env_steps_per_s": steps / ms * 1e3,
+            "alg_GBps_if_per_step_io": steps * bytes_step / ms * 1e-6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "all"])
+    a = ap.parse_args()
+    pts = []
+    if a.what in ("headline", "all"):
+        pts += [lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 256, True),
+                lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 256, False),
+                lambda: actor_point("3wrobot", "RQL", "quadratic", 10, 262144, 256, False),
+                lambda: actor_point("2tank", "SQL", "quad-nomix", 8, 262144, 256, False),
+                lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 256, True, torch.float32),
+                lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 7, 65536, 256, True)]
+    if a.what in ("sweep", "all"):
+        for N in (5, 10, 20, 50):
+            for C in (16, 64, 256, 1024):
+                for E in (4096, 65536, 1048576):
+                    per_env = E * C * N * 2 * 8 <= 4e9
+                    if E * C > 3e8:
+                        continue
+                    pts.append(lambda N=N, C=C, E=E, pe=per_env: actor_point("3wrobotNI", "MPC", "quad-nomix", N, E, C, pe, iters=5))
+    if a.what in ("rk45", "all"):
+        for system in ("3wrobotNI", "3wrobot", "2tank"):
+            for spl in (1, 16, 256):
+                pts.append(lambda s=system, k=spl: rk45_point(s, 1 << 20, k))
+    for p in pts:
+        print(json.dumps(p()), flush=True)
+
+
+if __name__ == "__main__":
+    main()
