@@ -71,6 +71,7 @@ def _load():
     L.rcg_stage_obj.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, dbl, vp]
     L.rcg_critic.argtypes = [objp, i32, i32, i64, vp, vp, vp, i32, vp, vp]
     L.rcg_critic_cost.argtypes = [objp, i32, i32, i64, i32, vp, vp, vp, vp, vp, vp]
+    L.rcg_critic_fit.argtypes = [objp, i32, i32, i64, vp, vp, vp, dbl, dbl, vp, vp, i32, vp, vp]
     L.rcg_ctrl_sample.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
     L.rcg_push_buffers.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, vp, vp]
     return L
@@ -82,7 +83,7 @@ EXPORTS = [
     "rcg_version", "rcg_last_error_string", "rcg_device_count", "rcg_dim_state", "rcg_dim_input", "rcg_dim_critic",
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
     "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_actor_cost", "rcg_actor_cost_f32",
-    "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_ctrl_sample", "rcg_push_buffers",
+    "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 
 

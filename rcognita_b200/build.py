@@ -27,6 +27,7 @@ SOURCES = {
     "actor_ni_f64.cu": [], "actor_3w_f64.cu": [], "actor_2t_f64.cu": [],
     "actor_ni_f32.cu": [], "actor_3w_f32.cu": [], "actor_2t_f32.cu": [],
     "critic.cu": ["-fmad=false"],
+    "critic_fit.cu": [],
 }
 HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", os.path.join(INCLUDE, "rcg.h")]
 

@@ -1,5 +1,7 @@
 // actor.cu -- host side of rcg_actor_cost / rcg_actor_cost_f32: argument checks, launch geometry
 // and dispatch to the per-system kernel instantiations (actor_impl.cuh, actor_{ni,3w,2t}_{f64,f32}.cu).
+#include <cstdlib>
+
 #include "actor_impl.cuh"
 
 namespace rcg {
@@ -49,6 +51,16 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     const int64_t blocks_needed = (L.A.num_groups + kActorWarps - 1) / kActorWarps;
     const int64_t max_grid = (int64_t)sms * 8;
     L.grid = (unsigned)(blocks_needed < max_grid ? blocks_needed : max_grid);
+    // pipelined kernel (per-env candidates): shared-memory ring limits residency to a few blocks per SM
+    {
+        const size_t stage_bytes = (size_t)obj->Nactor * m * kActorThreads * sizeof(T);
+        const int per_sm = (int)((size_t)220 * 1024 / (kPipeStages * stage_bytes + 1024));
+        const int resident = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+        const int64_t pg = (int64_t)sms * resident;
+        L.pipe_grid = (unsigned)(blocks_needed < pg ? blocks_needed : pg);
+        // worth it only when the candidate stream is large and every lane has several items to pipeline
+        L.use_pipe = per_sm >= 1 && getenv("RCG_ACTOR_NO_PIPE") == nullptr;
+    }
     L.stream = (cudaStream_t)stream;
     int rc;
     switch (sys->sys_id) {

@@ -108,22 +108,28 @@ struct RegW {
 
 // Template flag RDIAG of the actor kernels = "R1 diagonal AND stage_obj_struct == 'quadratic'" (every
 // preset); the general kernels (RDIAG = false) take dense R1/R2 and branch on the structure.
-// One _actor_cost evaluation.  `cp` points at component 0 of this lane's candidate, `ld` is the
-// distance between consecutive components.  NA > 0: compile-time horizon, fully unrolled.
-template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
-__device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T> &O, const T *x0, const T *ob0, T s0,
-                                             T c0, const T *__restrict__ cp, int64_t ld, const T *w_r)
-{
-    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
-    constexpr int DIMC = dim_critic_c(CS, N, M);
-    const RegW<T, DIMC> w{w_r};
+// ActorEval holds the running state of one _actor_cost evaluation (rollout state, cached heading
+// trigonometry, accumulated cost); stage(k) adds the cost of stage k and advances the predictor.
+template <typename T, int SYS, int MODE, int CS, bool RDIAG>
+struct ActorEval {
+    static constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    static constexpr int DIMC = dim_critic_c(CS, N, M);
+    const SysDev<T> &S;
+    const ObjDev<T> &O;
+    const RegW<T, DIMC> w;
     T state[N], obs[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { state[i] = x0[i]; obs[i] = ob0[i]; }    // controllers.py:1290-1291
-    T s = s0, c = c0, J = T(0);
-    const T h = O.pred_step_size;
+    T s, c, J, h;
 
-    auto stage = [&](int k, bool last, const T *a) {
+    __device__ __forceinline__ ActorEval(const SysDev<T> &S_, const ObjDev<T> &O_, const T *x0, const T *ob0, T s0, T c0,
+                                         const T *w_r)
+        : S(S_), O(O_), w{w_r}, s(s0), c(c0), J(T(0)), h(O_.pred_step_size)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { state[i] = x0[i]; obs[i] = ob0[i]; }    // controllers.py:1290-1291
+    }
+
+    __device__ __forceinline__ void stage(int k, bool last, const T *a)
+    {
         if constexpr (MODE == RCG_MODE_MPC) {
             J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);          // :1305-1306
         } else if constexpr (MODE == RCG_MODE_RQL) {
@@ -137,8 +143,17 @@ __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T>
 #pragma unroll
             for (int i = 0; i < N; ++i) obs[i] = state[i];                              // sys_out = identity
         }
-    };
+    }
+};
 
+// One _actor_cost evaluation.  `cp` points at component 0 of this lane's candidate, `ld` is the
+// distance between consecutive components.  NA > 0: compile-time horizon, fully unrolled.
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+__device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T> &O, const T *x0, const T *ob0, T s0,
+                                             T c0, const T *__restrict__ cp, int64_t ld, const T *w_r)
+{
+    constexpr int M = SysDim<SYS>::m;
+    ActorEval<T, SYS, MODE, CS, RDIAG> ev(S, O, x0, ob0, s0, c0, w_r);
     if constexpr (NA > 0) {
         T a[NA][M];
 #pragma unroll
@@ -146,7 +161,7 @@ __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T>
 #pragma unroll
             for (int j = 0; j < M; ++j) a[k][j] = __ldg(cp + (int64_t)(k * M + j) * ld);
 #pragma unroll
-        for (int k = 0; k < NA; ++k) stage(k, k + 1 == NA, a[k]);
+        for (int k = 0; k < NA; ++k) ev.stage(k, k + 1 == NA, a[k]);
     } else {
         // runtime horizon: chunks of CH stages, the next chunk's actions are in flight while the
         // current chunk is evaluated
@@ -165,14 +180,14 @@ __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T>
                     an[i][j] = (k0 + CH + i < na) ? __ldg(cp + ((int64_t)(k0 + CH + i) * M + j) * ld) : T(0);
 #pragma unroll
             for (int i = 0; i < CH; ++i)
-                if (k0 + i < na) stage(k0 + i, k0 + i + 1 == na, a[i]);
+                if (k0 + i < na) ev.stage(k0 + i, k0 + i + 1 == na, a[i]);
 #pragma unroll
             for (int i = 0; i < CH; ++i)
 #pragma unroll
                 for (int j = 0; j < M; ++j) a[i][j] = an[i][j];
         }
     }
-    return J;
+    return ev.J;
 }
 
 struct ActorArgs {
@@ -253,6 +268,145 @@ actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ O
     }
 }
 
+
+// ---- pipelined variant for per-environment candidates (the HBM-bound configuration) ----------------
+// Same mapping and arithmetic as actor_cost_kernel, but the candidate stream is staged through shared
+// memory with cp.async (LDGSTS): every thread owns one slot of Nactor*m values per pipeline stage
+// (layout [stage][component][thread]: conflict-free, and a warp's copy of one component is one
+// coalesced 256-byte request) and keeps STAGES - 1 candidates in flight behind the one it evaluates.
+// The copies hold no registers while in flight, so the memory pipe stays full during the FP64-heavy
+// rollout instead of idling until the next batch of loads is issued.  A thread only ever reads what
+// it copied itself, so cp.async.wait_group is the only synchronisation; the pipeline runs across
+// environment boundaries (items = this lane's (environment, candidate) pairs in order).
+template <int BYTES>
+__device__ __forceinline__ void cp_async_ca(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+
+template <typename T, int SYS, int MODE, int CS, int NA, int STAGES>
+__global__ void __launch_bounds__(kActorThreads)
+actor_cost_pipe_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ ObjDev<T> O,
+                       const __grid_constant__ ActorArgs A, const T *__restrict__ state_sys_g, const T *__restrict__ obs_g,
+                       const T *__restrict__ cand_g, const T *__restrict__ w_g, const int32_t *__restrict__ mask_g,
+                       T *__restrict__ J_g, int32_t *__restrict__ argmin_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
+                       T *__restrict__ accum_g, T sampling_time)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m, L = NA * M;
+    constexpr int DIMC = (MODE == RCG_MODE_MPC) ? 1 : dim_critic_c(CS, N, M);
+    constexpr int kNone = 0x7fffffff;
+    extern __shared__ __align__(16) unsigned char actor_smem[];
+    T *ring = reinterpret_cast<T *>(actor_smem) + threadIdx.x;          // [STAGES][L][kActorThreads]
+    const int64_t E = A.E;
+    const int C = A.C, seg = A.seg;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane >> A.seg_shift, cl = lane & (seg - 1);
+    const int epw = 32 >> A.seg_shift;
+    const int cpl = (C + seg - 1) >> A.seg_shift;                       // candidates per lane and environment
+    const int64_t ld = E * (int64_t)C;
+    const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kActorWarps;
+    const int64_t ngroups = (A.num_groups > warp0) ? (A.num_groups - warp0 + nwarps - 1) / nwarps : 0;
+
+    auto env_of = [&](int64_t gi) { return (warp0 + gi * nwarps) * epw + slot; };
+    auto env_active = [&](int64_t gi) -> int {
+        if (gi >= ngroups) return 0;
+        const int64_t e = env_of(gi);
+        return (e < E && (mask_g == nullptr || mask_g[e] != 0)) ? 1 : 0;
+    };
+
+    // producer side: next (environment, candidate) item to copy
+    int64_t p_gi = 0;
+    int p_ci = 0, p_act = env_active(0), p_act_next = env_active(1);
+    auto issue = [&](int stage) {
+        if (p_gi < ngroups) {
+            const int c = cl + p_ci * seg;
+            if (p_act && c < C) {
+                const T *src = cand_g + env_of(p_gi) * (int64_t)C + c;
+                T *dst = ring + (int64_t)stage * L * kActorThreads;
+#pragma unroll
+                for (int k = 0; k < L; ++k) cp_async_ca<sizeof(T)>(dst + k * kActorThreads, src + (int64_t)k * ld);
+            }
+            if (++p_ci == cpl) {
+                p_ci = 0;
+                ++p_gi;
+                p_act = p_act_next;
+                p_act_next = env_active(p_gi + 1);
+            }
+        }
+        cp_async_commit();                     // one group per item, empty or not: uniform wait counts
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) issue(s);
+
+    int stage = 0;
+    for (int64_t gi = 0; gi < ngroups; ++gi) {
+        const int64_t e = env_of(gi);
+        const bool active = env_active(gi) != 0;
+        T bestJ = T(0);
+        int bestI = kNone;
+        T x0[N], ob[N], w[DIMC];
+        T s0 = T(0), c0 = T(1);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { x0[i] = state_sys_g[i * E + e]; ob[i] = obs_g[i * E + e]; }
+            if constexpr (MODE != RCG_MODE_MPC) {
+#pragma unroll
+                for (int i = 0; i < DIMC; ++i) w[i] = A.w_per_env ? w_g[i * E + e] : w_g[i];
+            }
+            if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
+        }
+        for (int ci = 0; ci < cpl; ++ci) {
+            cp_async_wait<STAGES - 1>();       // the oldest outstanding item (this one) has landed
+            const int c = cl + ci * seg;
+            const bool valid = active && c < C;
+            if (valid) {
+                const T *src = ring + (int64_t)stage * L * kActorThreads;
+                ActorEval<T, SYS, MODE, CS, true> ev(S, O, x0, ob, s0, c0, w);
+#pragma unroll
+                for (int k = 0; k < NA; ++k) {
+                    T a[M];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) a[j] = src[(k * M + j) * kActorThreads];
+                    ev.stage(k, k + 1 == NA, a);
+                }
+                const T J = ev.J;
+                if (J_g) J_g[e * (int64_t)C + c] = J;
+                if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
+            }
+            issue(stage);                      // refill the slot just consumed
+            stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+        }
+        for (int off = seg >> 1; off > 0; off >>= 1) {
+            const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
+            const int oI = __shfl_xor_sync(0xffffffffu, bestI, off);
+            if (oI != kNone && (bestI == kNone || argmin_better(oJ, oI, bestJ, bestI))) { bestJ = oJ; bestI = oI; }
+        }
+        if (active && cl == 0 && bestI != kNone) {
+            if (argmin_g) argmin_g[e] = bestI;
+            if (Jmin_g) Jmin_g[e] = bestJ;
+            if (action_g || accum_g) {
+                T act[M];
+                const T *cb = cand_g + e * (int64_t)C + bestI;
+#pragma unroll
+                for (int j = 0; j < M; ++j) act[j] = cb[j * ld];
+                if (action_g) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
+                }
+                if (accum_g) accum_g[e] += stage_obj<T, N, M, true, true>(O, ob, act) * sampling_time;
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+constexpr int kPipeStages = 3;
+
 template <typename T>
 struct ActorLaunch {
     SysDev<T> S;
@@ -266,13 +420,28 @@ struct ActorLaunch {
     T sampling_time;
     bool rdiag;
     int mode, cs;
-    unsigned grid;
+    unsigned grid, pipe_grid;
+    bool use_pipe;
     cudaStream_t stream;
 };
 
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
 static void launch_actor_one(const ActorLaunch<T> &L)
 {
+    if constexpr (RDIAG && NA > 0 && sizeof(T) == 8) {
+        if (L.A.cand_per_env && L.use_pipe) {
+            auto kern = actor_cost_pipe_kernel<T, SYS, MODE, CS, NA, kPipeStages>;
+            const size_t smem = (size_t)kPipeStages * NA * SysDim<SYS>::m * kActorThreads * sizeof(T);
+            static bool configured = false;                   // per instantiation
+            if (!configured) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured = true;
+            }
+            kern<<<L.pipe_grid, kActorThreads, smem, L.stream>>>(L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
+                                                                L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
+            return;
+        }
+    }
     actor_cost_kernel<T, SYS, MODE, CS, RDIAG, NA><<<L.grid, kActorThreads, 0, L.stream>>>(
         L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J, L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
 }

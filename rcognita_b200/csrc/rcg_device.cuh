@@ -223,6 +223,42 @@ __device__ __forceinline__ T critic(const ObjDev<T> &O, const T *obs, const T *a
     return q;
 }
 
+// The feature vector phi(obs, act) of CtrlOptPred._critic (same order as critic() above), written out
+// explicitly: _critic_cost is linear least squares in w with rows phi (used by the critic fit).
+template <typename T, int N, int M, int CS>
+__device__ __forceinline__ void critic_phi(const ObjDev<T> &O, const T *obs, const T *act, T *phi)
+{
+    constexpr int P = N + M;
+    T chi[P];
+#pragma unroll
+    for (int i = 0; i < N; ++i) chi[i] = obs[i] - O.target[i];
+#pragma unroll
+    for (int j = 0; j < M; ++j) chi[N + j] = act[j];
+    int k = 0;
+    if constexpr (CS == RCG_CRITIC_QUAD_LIN || CS == RCG_CRITIC_QUADRATIC) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = i; j < P; ++j) phi[k++] = chi[i] * chi[j];
+        if constexpr (CS == RCG_CRITIC_QUAD_LIN) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) phi[k++] = chi[i];
+        }
+    } else if constexpr (CS == RCG_CRITIC_QUAD_NOMIX) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) phi[k++] = chi[i] * chi[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) phi[k++] = obs[i] * obs[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) phi[k++] = obs[i] * act[j];
+#pragma unroll
+        for (int j = 0; j < M; ++j) phi[k++] = act[j] * act[j];
+    }
+}
+
 __host__ __device__ constexpr int dim_critic_c(int cs, int n, int m)
 {
     const int p = n + m;

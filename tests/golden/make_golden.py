@@ -239,6 +239,44 @@ def gen_closed_loop():
         json.dump(out, fh)
 
 
+
+# --------------------------------------------------------------------------- critic fit (reference SLSQP as the bar)
+def gen_critic_fit():
+    """Reference `_critic_optimizer` (SLSQP, controllers.py:1248-1271) on seeded buffers: the fitted cost is
+    the bar the batched bounded-least-squares fit must reach (the minimiser itself is not unique)."""
+    out = []
+    for name, cfg in SYSTEMS.items():
+        n, m = cfg["n"], cfg["m"]
+        bn = np.array(cfg["bnds"], dtype=float)
+        my_sys = make_sys(name)
+        rng = np.random.default_rng(4242 + n)
+        for cs in ["quad-lin", "quadratic", "quad-nomix", "quad-mix"]:
+            for regime in ["random", "trajectory", "cold", "random_wprev"]:
+                for gamma in (1.0, 0.9):
+                    ctrl = make_ctrl(name, my_sys, "RQL", 4, critic_struct=cs, gamma=gamma)
+                    if regime in ("random", "random_wprev"):
+                        ob = rng.normal(size=(10, n)); ac = rng.uniform(bn[:, 0], bn[:, 1], size=(10, m))
+                    elif regime == "trajectory":       # consecutive samples of a smooth run: nearly collinear rows
+                        x = rng.uniform(-5, 5, size=n); v = rng.normal(size=n) * 0.05
+                        ob = np.array([x + k * v for k in range(10)])
+                        a0 = rng.uniform(bn[:, 0], bn[:, 1])
+                        ac = np.array([a0 * (1 - 0.02 * k) for k in range(10)])
+                    else:                              # first samples of an episode: zero rows at the top
+                        ob = np.zeros((10, n)); ac = np.zeros((10, m))
+                        ob[2:] = rng.normal(size=(8, n)); ac[2:] = rng.uniform(bn[:, 0], bn[:, 1], size=(8, m))
+                    ctrl.observation_buffer, ctrl.action_buffer = ob, ac
+                    if regime == "random_wprev":
+                        ctrl.w_critic_prev = rng.uniform(0, 3, size=ctrl.dim_critic)
+                    w_ref = ctrl._critic_optimizer()
+                    out.append(dict(system=name, critic_struct=cs, regime=regime, gamma=gamma, Ncritic=int(ctrl.Ncritic),
+                                    target=list(cfg["target"]), R1_diag=cfg["R1_diag"], obs_buf=L(ob), act_buf=L(ac),
+                                    w_prev=L(ctrl.w_critic_prev), w_init=L(ctrl.w_critic_init), Wmin=float(ctrl.Wmin[0]),
+                                    Wmax=float(ctrl.Wmax[0]), w_ref=L(w_ref), J_ref=float(ctrl._critic_cost(w_ref)),
+                                    J_init=float(ctrl._critic_cost(ctrl.w_critic_init))))
+    with open(os.path.join(HERE, "critic_fit.json"), "w") as fh:
+        json.dump(out, fh)
+    print("critic_fit.json", len(out), "cases; J_ref range", min(c["J_ref"] for c in out), max(c["J_ref"] for c in out))
+
 # --------------------------------------------------------------------------- config 1: preset-faithful SLSQP episode (App. A.2)
 def gen_config1():
     name = "3wrobotNI"
@@ -276,7 +314,7 @@ def gen_config1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1"]
+    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit"]
     if "functions" in which:
         gen_functions()
     if "integrator" in which:
@@ -285,3 +323,5 @@ if __name__ == "__main__":
         gen_closed_loop()
     if "config1" in which:
         gen_config1()
+    if "critic_fit" in which:
+        gen_critic_fit()

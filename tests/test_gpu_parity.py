@@ -212,6 +212,67 @@ def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
         assert rel_err(accum[e], 0.5 + oracle.stage_obj(c, n, m, obs[e], tab[am[e], :m]) * 0.01) <= COST_RTOL
 
 
+@pytest.mark.parametrize("name,mode,cs,N,E,C_", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 4099, 256), ("3wrobotNI", "MPC", "quad-nomix", 6, 3000, 100),
+    ("3wrobotNI", "MPC", "quad-nomix", 5, 2500, 12), ("3wrobot", "RQL", "quadratic", 10, 1500, 77),
+    ("2tank", "SQL", "quad-nomix", 8, 6000, 33),
+])
+def test_actor_pipelined_kernel_is_bit_identical(rb, name, mode, cs, N, E, C_):
+    """The cp.async-pipelined kernel (per-env candidates, compile-time horizon) and the direct-load kernel run
+    the same arithmetic: identical costs, arg-min, actions and accumulators on every lane, with a ragged mask,
+    many environments per warp and C not a multiple of the lane count."""
+    import os
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], gamma=0.97, critic_struct=cs,
+                            R1=p["R1_diag"], observation_target=p["target"])
+    obs = random_states(name, E, 11)
+    xs = obs + 0.01 * np.random.default_rng(12).normal(size=obs.shape)
+    g = torch.Generator(device="cuda").manual_seed(13)
+    b = torch.tensor(p["bnds"], device="cuda", dtype=torch.float64)
+    cdev = torch.empty((N * m, E * C_), device="cuda", dtype=torch.float64)
+    for k in range(N * m):
+        j = k % m
+        cdev[k] = b[j, 0] + (b[j, 1] - b[j, 0]) * torch.rand((E * C_,), device="cuda", dtype=torch.float64, generator=g)
+    dimc = _C.dim_critic(cs, n, m)
+    w = dev(np.random.default_rng(14).uniform(0, 2, size=(dimc, E)))
+    mask = (np.random.default_rng(15).uniform(size=E) < 0.8).astype(np.int32)
+    outs = []
+    for no_pipe in (False, True):
+        if no_pipe:
+            os.environ["RCG_ACTOR_NO_PIPE"] = "1"
+        else:
+            os.environ.pop("RCG_ACTOR_NO_PIPE", None)
+        try:
+            action_out = torch.full((m, E), -777.0, device="cuda", dtype=torch.float64)
+            accum = torch.full((E,), 0.25, device="cuda", dtype=torch.float64)
+            J = torch.full((E, C_), -1.0, device="cuda", dtype=torch.float64)
+            _, am, Jmin = ops.actor_cost(sysd, obj, soa(xs), soa(obs), cdev, True, C_, w_critic=w, w_per_env=True,
+                                         mask=dev(mask, torch.int32), J_out=J, action_out=action_out, accum=accum,
+                                         sampling_time=0.01)
+            torch.cuda.synchronize()
+            outs.append([t.cpu().numpy() for t in (J, am, Jmin, action_out, accum)])
+        finally:
+            os.environ.pop("RCG_ACTOR_NO_PIPE", None)
+    for a, b_ in zip(*outs):
+        assert np.array_equal(a, b_, equal_nan=True)
+    J, am = outs[0][0], outs[0][1]
+    on = mask.astype(bool)
+    assert np.all(am[~on] == -1) and np.all(J[~on] == -1.0)
+    assert np.array_equal(am[on], np.argmin(J[on], axis=1))
+    # spot-check a few lanes against the oracle
+    s = oracle.make_sys(name, p["pars"], p["bnds"])
+    c = oracle.make_ctrl(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], gamma=0.97, critic_struct=cs,
+                         R1=p["R1_diag"], observation_target=p["target"])
+    ch = cdev.cpu().numpy().reshape(N * m, E, C_)
+    wh = w.cpu().numpy()
+    for e in list(np.flatnonzero(on)[:3]) + [int(np.flatnonzero(on)[-1])]:
+        Jr, _ = oracle.actor_cost_table(c, s, ch[:, e, :].T.copy(), obs[e], xs[e], wh[:, e].copy())
+        assert rel_err(J[e], Jr) <= COST_RTOL
+
+
 def test_argmin_ties_and_nan(rb):
     """np.argmin semantics: first minimum wins; NaN counts as minimal (first NaN wins)."""
     _, _C, ops = rb
