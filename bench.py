@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="environments in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="environment blocks (streams) of the host-staged loop")
     return ap.parse_args()
 
 
@@ -172,7 +173,7 @@ def run_b200(args):
 
     import rcognita_b200
     from rcognita_b200 import shard
-    from rcognita_b200.engine import ClosedLoopEngine
+    from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop
     from bench_workload import make_workload
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +193,6 @@ def run_b200(args):
     t1 = max(10.0, (2 * (K + W) + 32) * 3 * DT)             # long enough that no lane finishes mid-bench
     eng = ClosedLoopEngine(SYSTEM, x0, cand, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
                            action_init=ACTION_INIT, device=dev)
-    del cand
 
     def barrier():
         if world > 1:
@@ -239,26 +239,30 @@ def run_b200(args):
     # ---- end to end: lane state owned by the HOST (pinned), copied in and out every step
     e2e = None
     if not args.no_e2e:
-        host = eng.make_host_state()
+        loop = HostStagedLoop(SYSTEM, x0, cand, nchunks=args.e2e_chunks, device=dev, ctrl_bnds=BNDS, mode="MPC", Nactor=N,
+                              dt=DT, t1=t1, R1=R1_DIAG, action_init=ACTION_INIT)
+        del cand
         for _ in range(3):
-            eng.run_interval_host(host)
+            loop.step()
         barrier()
-        s0 = int(host["nsamples"].sum().item())
+        s0 = int(loop.host_field("nsamples").sum().item())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(K):
-            h2d, d2h = eng.run_interval_host(host)
+            h2d, d2h = loop.step()
         e1.record()
         barrier()
         ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        ev_e2e = torch.tensor([(int(host["nsamples"].sum().item()) - s0) * C], dtype=torch.int64, device=dev)
+        ev_e2e = torch.tensor([(int(loop.host_field("nsamples").sum().item()) - s0) * C], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
             dist.all_reduce(ev_e2e, op=dist.ReduceOp.SUM)
         e2e = {"value": float(ev_e2e.item()) / (float(ms_e2e.item()) * 1e-3), "unit": "evals/s",
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                "ms_per_step": float(ms_e2e.item()) / K,
-               "api": "ClosedLoopEngine.run_interval_host (pinned host lane state in/out every step; candidates resident)"}
+               "api": f"HostStagedLoop.step: pinned host lane state in and out every step, {args.e2e_chunks} env blocks on "
+                      "separate streams (copies overlap kernels); candidate sets resident on the device"}
+        del loop
 
     if rank != 0:
         if world > 1:

@@ -1,10 +1,46 @@
 // actor.cu -- host side of rcg_actor_cost / rcg_actor_cost_f32: argument checks, launch geometry
 // and dispatch to the per-system kernel instantiations (actor_impl.cuh, actor_{ni,3w,2t}_{f64,f32}.cu).
+#include <cstdint>
 #include <cstdlib>
 
 #include "actor_impl.cuh"
 
 namespace rcg {
+
+// 2-D tensor map of a per-environment candidate array [rows = Nactor*m][cols = E*C] (row-major, cols
+// contiguous), box = 32 columns x all rows.  cuTensorMapEncodeTiled is resolved through the runtime so
+// that the library does not link against libcuda directly.
+static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, int64_t cols, int rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            (void)cudaGetLastError();
+            set_error("rcg_actor_cost: cuTensorMapEncodeTiled is not available from this driver");
+            return RCG_ENODEV;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * elem};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)rows};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult r = encode(tm, elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("rcg_actor_cost: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return RCG_EINVAL;
+    }
+    return 0;
+}
 
 template <typename T>
 static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t C,
@@ -51,15 +87,21 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     const int64_t blocks_needed = (L.A.num_groups + kActorWarps - 1) / kActorWarps;
     const int64_t max_grid = (int64_t)sms * 8;
     L.grid = (unsigned)(blocks_needed < max_grid ? blocks_needed : max_grid);
-    // pipelined kernel (per-env candidates): shared-memory ring limits residency to a few blocks per SM
+    L.sms = sms;
+    L.blocks_needed = blocks_needed;
+    // TMA-staged kernel: per-environment candidates, diagonal R, a specialised horizon, and a candidate
+    // count whose lane mapping is a contiguous box (C a multiple of 32, or a power of two below 32)
+    L.use_tma = false;
     {
-        const size_t stage_bytes = (size_t)obj->Nactor * m * kActorThreads * sizeof(T);
-        const int per_sm = (int)((size_t)220 * 1024 / (kPipeStages * stage_bytes + 1024));
-        const int resident = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
-        const int64_t pg = (int64_t)sms * resident;
-        L.pipe_grid = (unsigned)(blocks_needed < pg ? blocks_needed : pg);
-        // worth it only when the candidate stream is large and every lane has several items to pipeline
-        L.use_pipe = per_sm >= 1 && getenv("RCG_ACTOR_NO_PIPE") == nullptr;
+        const int na = obj->Nactor;
+        const bool na_ok = na == 3 || na == 5 || na == 6 || na == 8 || na == 10;
+        const bool c_ok = (C % 32 == 0) || (C < 32 && (C & (C - 1)) == 0);
+        const int64_t cols = E * (int64_t)C;
+        if (cand_per_env && L.rdiag && na_ok && c_ok && cols % (16 / (int)sizeof(T)) == 0 && cols < (int64_t)1 << 31 &&
+            ((uintptr_t)cand % 16) == 0 && getenv("RCG_ACTOR_NO_TMA") == nullptr) {
+            if (int rc = make_cand_tensor_map(&L.tmap, cand, sizeof(T), cols, na * m)) return rc;
+            L.use_tma = true;
+        }
     }
     L.stream = (cudaStream_t)stream;
     int rc;

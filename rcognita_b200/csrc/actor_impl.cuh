@@ -20,6 +20,8 @@
 // <= 2 ulp, i.e. ~1e-15 over the longest horizon -- against the 1e-9 cost tolerance.
 #pragma once
 
+#include <cuda.h>
+
 #include "rcg_host.h"
 
 namespace rcg {
@@ -71,7 +73,24 @@ __device__ __forceinline__ void rotate_trig(double theta_new, double delta, doub
         c = r.y;
     }
 }
-__device__ __forceinline__ void rotate_trig(float theta_new, float, float &s, float &c) { sincosf(theta_new, &s, &c); }
+// fp32 twin: same rotation with single-precision minimax kernels (Cephes sinf/cosf coefficients,
+// < 1 ulp on [-pi/4, pi/4]); the accumulated rotation error (~1e-7 per stage) is inside the fp32
+// tolerance of the path (tests: 2e-5 relative on costs).
+__device__ __forceinline__ void rotate_trig(float theta_new, float delta, float &s, float &c)
+{
+    if (fabsf(delta) <= 0.78539816f) {
+        const float z = delta * delta;
+        const float sd = fmaf(delta * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), delta);
+        const float cd = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                              fmaf(z, -0.5f, 1.0f));
+        const float cn = fmaf(c, cd, -(s * sd));
+        const float sn = fmaf(s, cd, c * sd);
+        s = sn;
+        c = cn;
+    } else {
+        sincosf(theta_new, &s, &c);
+    }
+}
 
 // One explicit-Euler predictor step, state += h * _state_dyn(state, a)  (controllers.py:1294 with
 // sys_rhs = System._state_dyn, unclipped).  (s, c) caches sin/cos of the heading state[2].
@@ -269,84 +288,136 @@ actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ O
 }
 
 
-// ---- pipelined variant for per-environment candidates (the HBM-bound configuration) ----------------
-// Same mapping and arithmetic as actor_cost_kernel, but the candidate stream is staged through shared
-// memory with cp.async (LDGSTS): every thread owns one slot of Nactor*m values per pipeline stage
-// (layout [stage][component][thread]: conflict-free, and a warp's copy of one component is one
-// coalesced 256-byte request) and keeps STAGES - 1 candidates in flight behind the one it evaluates.
-// The copies hold no registers while in flight, so the memory pipe stays full during the FP64-heavy
-// rollout instead of idling until the next batch of loads is issued.  A thread only ever reads what
-// it copied itself, so cp.async.wait_group is the only synchronisation; the pipeline runs across
-// environment boundaries (items = this lane's (environment, candidate) pairs in order).
-template <int BYTES>
-__device__ __forceinline__ void cp_async_ca(void *smem_dst, const void *gmem_src)
+// ---- TMA-staged variant for per-environment candidates (the HBM-bound configuration) ---------------
+// Same mapping and arithmetic as actor_cost_kernel, but the candidate stream never touches the
+// load/store pipe of the lanes: the per-environment candidate array [Nactor*m][E*C] is described by a
+// 2-D tensor map and one elected lane per warp issues ONE cp.async.bulk.tensor (TMA) per 32
+// candidates -- a box of 32 consecutive (environment, candidate) columns x Nactor*m component rows --
+// into the warp's private shared-memory ring, completion signalled on an mbarrier.  The ring keeps
+// STAGES boxes in flight per warp while the lanes run the FP64-heavy rollouts of the current box, so
+// HBM stays busy regardless of where the warps are in their arithmetic; the lanes read their candidate
+// as conflict-free LDS.64 ([component][lane] layout = the box as TMA writes it) and spend no
+// instructions on 64-bit address arithmetic or global loads.  The pipeline runs across environment
+// boundaries (items = this warp's (environment group, 32-candidate box) pairs in order).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
 
-template <typename T, int SYS, int MODE, int CS, int NA, int STAGES>
-__global__ void __launch_bounds__(kActorThreads)
-actor_cost_pipe_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ ObjDev<T> O,
-                       const __grid_constant__ ActorArgs A, const T *__restrict__ state_sys_g, const T *__restrict__ obs_g,
-                       const T *__restrict__ cand_g, const T *__restrict__ w_g, const int32_t *__restrict__ mask_g,
-                       T *__restrict__ J_g, int32_t *__restrict__ argmin_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
-                       T *__restrict__ accum_g, T sampling_time)
+// Ring depth and residency per horizon length.  A lane copies its candidate (its column of the box)
+// into registers as soon as the box has landed and the slot is refilled at once, so STAGES boxes per
+// warp are in flight while the rollouts run.  Measured on B200 (profiles/): three resident CTAs with a
+// 3-deep ring (80 registers) beat four CTAs with a 2-deep ring that read the box lazily (64 registers,
+// more moves, exposed LDS latency) -- 0.311 ms vs 0.346 ms on the 65,536 x 256 headline launch.
+template <typename T, int L>
+__host__ __device__ constexpr int tma_stages() { return (L * (int)sizeof(T) <= 64) ? 4 : (L * (int)sizeof(T) <= 96) ? 3 : 2; }
+template <typename T, int L>
+__host__ __device__ constexpr int tma_smem_bytes() { return kActorWarps * tma_stages<T, L>() * (L * 32 * (int)sizeof(T) + 8); }
+template <typename T, int L>
+__host__ __device__ constexpr int tma_min_ctas() { return (225 * 1024 / (tma_smem_bytes<T, L>() + 1024)) >= 3 ? 3 : 2; }
+
+template <typename T, int SYS, int MODE, int CS, int NA>
+__global__ void __launch_bounds__(kActorThreads, tma_min_ctas<T, NA * SysDim<SYS>::m>())
+actor_cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SysDev<T> S,
+                      const __grid_constant__ ObjDev<T> O, const __grid_constant__ ActorArgs A,
+                      const T *__restrict__ state_sys_g, const T *__restrict__ obs_g, const T *__restrict__ cand_g,
+                      const T *__restrict__ w_g, const int32_t *__restrict__ mask_g, T *__restrict__ J_g,
+                      int32_t *__restrict__ argmin_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
+                      T *__restrict__ accum_g, T sampling_time)
 {
     constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m, L = NA * M;
+    constexpr int STAGES = tma_stages<T, L>();
+    constexpr int BOX = L * 32;                                         // elements per box
     constexpr int DIMC = (MODE == RCG_MODE_MPC) ? 1 : dim_critic_c(CS, N, M);
     constexpr int kNone = 0x7fffffff;
-    extern __shared__ __align__(16) unsigned char actor_smem[];
-    T *ring = reinterpret_cast<T *>(actor_smem) + threadIdx.x;          // [STAGES][L][kActorThreads]
+    extern __shared__ __align__(128) unsigned char actor_smem[];
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *ring = reinterpret_cast<T *>(actor_smem) + (size_t)wi * STAGES * BOX;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(actor_smem + (size_t)kActorWarps * STAGES * BOX * sizeof(T)) + wi * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
     const int64_t E = A.E;
     const int C = A.C, seg = A.seg;
-    const int lane = threadIdx.x & 31;
     const int slot = lane >> A.seg_shift, cl = lane & (seg - 1);
-    const int epw = 32 >> A.seg_shift;
-    const int cpl = (C + seg - 1) >> A.seg_shift;                       // candidates per lane and environment
+    const int epw = 32 >> A.seg_shift;                                  // environments per warp (1 when C >= 32)
+    const int cpl = (C + seg - 1) >> A.seg_shift;                       // 32-candidate boxes per environment group
     const int64_t ld = E * (int64_t)C;
-    const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + (threadIdx.x >> 5);
+    const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + wi;
     const int64_t nwarps = (int64_t)gridDim.x * kActorWarps;
     const int64_t ngroups = (A.num_groups > warp0) ? (A.num_groups - warp0 + nwarps - 1) / nwarps : 0;
 
-    auto env_of = [&](int64_t gi) { return (warp0 + gi * nwarps) * epw + slot; };
-    auto env_active = [&](int64_t gi) -> int {
+    auto env_active = [&](int64_t gi, int sl) -> int {
         if (gi >= ngroups) return 0;
-        const int64_t e = env_of(gi);
+        const int64_t e = (warp0 + gi * nwarps) * epw + sl;
         return (e < E && (mask_g == nullptr || mask_g[e] != 0)) ? 1 : 0;
     };
-
-    // producer side: next (environment, candidate) item to copy
+    // producer (lane 0): next box to fetch.  A group whose only environment is masked out is skipped
+    // (plain arrive, nothing copied); groups of several small environments are always fetched.
     int64_t p_gi = 0;
-    int p_ci = 0, p_act = env_active(0), p_act_next = env_active(1);
+    int p_ci = 0, p_act = 0, p_act_next = 0;
+    if (lane == 0) {
+        p_act = (epw == 1) ? env_active(0, 0) : (ngroups > 0);
+        p_act_next = (epw == 1) ? env_active(1, 0) : (ngroups > 1);
+    }
     auto issue = [&](int stage) {
         if (p_gi < ngroups) {
-            const int c = cl + p_ci * seg;
-            if (p_act && c < C) {
-                const T *src = cand_g + env_of(p_gi) * (int64_t)C + c;
-                T *dst = ring + (int64_t)stage * L * kActorThreads;
-#pragma unroll
-                for (int k = 0; k < L; ++k) cp_async_ca<sizeof(T)>(dst + k * kActorThreads, src + (int64_t)k * ld);
+            if (p_act) {
+                const int64_t x = (warp0 + p_gi * nwarps) * (int64_t)epw * C + (int64_t)p_ci * 32;
+                mbar_arrive_expect_tx(&bars[stage], (uint32_t)(BOX * sizeof(T)));
+                tma_load_box(ring + (size_t)stage * BOX, &tmap, (int)x, 0, &bars[stage]);
+            } else {
+                mbar_arrive(&bars[stage]);
             }
             if (++p_ci == cpl) {
                 p_ci = 0;
                 ++p_gi;
                 p_act = p_act_next;
-                p_act_next = env_active(p_gi + 1);
+                p_act_next = (epw == 1) ? env_active(p_gi + 1, 0) : (p_gi + 1 < ngroups);
             }
         }
-        cp_async_commit();                     // one group per item, empty or not: uniform wait counts
     };
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) issue(s);
+        for (int s = 0; s < STAGES; ++s) issue(s);
+    }
 
     int stage = 0;
+    uint32_t phase = 0;
     for (int64_t gi = 0; gi < ngroups; ++gi) {
-        const int64_t e = env_of(gi);
-        const bool active = env_active(gi) != 0;
+        const int64_t e = (warp0 + gi * nwarps) * epw + slot;
+        const bool active = env_active(gi, slot) != 0;
         T bestJ = T(0);
         int bestI = kNone;
         T x0[N], ob[N], w[DIMC];
@@ -361,25 +432,28 @@ actor_cost_pipe_kernel(const __grid_constant__ SysDev<T> S, const __grid_constan
             if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
         }
         for (int ci = 0; ci < cpl; ++ci) {
-            cp_async_wait<STAGES - 1>();       // the oldest outstanding item (this one) has landed
+            mbar_wait(&bars[stage], phase);                        // this box has landed
             const int c = cl + ci * seg;
             const bool valid = active && c < C;
+            T a[NA][M];
+            {
+                const T *src = ring + (size_t)stage * BOX + lane;
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+#pragma unroll
+                    for (int j = 0; j < M; ++j) a[k][j] = src[(k * M + j) * 32];
+            }
+            __syncwarp();                                          // every lane has copied its column out
+            if (lane == 0) issue(stage);                           // refill the slot
             if (valid) {
-                const T *src = ring + (int64_t)stage * L * kActorThreads;
                 ActorEval<T, SYS, MODE, CS, true> ev(S, O, x0, ob, s0, c0, w);
 #pragma unroll
-                for (int k = 0; k < NA; ++k) {
-                    T a[M];
-#pragma unroll
-                    for (int j = 0; j < M; ++j) a[j] = src[(k * M + j) * kActorThreads];
-                    ev.stage(k, k + 1 == NA, a);
-                }
+                for (int k = 0; k < NA; ++k) ev.stage(k, k + 1 == NA, a[k]);
                 const T J = ev.J;
                 if (J_g) J_g[e * (int64_t)C + c] = J;
                 if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
             }
-            issue(stage);                      // refill the slot just consumed
-            stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         for (int off = seg >> 1; off > 0; off >>= 1) {
             const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
@@ -402,10 +476,7 @@ actor_cost_pipe_kernel(const __grid_constant__ SysDev<T> S, const __grid_constan
             }
         }
     }
-    cp_async_wait<0>();
 }
-
-constexpr int kPipeStages = 3;
 
 template <typename T>
 struct ActorLaunch {
@@ -420,25 +491,31 @@ struct ActorLaunch {
     T sampling_time;
     bool rdiag;
     int mode, cs;
-    unsigned grid, pipe_grid;
-    bool use_pipe;
+    unsigned grid;
+    int sms;
+    int64_t blocks_needed;
+    bool use_tma;              // per-env candidates staged by TMA (tmap valid)
+    CUtensorMap tmap;
     cudaStream_t stream;
 };
 
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
 static void launch_actor_one(const ActorLaunch<T> &L)
 {
-    if constexpr (RDIAG && NA > 0 && sizeof(T) == 8) {
-        if (L.A.cand_per_env && L.use_pipe) {
-            auto kern = actor_cost_pipe_kernel<T, SYS, MODE, CS, NA, kPipeStages>;
-            const size_t smem = (size_t)kPipeStages * NA * SysDim<SYS>::m * kActorThreads * sizeof(T);
+    if constexpr (RDIAG && NA > 0) {
+        if (L.use_tma) {
+            constexpr int LL = NA * SysDim<SYS>::m;
+            auto kern = actor_cost_tma_kernel<T, SYS, MODE, CS, NA>;
+            const size_t smem = (size_t)tma_smem_bytes<T, LL>();
             static bool configured = false;                   // per instantiation
             if (!configured) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 configured = true;
             }
-            kern<<<L.pipe_grid, kActorThreads, smem, L.stream>>>(L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
-                                                                L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
+            const int64_t pg = (int64_t)L.sms * tma_min_ctas<T, LL>();
+            const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
+            kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
+                                                         L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
             return;
         }
     }
@@ -452,15 +529,13 @@ template <typename T, int SYS, int MODE, int CS>
 static void launch_actor_mc(const ActorLaunch<T> &L)
 {
     if (!L.rdiag) { launch_actor_one<T, SYS, MODE, CS, false, 0>(L); return; }
-    if constexpr (sizeof(T) == 8) {
-        switch (L.O.Nactor) {
-        case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3>(L); return;
-        case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5>(L); return;
-        case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6>(L); return;
-        case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8>(L); return;
-        case 10: launch_actor_one<T, SYS, MODE, CS, true, 10>(L); return;
-        default: break;
-        }
+    switch (L.O.Nactor) {
+    case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3>(L); return;
+    case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5>(L); return;
+    case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6>(L); return;
+    case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8>(L); return;
+    case 10: launch_actor_one<T, SYS, MODE, CS, true, 10>(L); return;
+    default: break;
     }
     launch_actor_one<T, SYS, MODE, CS, true, 0>(L);
 }

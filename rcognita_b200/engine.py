@@ -226,9 +226,9 @@ class ClosedLoopEngine:
             self._first_step()
         return {k: getattr(self, k).cpu().pin_memory() for k in self.LANE_FIELDS + self.RESULT_FIELDS}
 
-    def run_interval_host(self, host):
-        """H2D lane state -> rk45_advance + actor_cost -> D2H lane state and results; returns the
-        bytes moved (h2d, d2h).  Synchronises: the host buffers are valid on return."""
+    def run_interval_host(self, host, sync=True):
+        """H2D lane state -> rk45_advance + actor_cost -> D2H lane state and results, all on the current
+        stream; returns the bytes moved (h2d, d2h).  With ``sync`` the host buffers are valid on return."""
         h2d = d2h = 0
         for k in self.LANE_FIELDS:
             getattr(self, k).copy_(host[k], non_blocking=True)
@@ -237,5 +237,52 @@ class ClosedLoopEngine:
         for k in self.LANE_FIELDS + self.RESULT_FIELDS:
             host[k].copy_(getattr(self, k), non_blocking=True)
             d2h += host[k].numel() * host[k].element_size()
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
         return h2d, d2h
+
+
+class HostStagedLoop:
+    """The closed loop for a caller that owns its environments in HOST memory (like the reference's Python
+    loop does): the batch is split into ``nchunks`` contiguous blocks of environments, each with its own
+    ``ClosedLoopEngine`` and CUDA stream, so that the host->device copy of block i+1, the two kernels of block i
+    and the device->host copy of block i-1 overlap (PCIe is full duplex, kernels of different blocks may share
+    the GPU).  ``step()`` = one control interval of every environment, host buffers valid on return.
+    Candidate tables stay resident on the device (they are parameters of the controller, not per-step inputs)."""
+
+    def __init__(self, system, state_init, candidates, nchunks=4, device=None, **engine_kwargs):
+        x0 = state_init if isinstance(state_init, torch.Tensor) else np.asarray(state_init, dtype=np.float64)
+        E = x0.shape[0]
+        nchunks = max(1, min(int(nchunks), E))
+        bounds = [(E * i) // nchunks for i in range(nchunks + 1)]
+        per_env = candidates.ndim == 3 if not isinstance(candidates, torch.Tensor) else candidates.dim() == 3
+        self.engines, self.streams, self.hosts = [], [], []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            cand = candidates[a:b] if per_env else candidates
+            eng = ClosedLoopEngine(system, x0[a:b], cand, device=device, **engine_kwargs)
+            self.engines.append(eng)
+        dev = self.engines[0].device
+        with torch.cuda.device(dev):
+            for eng in self.engines:
+                self.streams.append(torch.cuda.Stream(device=dev))
+                self.hosts.append(eng.make_host_state())
+        torch.cuda.synchronize(dev)
+        self.E = E
+
+    def step(self):
+        h2d = d2h = 0
+        cur = torch.cuda.current_stream()
+        for eng, st, host in zip(self.engines, self.streams, self.hosts):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                a, b = eng.run_interval_host(host, sync=False)
+            h2d += a
+            d2h += b
+        for st in self.streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+        return h2d, d2h
+
+    def host_field(self, name):
+        """Concatenated host view of one lane field over all blocks (lane axis last)."""
+        return torch.cat([h[name] for h in self.hosts], dim=-1)
