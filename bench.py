@@ -5,8 +5,8 @@ Workload (BASELINE.json configs[1]): 3wrobot_NI, MPC, Nactor=6, dt=0.01; 65,536 
 PER GPU x 256 candidate action sequences per environment, RK45 closed loop.  One bench "step"
 = one control interval of the whole batch: `rcg_rk45_advance` integrates every environment
 to its next controller sample (scipy-faithful RK45, ~2-3 accepted steps) and `rcg_actor_cost`
-evaluates E x C `_actor_cost` rollouts, takes the per-environment arg-min and hands the action
-over.  `value` = `_actor_cost` evaluations per second over the whole closed loop (all GPUs),
+evaluates E x C `_actor_cost` rollouts (candidate stream staged by TMA), takes the per-environment
+arg-min and hands the action over.  `value` = `_actor_cost` evaluations per second over the whole closed loop (all GPUs),
 `env_steps_per_s` the accepted RK45 steps per second of the same timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA)
@@ -40,7 +40,7 @@ BYTES_PER_EVAL_PER_ENV_CAND = lambda N, m: N * m * 8 + 8      # candidate read +
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
@@ -281,7 +281,7 @@ def run_b200(args):
     evals_per_launch = d_evals / max(1, K)
     bytes_per_eval = (N * 2 * 8 + 8) if not args.shared_cands else 8
     achieved = evals_per_launch * bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "actor_cost_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "actor_cost_tma_kernel" if not args.shared_cands else "actor_cost_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,

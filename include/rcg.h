@@ -193,14 +193,17 @@ int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E,
 
 /* CtrlOptPred._critic_optimizer (rcognita/controllers.py:1248-1271) for E environments: the minimiser of
  * _critic_cost(w) subject to w_min <= w_i <= w_max (the reference's Bounds(Wmin, Wmax), controllers.py:1024-1039,
- * uniform per structure), started from the values found in w [dimc][E] (w_critic_init) and written back there.
- * The reference runs SLSQP; here a bounded linear least-squares solve per environment (critic_fit.cu) --
- * the fitted cost is <= the cost at the start point and, on the committed goldens, <= the reference's.
- * Lanes with mask == 0 are left untouched.  max_outer <= 0 selects the default iteration budget.
- * Jc_out[E] (may be NULL) receives _critic_cost at the returned weights. */
+ * uniform per structure), started from w_init [dimc] (w_critic_init, shared by all environments; NULL = start
+ * from the values found in w) and written to w [dimc][E].  The reference runs SLSQP; here a bounded linear
+ * least-squares solve per environment (critic_fit.cu) -- the fitted cost is <= the cost at the start point
+ * and, on the committed goldens, <= the reference's.  Lanes with mask == 0 are left untouched.
+ * update_prev != 0 additionally stores the result in w_prev [dimc][E] (controllers.py:1471).
+ * max_outer <= 0 selects the default iteration budget.  Jc_out[E] (may be NULL) receives _critic_cost at the
+ * returned weights. */
 int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs_buf,
-                   const double *act_buf, const double *w_prev, double w_min, double w_max, double *w,
-                   const int32_t *mask, int32_t max_outer, double *Jc_out, void *stream);
+                   const double *act_buf, double *w_prev, double w_min, double w_max, const double *w_init,
+                   double *w, const int32_t *mask, int32_t max_outer, int32_t update_prev, double *Jc_out,
+                   void *stream);
 
 /* The sampling-clock test of CtrlOptPred.compute_action (rcognita/controllers.py:1440-1442;
  * the critic clock of :1459-1468 uses the same form): for every lane with in_mask != 0 (all

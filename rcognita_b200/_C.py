@@ -71,7 +71,7 @@ def _load():
     L.rcg_stage_obj.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, dbl, vp]
     L.rcg_critic.argtypes = [objp, i32, i32, i64, vp, vp, vp, i32, vp, vp]
     L.rcg_critic_cost.argtypes = [objp, i32, i32, i64, i32, vp, vp, vp, vp, vp, vp]
-    L.rcg_critic_fit.argtypes = [objp, i32, i32, i64, vp, vp, vp, dbl, dbl, vp, vp, i32, vp, vp]
+    L.rcg_critic_fit.argtypes = [objp, i32, i32, i64, vp, vp, vp, dbl, dbl, vp, vp, vp, i32, i32, vp, vp]
     L.rcg_ctrl_sample.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
     L.rcg_push_buffers.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, vp, vp]
     return L

@@ -158,7 +158,7 @@ class CtrlOptPred:
         self._act_buf = torch.zeros((self.buffer_size, m, E), dtype=_F64, device=dev)
         self._w_critic = torch.ones((self.dim_critic, E), dtype=_F64, device=dev)
         self._w_critic_prev = torch.ones((self.dim_critic, E), dtype=_F64, device=dev)       # :1041-1042
-        self._w_critic_init = torch.ones((self.dim_critic, E), dtype=_F64, device=dev)
+        self._w_critic_init = torch.ones((self.dim_critic,), dtype=_F64, device=dev)
         self._mask = torch.zeros((E,), dtype=_I32, device=dev)
         self._cmask = torch.zeros((E,), dtype=_I32, device=dev)
         self._argmin = torch.full((E,), -1, dtype=_I32, device=dev)
@@ -195,7 +195,7 @@ class CtrlOptPred:
     accum_obj_val = property(lambda self: self._vec(self._accum))
     w_critic = property(lambda self: self._out(self._w_critic))
     w_critic_prev = property(lambda self: self._out(self._w_critic_prev))
-    w_critic_init = property(lambda self: self._out(self._w_critic_init))
+    w_critic_init = property(lambda self: self._out(self._w_critic_init[:, None].expand(-1, self._E)))
     action_buffer = property(lambda self: self._buf_out(self._act_buf))
     observation_buffer = property(lambda self: self._buf_out(self._obs_buf))
 
@@ -261,9 +261,9 @@ class CtrlOptPred:
         ``w_critic_init``.  ``_critic_cost`` is a linear least-squares objective in ``w``; the fit runs
         per environment in ``rcg_critic_fit`` (bounded least squares) instead of SLSQP.  Returns
         ``[dimc, E]`` SoA weights (only the lanes with ``mask`` != 0 are refitted)."""
-        w = self._w_critic_init.clone()
+        w = self._w_critic.clone()
         ops.critic_fit(self._obj, self.dim_output, self.dim_input, self._obs_buf, self._act_buf, self._w_critic_prev,
-                       float(self.Wmin[0]), float(self.Wmax[0]), w, mask=mask)
+                       float(self.Wmin[0]), float(self.Wmax[0]), w, w_init=self._w_critic_init, mask=mask)
         return w
 
     def _actor_cost(self, action_sqn, observation):

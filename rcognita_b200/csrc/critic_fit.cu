@@ -12,6 +12,8 @@
 // changing).  The iterate with the smallest J_c is returned, so the result is never worse than w_critic_init.
 // Parity is on the fitted COST against the reference's SLSQP result (tests/golden/critic_fit.json), never on
 // the weights (hard part 5).
+#include <type_traits>
+
 #include "rcg_host.h"
 
 namespace rcg {
@@ -28,9 +30,9 @@ struct GlobalWF {
 template <int N, int M, int CS, bool RDIAG>
 __global__ void __launch_bounds__(128)
 critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const double *__restrict__ obs_buf,
-                  const double *__restrict__ act_buf, const double *__restrict__ wprev_g, double lo, double hi,
-                  double *__restrict__ w_g, const int32_t *__restrict__ mask, double mu_rel, int max_outer,
-                  int max_newton, double *__restrict__ Jc_out)
+                  const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
+                  const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
+                  double mu_rel, int max_outer, int max_newton, int update_prev, double *__restrict__ Jc_out)
 {
     constexpr int D = dim_critic_c(CS, N, M);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +46,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
     signed char st[D];
 
     // rows of the least-squares problem (controllers.py:1230-1242)
-    const GlobalWF<double> wp{wprev_g, E, e};
+    const GlobalWF<double> wp{wprev_g, E, e};          // read in full before the optional update below
     double trace = 0, bb = 0;
     for (int r = 0; r < K; ++r) {
         const int k = K - r;
@@ -76,7 +78,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
         }
         return J;
     };
-    for (int j = 0; j < D; ++j) { w0[j] = clipw(w_g[j * E + e]); wb[j] = w0[j]; }
+    for (int j = 0; j < D; ++j) { w0[j] = clipw(winit_g ? winit_g[j] : w_g[j * E + e]); wb[j] = w0[j]; }
     double Jbest = cost(w0);
 
     if (K >= 1 && trace > 0 && isfinite(trace) && isfinite(bb)) {
@@ -173,6 +175,239 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
         }
     }
     for (int j = 0; j < D; ++j) w_g[j * E + e] = wb[j];
+    if (update_prev)                                   // controllers.py:1471: w_critic_prev = w_critic
+        for (int j = 0; j < D; ++j) wprev_g[j * E + e] = wb[j];
+    if (Jc_out) Jc_out[e] = Jbest;
+}
+
+
+// ---- fast path: K = Ncritic - 1 <= 3 rows (every preset) ------------------------------------------------
+// Same algorithm, laid out for the register file: every critic feature is a product u[a] * u[b] of two entries
+// of the row vector u = [chi, 1] (quad-mix: [observation, action, 1]) with compile-time (a, b), so the three
+// rows are kept as 3 x (p+1) registers and the features are recomputed on the fly (one DMUL each) instead of
+// being stored -- the generic kernel's K x D matrix in local memory thrashed L1 (528 ms for 1 M fits of the
+// 28-weight 'quadratic' critic).  The two D-vectors (prox centre, trial point) live in shared memory,
+// [weight][thread], conflict-free.  One Newton iteration = two unrolled passes over the D weights.
+template <int CS, int N, int M>
+struct FeatIdx {
+    static constexpr int P = N + M;
+    // entry j of phi = u[a(j)] * u[b(j)]; u[P] == 1
+    __host__ __device__ static constexpr int a(int j)
+    {
+        if (CS == RCG_CRITIC_QUAD_LIN || CS == RCG_CRITIC_QUADRATIC) {
+            int k = 0;
+            for (int i = 0; i < P; ++i)
+                for (int l = i; l < P; ++l) { if (k == j) return i; ++k; }
+            return j - k;                                   // linear tail of quad-lin: chi[j - k] * 1
+        } else if (CS == RCG_CRITIC_QUAD_NOMIX) {
+            return j;
+        } else {
+            if (j < N) return j;
+            if (j < N + N * M) return (j - N) / M;
+            return N + (j - N - N * M);
+        }
+    }
+    __host__ __device__ static constexpr int b(int j)
+    {
+        if (CS == RCG_CRITIC_QUAD_LIN || CS == RCG_CRITIC_QUADRATIC) {
+            int k = 0;
+            for (int i = 0; i < P; ++i)
+                for (int l = i; l < P; ++l) { if (k == j) return l; ++k; }
+            return P;
+        } else if (CS == RCG_CRITIC_QUAD_NOMIX) {
+            return j;
+        } else {
+            if (j < N) return j;
+            if (j < N + N * M) return N + (j - N) % M;
+            return N + (j - N - N * M);
+        }
+    }
+};
+
+template <int J, int END, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (J < END) {
+        f(std::integral_constant<int, J>{});
+        static_for<J + 1, END>(f);
+    }
+}
+
+template <int N, int M, int CS, bool RDIAG>
+__global__ void __launch_bounds__(128)
+critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const double *__restrict__ obs_buf,
+                   const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
+                   const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
+                   double mu_rel, int max_outer, int max_newton, int update_prev, double *__restrict__ Jc_out)
+{
+    constexpr int D = dim_critic_c(CS, N, M), P = N + M;
+    using FI = FeatIdx<CS, N, M>;
+    extern __shared__ double fit_smem[];                   // [2][D][blockDim.x]
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (mask && mask[e] == 0) return;
+    const int K = O.Ncritic - 1;
+    double *wa = fit_smem + threadIdx.x;                   // prox centre / best iterate
+    double *wbuf = fit_smem + (size_t)D * blockDim.x + threadIdx.x;
+    const int ws = blockDim.x;
+
+    double u[3][P + 1], b[3];
+    const GlobalWF<double> wp{wprev_g, E, e};
+    double trace = 0, bb = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int i = 0; i <= P; ++i) u[r][i] = 0.0;
+        b[r] = 0.0;
+        if (r < K) {
+            const int k = K - r;
+            double op[N], on[N], ap[M], an[M];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                op[i] = obs_buf[((int64_t)(k - 1) * N + i) * E + e];
+                on[i] = obs_buf[((int64_t)k * N + i) * E + e];
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                ap[j] = act_buf[((int64_t)(k - 1) * M + j) * E + e];
+                an[j] = act_buf[((int64_t)k * M + j) * E + e];
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) u[r][i] = (CS == RCG_CRITIC_QUAD_MIX) ? op[i] : op[i] - O.target[i];
+#pragma unroll
+            for (int j = 0; j < M; ++j) u[r][N + j] = ap[j];
+            u[r][P] = 1.0;
+            b[r] = O.gamma * critic<double, N, M, CS>(O, on, an, wp) + stage_obj<double, N, M, RDIAG>(O, op, ap);
+        }
+        bb = fma(b[r], b[r], bb);
+    }
+    static_for<0, D>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double ph = u[r][FI::a(j)] * u[r][FI::b(j)];
+            trace = fma(ph, ph, trace);
+        }
+    });
+    auto clipw = [&](double z) { return z < lo ? lo : (z > hi ? hi : z); };
+    // Each pass recomputes the feature products from u.  Without this fence the compiler keeps all 3*D products
+    // alive across the passes (common-subexpression elimination): 255 registers and kilobytes of spills for the
+    // 28- and 35-weight critics.  The empty asm makes the rows opaque per pass at no run-time cost.
+    auto fence_rows = [&]() {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int i = 0; i <= P; ++i) asm volatile("" : "+d"(u[r][i]));
+    };
+    // start point and its cost
+    fence_rows();
+    double r0 = -b[0], r1 = -b[1], r2 = -b[2];
+    static_for<0, D>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const double w = clipw(winit_g ? winit_g[j] : w_g[j * E + e]);
+        wa[j * ws] = w;
+        r0 = fma(u[0][FI::a(j)] * u[0][FI::b(j)], w, r0);
+        r1 = fma(u[1][FI::a(j)] * u[1][FI::b(j)], w, r1);
+        r2 = fma(u[2][FI::a(j)] * u[2][FI::b(j)], w, r2);
+    });
+    double Jbest = 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
+
+    if (K >= 1 && trace > 0 && isfinite(trace) && isfinite(bb)) {
+        const double mu = mu_rel * trace / K;
+        for (int outer = 0; outer < max_outer; ++outer) {
+            double l0 = 0, l1 = 0, l2 = 0;
+            for (int it = 0; it < max_newton; ++it) {
+                // pass A: residual F, Gram matrix H of the free columns, dual value and clip pattern at lam
+                double F0 = mu * l0 - b[0], F1 = mu * l1 - b[1], F2 = mu * l2 - b[2];
+                double H00 = mu, H10 = 0, H11 = mu, H20 = 0, H21 = 0, H22 = mu;
+                double D0 = fma(0.5 * mu, l0 * l0 + l1 * l1 + l2 * l2, -(b[0] * l0 + b[1] * l1 + b[2] * l2));
+                uint64_t lowA = 0, highA = 0;
+                fence_rows();
+                static_for<0, D>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const double p0 = u[0][FI::a(j)] * u[0][FI::b(j)], p1 = u[1][FI::a(j)] * u[1][FI::b(j)],
+                                 p2 = u[2][FI::a(j)] * u[2][FI::b(j)];
+                    const double z = fma(p2, l2, fma(p1, l1, fma(p0, l0, wa[j * ws])));
+                    const bool below = !(z > lo), above = !(z < hi);
+                    const double w = below ? lo : (above ? hi : z);
+                    D0 += below ? lo * z - 0.5 * lo * lo : (above ? hi * z - 0.5 * hi * hi : 0.5 * z * z);
+                    lowA |= (uint64_t)below << j;
+                    highA |= (uint64_t)above << j;
+                    F0 = fma(p0, w, F0); F1 = fma(p1, w, F1); F2 = fma(p2, w, F2);
+                    if (!below && !above) {
+                        H00 = fma(p0, p0, H00); H10 = fma(p1, p0, H10); H11 = fma(p1, p1, H11);
+                        H20 = fma(p2, p0, H20); H21 = fma(p2, p1, H21); H22 = fma(p2, p2, H22);
+                    }
+                });
+                // Cholesky of the 3 x 3 system, solve H d = -F
+                if (!(H00 > 0)) break;
+                const double c00 = sqrt(H00), c10 = H10 / c00, c20 = H20 / c00;
+                const double t11 = H11 - c10 * c10;
+                if (!(t11 > 0)) break;
+                const double c11 = sqrt(t11), c21 = (H21 - c20 * c10) / c11;
+                const double t22 = H22 - c20 * c20 - c21 * c21;
+                if (!(t22 > 0)) break;
+                const double c22 = sqrt(t22);
+                const double y0 = -F0 / c00, y1 = (-F1 - c10 * y0) / c11, y2 = (-F2 - c20 * y0 - c21 * y1) / c22;
+                const double d2 = y2 / c22, d1 = (y1 - c21 * d2) / c11, d0 = (y0 - c10 * d1 - c20 * d2) / c00;
+                const double slope = F0 * d0 + F1 * d1 + F2 * d2;
+                if (!(slope < 0)) break;
+                // pass B: Armijo backtracking on the dual; the clip pattern of the trial point comes for free
+                double a = 1.0;
+                bool ok = false, same = false;
+                for (int ls = 0; ls < 40; ++ls) {
+                    const double t0 = fma(a, d0, l0), t1 = fma(a, d1, l1), t2 = fma(a, d2, l2);
+                    double Dt = fma(0.5 * mu, t0 * t0 + t1 * t1 + t2 * t2, -(b[0] * t0 + b[1] * t1 + b[2] * t2));
+                    uint64_t lowB = 0, highB = 0;
+                    fence_rows();
+                    static_for<0, D>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const double p0 = u[0][FI::a(j)] * u[0][FI::b(j)], p1 = u[1][FI::a(j)] * u[1][FI::b(j)],
+                                     p2 = u[2][FI::a(j)] * u[2][FI::b(j)];
+                        const double z = fma(p2, t2, fma(p1, t1, fma(p0, t0, wa[j * ws])));
+                        const bool below = !(z > lo), above = !(z < hi);
+                        Dt += below ? lo * z - 0.5 * lo * lo : (above ? hi * z - 0.5 * hi * hi : 0.5 * z * z);
+                        lowB |= (uint64_t)below << j;
+                        highB |= (uint64_t)above << j;
+                    });
+                    if (Dt <= D0 + 1e-4 * a * slope + 1e-14 * fabs(D0)) {
+                        ok = true;
+                        l0 = t0; l1 = t1; l2 = t2;
+                        same = (a == 1.0) && lowB == lowA && highB == highA;
+                        break;
+                    }
+                    a *= 0.5;
+                }
+                if (!ok || same) break;                    // full step inside one linear piece: exact
+            }
+            // prox step result, its cost
+            double q0 = -b[0], q1 = -b[1], q2 = -b[2];
+            fence_rows();
+            static_for<0, D>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const double p0 = u[0][FI::a(j)] * u[0][FI::b(j)], p1 = u[1][FI::a(j)] * u[1][FI::b(j)],
+                             p2 = u[2][FI::a(j)] * u[2][FI::b(j)];
+                const double w = clipw(fma(p2, l2, fma(p1, l1, fma(p0, l0, wa[j * ws]))));
+                wbuf[j * ws] = w;
+                q0 = fma(p0, w, q0); q1 = fma(p1, w, q1); q2 = fma(p2, w, q2);
+            });
+            const double Jn = 0.5 * (q0 * q0 + q1 * q1 + q2 * q2);
+            if (!(Jn < Jbest)) break;
+            const bool improved = Jn < Jbest * (1 - 1e-3);
+            Jbest = Jn;
+            static_for<0, D>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                wa[j * ws] = wbuf[j * ws];
+            });
+            if (!improved || Jn <= 1e-24 * bb) break;
+        }
+    }
+    static_for<0, D>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const double w = wa[j * ws];
+        w_g[j * E + e] = w;
+        if (update_prev) wprev_g[j * E + e] = w;           // controllers.py:1471
+    });
     if (Jc_out) Jc_out[e] = Jbest;
 }
 
@@ -184,8 +419,9 @@ static bool fit_rdiag(const rcg_objective_t *obj, int p)
 }  // namespace rcg
 
 extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs_buf,
-                              const double *act_buf, const double *w_prev, double w_min, double w_max, double *w,
-                              const int32_t *mask, int32_t max_outer, double *Jc_out, void *stream)
+                              const double *act_buf, double *w_prev, double w_min, double w_max, const double *w_init,
+                              double *w, const int32_t *mask, int32_t max_outer, int32_t update_prev, double *Jc_out,
+                              void *stream)
 {
     using namespace rcg;
     RCG_REQUIRE(obj && obs_buf && act_buf && w_prev && w, "rcg_critic_fit: null argument");
@@ -205,11 +441,22 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     const int outer = max_outer > 0 ? max_outer : 8;
     const double mu_rel = 1e-10;
     const int newton = 20;
+    const bool fast = obj->Ncritic - 1 <= 3;
+#define FIT3(NN, MM, CS, RD)                                                                                              \
+    {                                                                                                                     \
+        auto kern = critic_fit3_kernel<NN, MM, CS, RD>;                                                                   \
+        const size_t smem = (size_t)2 * dim_critic_c(CS, NN, MM) * 128 * sizeof(double);                                  \
+        static bool configured = false;                                                                                   \
+        if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; } \
+        kern<<<grid, 128, smem, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mask, mu_rel, outer, newton,  \
+                                     update_prev, Jc_out);                                                                \
+    }
 #define FIT(NN, MM, CS)                                                                                                   \
-    if (rd) critic_fit_kernel<NN, MM, CS, true><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w, mask, \
-                                                                     mu_rel, outer, newton, Jc_out);                       \
-    else critic_fit_kernel<NN, MM, CS, false><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w, mask,  \
-                                                                   mu_rel, outer, newton, Jc_out);
+    if (fast) { if (rd) FIT3(NN, MM, CS, true) else FIT3(NN, MM, CS, false) }                                             \
+    else if (rd) critic_fit_kernel<NN, MM, CS, true><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, \
+                                                                     mask, mu_rel, outer, newton, update_prev, Jc_out);                       \
+    else critic_fit_kernel<NN, MM, CS, false><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w,  \
+                                                                   mask, mu_rel, outer, newton, update_prev, Jc_out);
 #define FITCS(NN, MM)                  \
     switch (obj->critic_struct) {      \
     case 0: FIT(NN, MM, 0) break;      \
@@ -220,5 +467,6 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     if (n == 3) { FITCS(3, 2) } else if (n == 5) { FITCS(5, 2) } else { FITCS(2, 1) }
 #undef FITCS
 #undef FIT
+#undef FIT3
     return check_launch("rcg_critic_fit");
 }

@@ -47,14 +47,37 @@ struct ObjDev {
 //    y^5 * x - 1 and the term for 0.2 != 1/5: correctly rounded (up to astronomically rare cases).
 // Translation units that need bit-reproducibility (rk45.cu) are compiled with -fmad=false, so the
 // plain * and + below are never contracted; the fma() calls are explicit.
+// Coefficients in constant memory: as literals every use costs two UMOVs to materialise the 64-bit immediate
+// (the RK45 kernels inline det_sincos seven times per step attempt).
+struct DetSincosC {
+    double two_over_pi, P1, P2, P3;
+    double S1, S2, S3, S4, S5, S6;
+    double C1, C2, C3, C4, C5, C6;
+};
+static __constant__ DetSincosC kDSC = {
+    6.36619772367581382433e-01, 1.5707963267948966e+00, 6.123233995736766e-17, -1.4973849048591698e-33,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+    -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,
+    2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
+static __device__ __noinline__ double2 sincos_libm(double x)      // cold path, kept out of line
+{
+    double2 r;
+    sincos(x, &r.x, &r.y);
+    return r;
+}
+
 __device__ __forceinline__ void det_sincos(double x, double *sn, double *cs)
 {
     if (!(fabs(x) <= 1.0e5)) {                  // huge, inf, NaN: outside the regime of the path
-        sincos(x, sn, cs);
+        const double2 r = sincos_libm(x);
+        *sn = r.x;
+        *cs = r.y;
         return;
     }
-    const double q = rint(__dmul_rn(x, 6.36619772367581382433e-01));
-    const double P1 = 1.5707963267948966e+00, P2 = 6.123233995736766e-17, P3 = -1.4973849048591698e-33;
+    const double q = rint(__dmul_rn(x, kDSC.two_over_pi));
+    const double P1 = kDSC.P1, P2 = kDSC.P2, P3 = kDSC.P3;
     const double ph = __dmul_rn(q, P1), pl = fma(q, P1, -ph);
     const double r = __dadd_rn(x, -ph);
     double t = fma(-q, P2, -pl);
@@ -62,12 +85,8 @@ __device__ __forceinline__ void det_sincos(double x, double *sn, double *cs)
     const double rh = __dadd_rn(r, t);
     const double bb = __dadd_rn(rh, -r);
     const double rl = __dadd_rn(__dadd_rn(r, -__dadd_rn(rh, -bb)), __dadd_rn(t, -bb));     // two-sum
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double S1 = kDSC.S1, S2 = kDSC.S2, S3 = kDSC.S3, S4 = kDSC.S4, S5 = kDSC.S5, S6 = kDSC.S6;
+    const double C1 = kDSC.C1, C2 = kDSC.C2, C3 = kDSC.C3, C4 = kDSC.C4, C5 = kDSC.C5, C6 = kDSC.C6;
     const double z = __dmul_rn(rh, rh), w = __dmul_rn(z, z), v = __dmul_rn(z, rh);
     // every product and sum rounded separately (intrinsics: immune to -fmad contraction)
     const double ps = __dadd_rn(__dadd_rn(S2, __dmul_rn(z, __dadd_rn(S3, __dmul_rn(z, S4)))),

@@ -17,35 +17,47 @@ struct SolverDev {
     double t_bound, max_step, rtol, atol;
 };
 
-// scipy rk.py:538-553 (class RK45)
-#define RK_A10 (1.0 / 5)
-#define RK_A20 (3.0 / 40)
-#define RK_A21 (9.0 / 40)
-#define RK_A30 (44.0 / 45)
-#define RK_A31 (-56.0 / 15)
-#define RK_A32 (32.0 / 9)
-#define RK_A40 (19372.0 / 6561)
-#define RK_A41 (-25360.0 / 2187)
-#define RK_A42 (64448.0 / 6561)
-#define RK_A43 (-212.0 / 729)
-#define RK_A50 (9017.0 / 3168)
-#define RK_A51 (-355.0 / 33)
-#define RK_A52 (46732.0 / 5247)
-#define RK_A53 (49.0 / 176)
-#define RK_A54 (-5103.0 / 18656)
-#define RK_B0 (35.0 / 384)
-#define RK_B1 (0.0)
-#define RK_B2 (500.0 / 1113)
-#define RK_B3 (125.0 / 192)
-#define RK_B4 (-2187.0 / 6784)
-#define RK_B5 (11.0 / 84)
-#define RK_E0 (-71.0 / 57600)
-#define RK_E1 (0.0)
-#define RK_E2 (71.0 / 16695)
-#define RK_E3 (-71.0 / 1920)
-#define RK_E4 (17253.0 / 339200)
-#define RK_E5 (-22.0 / 525)
-#define RK_E6 (1.0 / 40)
+// scipy rk.py:538-553 (class RK45).  The coefficients sit in constant memory so that every DMUL takes its
+// coefficient as a c[bank][offset] operand: as literals each use costs two UMOVs to materialise the 64-bit
+// immediate (21 % of the issued instructions in the first profile of this kernel).
+struct Tableau {
+    double a10, a20, a21, a30, a31, a32, a40, a41, a42, a43, a50, a51, a52, a53, a54;
+    double b0, b1, b2, b3, b4, b5;
+    double e0, e1, e2, e3, e4, e5, e6;
+};
+static __constant__ Tableau kRK = {
+    1.0 / 5, 3.0 / 40, 9.0 / 40, 44.0 / 45, -56.0 / 15, 32.0 / 9, 19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561,
+    -212.0 / 729, 9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656,
+    35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84,
+    -71.0 / 57600, 0.0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+#define RK_A10 kRK.a10
+#define RK_A20 kRK.a20
+#define RK_A21 kRK.a21
+#define RK_A30 kRK.a30
+#define RK_A31 kRK.a31
+#define RK_A32 kRK.a32
+#define RK_A40 kRK.a40
+#define RK_A41 kRK.a41
+#define RK_A42 kRK.a42
+#define RK_A43 kRK.a43
+#define RK_A50 kRK.a50
+#define RK_A51 kRK.a51
+#define RK_A52 kRK.a52
+#define RK_A53 kRK.a53
+#define RK_A54 kRK.a54
+#define RK_B0 kRK.b0
+#define RK_B1 kRK.b1
+#define RK_B2 kRK.b2
+#define RK_B3 kRK.b3
+#define RK_B4 kRK.b4
+#define RK_B5 kRK.b5
+#define RK_E0 kRK.e0
+#define RK_E1 kRK.e1
+#define RK_E2 kRK.e2
+#define RK_E3 kRK.e3
+#define RK_E4 kRK.e4
+#define RK_E5 kRK.e5
+#define RK_E6 kRK.e6
 
 // One scipy RK45.step() for one lane.  Returns false if the step failed (TOO_SMALL_STEP).
 // On success t, h_abs, y, f are advanced and *attempts holds the number of rk_step calls.
@@ -139,7 +151,7 @@ __device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDe
 // CTRL = false: Simulator.sim_step (one accepted step per running lane).
 // CTRL = true : the fused loop body between two controller samples (see rcg_rk45_advance).
 template <typename T, int SYS, bool CTRL, bool RDIAG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
             const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,

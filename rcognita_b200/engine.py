@@ -36,7 +36,8 @@ class ClosedLoopEngine:
     def __init__(self, system, state_init, candidates, *, pars=(), ctrl_bnds=None, mode="MPC", Nactor=6, dt=0.01,
                  pred_step_size=None, t0=0.0, t1=10.0, first_step=1e-6, atol=1e-5, rtol=1e-3, gamma=1.0, R1=None,
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
-                 w_critic=None, action_init=(), device=None, dtype=torch.float64):
+                 w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
+                 buffer_size=10, critic_period=None):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -54,7 +55,7 @@ class ClosedLoopEngine:
         self.sol = _C.make_solver(t1, dt / 2, rtol, atol)
         self.obj = _C.make_objective(n, m, mode=mode, Nactor=Nactor,
                                      pred_step_size=dt if pred_step_size is None else pred_step_size, gamma=gamma,
-                                     critic_struct=critic_struct, stage_obj_struct=stage_obj_struct, R1=R1, R2=R2,
+                                     Ncritic=Ncritic, buffer_size=buffer_size, critic_struct=critic_struct, stage_obj_struct=stage_obj_struct, R1=R1, R2=R2,
                                      observation_target=observation_target)
         with torch.cuda.device(self.device):
             x0 = _as_dev(state_init, dtype, self.device)
@@ -80,9 +81,20 @@ class ClosedLoopEngine:
                 self.cand = cand.permute(2, 0, 1).reshape(L, E * self.C).contiguous()   # [L, E*C]
             else:
                 raise ValueError("candidates must be [C, N*m] or [E, C, N*m]")
-            if mode != "MPC":
+            self.critic_fit = bool(critic_fit) and mode != "MPC"
+            self.critic_period = float(dt if critic_period is None else critic_period)
+            self.buffer_size = int(buffer_size)
+            self.w_bounds = (-1e3, 1e3) if critic_struct in ("quad-lin", "quad-mix") else (0.0, 1e3)   # controllers.py:1024-1039
+            if self.critic_fit:
+                # CtrlOptPred with its critic: FIFO buffers, refit every critic_period, w_critic_init = ones
+                if dtype != torch.float64:
+                    raise ValueError("critic fitting runs in fp64")
+                dimc = _C.dim_critic(critic_struct, n, m)
+                self.w = torch.ones((dimc, E), dtype=dtype, device=self.device)
+                self.w_per_env = True
+            elif mode != "MPC":
                 if w_critic is None:
-                    raise ValueError("w_critic is required for RQL/SQL")
+                    raise ValueError("w_critic is required for RQL/SQL (or critic_fit=True)")
                 w = _as_dev(w_critic, dtype, self.device)
                 dimc = _C.dim_critic(critic_struct, n, m)
                 if w.dim() == 1:
@@ -100,21 +112,39 @@ class ClosedLoopEngine:
 
     def _alloc(self):
         n, m, E, dt, dev = self.n, self.m, self.E, self.dtype, self.device
-        self.y = torch.empty((n, E), dtype=dt, device=dev)
-        self.f = torch.empty((n, E), dtype=dt, device=dev)
-        self.state_sys = torch.empty((n, E), dtype=dt, device=dev)
-        self.action = torch.empty((m, E), dtype=dt, device=dev)
-        self.t = torch.empty((E,), dtype=torch.float64, device=dev)
-        self.h_abs = torch.empty((E,), dtype=torch.float64, device=dev)
-        self.ctrl_clock = torch.empty((E,), dtype=torch.float64, device=dev)
-        self.accum = torch.empty((E,), dtype=dt, device=dev)
-        self.status = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.nfev = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.nsteps = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.nsamples = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.sample_flag = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.argmin = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.Jmin = torch.empty((E,), dtype=dt, device=dev)
+        # All per-lane state lives in ONE device allocation (fields are typed views at 256-byte-aligned offsets):
+        # the lane fields first, the per-step results after them, so that a caller that owns its environments in
+        # host memory moves the whole state with one copy in (lane part) and one copy out (lane + result part).
+        es = torch.empty((), dtype=dt).element_size()
+        spec = [("y", (n, E), dt), ("f", (n, E), dt), ("state_sys", (n, E), dt), ("action", (m, E), dt),
+                ("t", (E,), torch.float64), ("h_abs", (E,), torch.float64), ("ctrl_clock", (E,), torch.float64),
+                ("accum", (E,), dt), ("status", (E,), torch.int32),
+                # results
+                ("nfev", (E,), torch.int32), ("nsteps", (E,), torch.int32), ("nsamples", (E,), torch.int32),
+                ("sample_flag", (E,), torch.int32), ("argmin", (E,), torch.int32), ("Jmin", (E,), dt)]
+        off, layout = 0, []
+        for name, shape, dtype_ in spec:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype_).element_size()
+            layout.append((name, shape, dtype_, off, nbytes))
+            off = (off + nbytes + 255) // 256 * 256
+            if name == "status":
+                self._lane_bytes = off
+        self._blob_bytes = off
+        self._layout = layout
+        self._blob = torch.empty((off,), dtype=torch.uint8, device=dev)
+        for name, shape, dtype_, o, nbytes in layout:
+            setattr(self, name, self._blob[o:o + nbytes].view(dtype_).view(shape))
+        del es
+        if self.critic_fit:
+            dimc = self.w.shape[0]
+            self.obs_buf = torch.empty((self.buffer_size, n, E), dtype=dt, device=dev)
+            self.act_buf = torch.empty((self.buffer_size, m, E), dtype=dt, device=dev)
+            self.w_prev = torch.empty((dimc, E), dtype=dt, device=dev)
+            self.w_init = torch.ones((dimc,), dtype=dt, device=dev)
+            self.critic_clock = torch.empty((E,), dtype=torch.float64, device=dev)
+            self.critic_flag = torch.empty((E,), dtype=torch.int32, device=dev)
+            self.Jc = torch.empty((E,), dtype=dt, device=dev)
+            self.nfits = torch.empty((E,), dtype=torch.int32, device=dev)
 
     def reset(self):
         """Documented intent of ``Simulator.reset`` + ``CtrlOptPred.reset``: restore y0, t0,
@@ -133,6 +163,15 @@ class ClosedLoopEngine:
         self.sample_flag.zero_()
         self.argmin.fill_(-1)
         self.Jmin.fill_(float("nan"))
+        if self.critic_fit:
+            self.obs_buf.zero_()                           # controllers.py:980-981
+            self.act_buf.zero_()
+            self.w.fill_(1.0)                              # w_critic_prev = w_critic_init = ones (:1041-1042)
+            self.w_prev.fill_(1.0)
+            self.critic_clock.fill_(self.t0)
+            self.critic_flag.zero_()
+            self.Jc.zero_()
+            self.nfits.zero_()
         ops.rhs(self.sysd, self.y, self.action, out=self.f)               # RK45.__init__: f = fun(t0, y0)
         self.intervals = 0
         self._first_done = False
@@ -169,7 +208,23 @@ class ClosedLoopEngine:
             ev[1].record()
             self.actor_events.append(ev)
 
+    def _critic_update(self):
+        """RQL/SQL part of compute_action for the sampling lanes (controllers.py:1455-1479): push (observation,
+        previous action) into the FIFO buffers, test the critic clock, refit the critic where it fired (those
+        lanes also remember the new weights as w_critic_prev), fall back to w_critic_prev elsewhere."""
+        n, m = self.n, self.m
+        ops.push_buffers(n, m, self.obs_buf, self.act_buf, self.y, self.action, mask=self.sample_flag)
+        ops.ctrl_sample(self.t, self.critic_clock, self.critic_period, in_mask=self.sample_flag, mask_out=self.critic_flag)
+        # every fit starts from w_critic_init = ones (:1264); refit lanes store the result as w_critic and
+        # w_critic_prev (:1470-1471).  Sampling lanes whose critic clock did not fire take w_critic_prev (:1479),
+        # which already equals their w_critic (both were written by their last refit, or are still ones).
+        ops.critic_fit(self.obj, n, m, self.obs_buf, self.act_buf, self.w_prev, self.w_bounds[0], self.w_bounds[1],
+                       self.w, w_init=self.w_init, mask=self.critic_flag, update_prev=True, Jc_out=self.Jc)
+        self.nfits += self.critic_flag
+
     def _actor_launch(self):
+        if self.critic_fit:
+            self._critic_update()
         ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
                        w_critic=self.w, w_per_env=self.w_per_env, mask=self.sample_flag, want_J=False,
                        argmin_out=self.argmin, Jmin_out=self.Jmin, action_out=self.action, accum=self.accum,
@@ -211,35 +266,40 @@ class ClosedLoopEngine:
             "status": self.status.cpu().numpy(), "nfev": self.nfev.cpu().numpy(),
             "nsteps": self.nsteps.cpu().numpy(), "nsamples": self.nsamples.cpu().numpy(),
             "argmin": self.argmin.cpu().numpy(), "Jmin": self.Jmin.cpu().numpy(),
+            **({"w_critic": self.w.t().contiguous().cpu().numpy(), "nfits": self.nfits.cpu().numpy(),
+                "Jc": self.Jc.cpu().numpy()} if self.critic_fit else {}),
         }
 
 
-    # -- host-buffer form of one control interval: the lane state lives in PINNED HOST memory
-    #    between calls (a caller that owns its environments on the host, like the reference's
-    #    Python loop does); every call copies it in, runs the two kernels and copies it back.
-    LANE_FIELDS = ("y", "f", "t", "h_abs", "status", "action", "ctrl_clock", "state_sys", "accum")
-    RESULT_FIELDS = ("argmin", "Jmin", "sample_flag", "nsteps", "nfev", "nsamples")
+    # -- host-buffer form of one control interval: the lane state lives in PINNED HOST memory between calls (a
+    #    caller that owns its environments on the host, like the reference's Python loop does); every call copies
+    #    it in, runs the two kernels and copies state + results back.
+    LANE_FIELDS = ("y", "f", "state_sys", "action", "t", "h_abs", "ctrl_clock", "accum", "status")
+    RESULT_FIELDS = ("nfev", "nsteps", "nsamples", "sample_flag", "argmin", "Jmin")
 
     def make_host_state(self):
-        """Pinned host mirrors of the lane state (initialised from the current device state)."""
+        """Pinned host mirror of the lane-state allocation (initialised from the current device state): a dict of
+        typed views per field plus the raw byte buffer under "_blob"."""
         if not self._first_done:
             self._first_step()
-        return {k: getattr(self, k).cpu().pin_memory() for k in self.LANE_FIELDS + self.RESULT_FIELDS}
+        blob = torch.empty((self._blob_bytes,), dtype=torch.uint8).pin_memory()
+        blob.copy_(self._blob)
+        host = {"_blob": blob}
+        for name, shape, dtype_, o, nbytes in self._layout:
+            host[name] = blob[o:o + nbytes].view(dtype_).view(shape)
+        return host
 
     def run_interval_host(self, host, sync=True):
-        """H2D lane state -> rk45_advance + actor_cost -> D2H lane state and results, all on the current
-        stream; returns the bytes moved (h2d, d2h).  With ``sync`` the host buffers are valid on return."""
-        h2d = d2h = 0
-        for k in self.LANE_FIELDS:
-            getattr(self, k).copy_(host[k], non_blocking=True)
-            h2d += host[k].numel() * host[k].element_size()
+        """H2D lane state (one copy) -> rk45_advance + actor_cost -> D2H lane state and results (one copy), all
+        on the current stream; returns the bytes moved (h2d, d2h).  With ``sync`` the host buffers are valid on
+        return."""
+        nl = self._lane_bytes
+        self._blob[:nl].copy_(host["_blob"][:nl], non_blocking=True)
         self.run_interval()
-        for k in self.LANE_FIELDS + self.RESULT_FIELDS:
-            host[k].copy_(getattr(self, k), non_blocking=True)
-            d2h += host[k].numel() * host[k].element_size()
+        host["_blob"].copy_(self._blob, non_blocking=True)
         if sync:
             torch.cuda.current_stream().synchronize()
-        return h2d, d2h
+        return nl, self._blob_bytes
 
 
 class HostStagedLoop:

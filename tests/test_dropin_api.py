@@ -272,12 +272,15 @@ def test_critic_fit_reaches_reference_slsqp_cost(rb):
         ob = torch.as_tensor(np.array(c["obs_buf"]), device="cuda")[:, :, None].expand(-1, -1, E).contiguous()
         ac = torch.as_tensor(np.array(c["act_buf"]), device="cuda")[:, :, None].expand(-1, -1, E).contiguous()
         wp = torch.as_tensor(np.array(c["w_prev"]), device="cuda")[:, None].expand(-1, E).contiguous()
-        w = torch.as_tensor(np.array(c["w_init"]), device="cuda")[:, None].expand(-1, E).contiguous()
+        w = torch.full((len(c["w_init"]), E), 7.0, dtype=torch.float64, device="cuda")
+        w_init = torch.as_tensor(np.array(c["w_init"]), device="cuda")
         mask = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
         Jc = torch.full((E,), -1.0, dtype=torch.float64, device="cuda")
-        ops.critic_fit(obj, n, m, ob, ac, wp, c["Wmin"], c["Wmax"], w, mask=mask, Jc_out=Jc)
+        wp0 = wp.clone()
+        ops.critic_fit(obj, n, m, ob, ac, wp, c["Wmin"], c["Wmax"], w, w_init=w_init, mask=mask, Jc_out=Jc)
+        assert torch.equal(wp, wp0)                                                          # update_prev off
         wh = w.cpu().numpy()
-        assert np.array_equal(wh[:, 1], np.array(c["w_init"])) and Jc[1].item() == -1.0      # masked lane untouched
+        assert np.all(wh[:, 1] == 7.0) and Jc[1].item() == -1.0                              # masked lane untouched
         assert np.array_equal(wh[:, 0], wh[:, 2])
         assert wh.min() >= c["Wmin"] and wh.max() <= c["Wmax"]
         oc = oracle.make_ctrl(n, m, mode="RQL", Nactor=4, gamma=c["gamma"], critic_struct=c["critic_struct"],
@@ -289,3 +292,58 @@ def test_critic_fit_reaches_reference_slsqp_cost(rb):
         if not J_fit <= c["J_ref"] * (1 + 1e-6) + 1e-9 * c["J_init"]:
             worse.append((c["system"], c["critic_struct"], c["regime"], c["gamma"], J_fit, c["J_ref"]))
     assert not worse, worse
+
+
+@gpu
+@pytest.mark.parametrize("name,mode,cs,N,t1", [("2tank", "SQL", "quad-nomix", 8, 4.0), ("3wrobot", "RQL", "quadratic", 10, 0.25),
+                                               ("3wrobotNI", "RQL", "quad-mix", 5, 0.3)])
+def test_engine_with_critic_fit_equals_class_loop(rb, name, mode, cs, N, t1):
+    """BASELINE configs 3/4 (RQL / SQL with critic buffer fitting): the fused ClosedLoopEngine (rk45_advance +
+    push_buffers + critic_fit + actor_cost per control interval) and the reference-style loop over the drop-in
+    classes take identical decisions: same step counts, times, actions, states, returns and critic weights."""
+    from rcognita_b200.controllers import ctrl_selector
+    from rcognita_b200.engine import ClosedLoopEngine
+    n, m = DIMS[name]
+    cfg = PRESET[name]
+    E = 40
+    rng = np.random.default_rng(21)
+    box = {"3wrobotNI": ([-5, -5, -3], [5, 5, 3]), "3wrobot": ([-5, -5, -3, -1, -1], [5, 5, 3, 1, 1]), "2tank": ([-2, -2], [2, 2])}[name]
+    x0 = rng.uniform(box[0], box[1], size=(E, n))
+    b = np.array(cfg["bnds"], dtype=float)
+    cand = rng.uniform(np.tile(b[:, 0], N), np.tile(b[:, 1], N), size=(48, N * m))
+    a_init = [0.5] if name == "2tank" else []
+    eng = ClosedLoopEngine(name, x0, cand, pars=cfg["pars"], ctrl_bnds=cfg["bnds"], mode=mode, Nactor=N, dt=cfg["dt"],
+                           pred_step_size=cfg["dt"] * cfg["psm"], t1=t1, R1=cfg["R1_diag"], observation_target=cfg["target"],
+                           critic_struct=cs, critic_fit=True, Ncritic=4, buffer_size=10, action_init=a_init)
+    eng.run()
+    got = eng.results()
+    assert np.all(got["nfits"] == got["nsamples"]) and got["nfits"].min() >= 5       # critic_period == sampling_time
+    lo_w = -1e3 if cs in ("quad-lin", "quad-mix") else 0.0
+    assert got["w_critic"].min() >= lo_w and got["w_critic"].max() <= 1e3 and np.any(got["w_critic"] != 1.0)
+
+    my_sys, ctrl, sim = build_objects(rb, name, mode, N, torch.as_tensor(x0, device="cuda"), t1, cand, critic_struct=cs,
+                                      action_init=a_init)
+    nsteps = torch.zeros(E, dtype=torch.int64, device="cuda")
+    for _ in range(100000):
+        running = torch.as_tensor([s == "running" for s in sim.ODE_solver.status], device="cuda")
+        if not bool(running.any()):
+            break
+        sim.sim_step()
+        nsteps += running
+        t, state, observation, state_full = sim.get_sim_step_data()
+        if not bool(running.all()):
+            # finished lanes must not be driven any further (the reference loop breaks at t >= t1)
+            keep_a, keep_acc = ctrl._action_curr.clone(), ctrl._accum.clone()
+        action = ctrl_selector(t, observation, None, None, ctrl, mode)
+        my_sys.receive_action(action)
+        ctrl.receive_sys_state(my_sys._state)
+        ctrl.upd_accum_obj(observation, action)
+        if not bool(running.all()):
+            ctrl._action_curr[:, ~running] = keep_a[:, ~running]
+            ctrl._accum[~running] = keep_acc[~running]
+    assert np.array_equal(nsteps.cpu().numpy(), got["nsteps"])
+    assert np.array_equal(ctrl.num_samples.cpu().numpy(), got["nsamples"])
+    assert np.array_equal(sim._t.cpu().numpy(), got["t"])
+    assert np.array_equal(sim._y.t().cpu().numpy(), got["y"])
+    assert rel_err(ctrl._accum.cpu().numpy(), got["accum"]) <= 1e-12       # fused vs separate accumulation kernels
+    assert np.array_equal(ctrl._w_critic.t().cpu().numpy(), got["w_critic"])

@@ -100,9 +100,36 @@ def rk45_point(system, E, steps_per_launch, iters=5):
             "alg_GBps_if_per_step_io": steps * bytes_step / ms * 1e-6}
 
 
+def critic_fit_point(system, cs, E, iters=5):
+    """rcg_critic_fit on trajectory-like buffers (consecutive samples of a smooth run) for E environments."""
+    p = PRESET[system]
+    n, m = _C.SYS_DIMS[_C.SYS_IDS[system]]
+    obj = _C.make_objective(n, m, mode="RQL", Nactor=4, Ncritic=4, buffer_size=10, critic_struct=cs, R1=p["R1"],
+                            observation_target=p["target"])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = (torch.tensor(v, device="cuda", dtype=torch.float64) for v in BOX[system])
+    x = lo[:, None] + (hi - lo)[:, None] * torch.rand((n, E), device="cuda", dtype=torch.float64, generator=g)
+    v = 0.05 * torch.randn((n, E), device="cuda", dtype=torch.float64, generator=g)
+    obs_buf = torch.stack([x + k * v for k in range(10)])
+    b = torch.tensor(p["bnds"], device="cuda", dtype=torch.float64)
+    a0 = b[:, :1] + (b[:, 1:] - b[:, :1]) * torch.rand((m, E), device="cuda", dtype=torch.float64, generator=g)
+    act_buf = torch.stack([a0 * (1 - 0.02 * k) for k in range(10)])
+    dimc = _C.dim_critic(cs, n, m)
+    w_prev = torch.ones((dimc, E), device="cuda", dtype=torch.float64)
+    w = torch.empty((dimc, E), device="cuda", dtype=torch.float64)
+    w_init = torch.ones((dimc,), device="cuda", dtype=torch.float64)
+    Jc = torch.empty((E,), device="cuda", dtype=torch.float64)
+    lo_w = -1e3 if cs in ("quad-lin", "quad-mix") else 0.0
+    fn = lambda: ops.critic_fit(obj, n, m, obs_buf, act_buf, w_prev, lo_w, 1e3, w, w_init=w_init, Jc_out=Jc)
+    ms = time_it(fn, iters)
+    J0 = ops.critic_cost(obj, n, m, obs_buf, act_buf, w_init[:, None, None].expand(dimc, E, 1).contiguous(), w_prev)[:, 0]
+    return {"kernel": "critic_fit", "system": system, "critic": cs, "dim_critic": dimc, "E": E, "ms": ms,
+            "fits_per_s": E / ms * 1e3, "median_cost_ratio_fit_over_init": float((Jc / J0.clamp_min(1e-300)).median().item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "all"])
+    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "rk45ni", "critic", "all"])
     a = ap.parse_args()
     pts = []
     if a.what in ("headline", "all"):
@@ -124,6 +151,11 @@ def main():
         for system in ("3wrobotNI", "3wrobot", "2tank"):
             for spl in (1, 16, 256):
                 pts.append(lambda s=system, k=spl: rk45_point(s, 1 << 20, k))
+    if a.what == "rk45ni":
+        pts += [lambda: rk45_point("3wrobotNI", 1 << 20, 1, iters=3), lambda: rk45_point("3wrobotNI", 1 << 20, 16, iters=3)]
+    if a.what in ("critic", "all"):
+        pts += [lambda: critic_fit_point("2tank", "quad-nomix", 262144), lambda: critic_fit_point("3wrobot", "quadratic", 1 << 20),
+                lambda: critic_fit_point("3wrobotNI", "quad-lin", 262144)]
     for p in pts:
         print(json.dumps(p()), flush=True)
 
