@@ -117,6 +117,21 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arms (oracle port)
 
+def host_threads():
+    """Host threads available to this process (torchrun exports OMP_NUM_THREADS=1 to its workers, which must not
+    turn the CPU arm into a single-thread run: the oracle's OpenMP loops are sized explicitly with this)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample_envs(args, threads):
+    """Environments in the CPU sample: 256 per thread, rounded up to whole Philox blocks of 1,024."""
+    n = args.cpu_sample_envs or 256 * threads
+    return max(1024, (n + 1023) // 1024 * 1024)
+
+
 def cpu_closed_loop(args, sample_envs, steps, warmup, budget_s=None):
     """Times the CPU restatement of the same closed loop (oracle/, C + OpenMP on all host threads)
     on a bounded sample of the workload: `sample_envs` environments with the same distributions.
@@ -128,13 +143,13 @@ def cpu_closed_loop(args, sample_envs, steps, warmup, budget_s=None):
     c = oracle.make_ctrl(3, 2, mode="MPC", Nactor=args.nactor, pred_step_size=DT, R1=R1_DIAG)
     t1 = max(10.0, (steps + warmup + 16) * 3 * DT)
     batch = oracle.EnvBatch(c, s, x0, cand, ACTION_INIT, DT, 0.0, t1, DT / 2)
-    threads = oracle.num_threads()
+    threads = host_threads() if oracle.num_threads() >= 1 and oracle.has_openmp() else 1
     for _ in range(warmup):
-        batch.interval()
+        batch.interval(threads)
     tot_steps = tot_evals = done = 0
     t_begin = time.perf_counter()
     for _ in range(steps):
-        st, ev = batch.interval()
+        st, ev = batch.interval(threads)
         tot_steps += st; tot_evals += ev; done += 1
         if budget_s is not None and time.perf_counter() - t_begin > budget_s:
             break
@@ -148,9 +163,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    threads = oracle.num_threads()
-    sample = args.cpu_sample_envs or 256 * threads
+    sample = cpu_sample_envs(args, host_threads())
     evals_s, steps_s, ms, threads, done = cpu_closed_loop(args, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": evals_s, "unit": "evals/s", "env_steps_per_s": steps_s,
@@ -297,9 +310,7 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        import oracle
-        threads = oracle.num_threads()
-        sample = args.cpu_sample_envs or 256 * threads
+        sample = cpu_sample_envs(args, host_threads())
         ev_s, st_s, ms, threads, done = cpu_closed_loop(args, sample, 400, 3, budget_s=15.0)
         cpu = {"value": ev_s, "unit": "evals/s", "cores": threads, "kind": "port", "env_steps_per_s": st_s,
                "sample": f"{sample} of {E} envs x {C} candidates, {done} control intervals "

@@ -115,6 +115,7 @@ def lib():
                                        C.c_int, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_longlong)]
         L.orc_env_interval.restype = C.c_longlong
         L.orc_num_threads.restype = C.c_int
+        L.orc_has_openmp.restype = C.c_int
         L.orc_sincos.argtypes = [C.c_double, dp, dp]
         L.orc_sincos.restype = None
         L.orc_pow_m02.argtypes = [C.c_double]
@@ -331,6 +332,11 @@ def pow_m02(x):
 def num_threads() -> int:
     """Threads the OpenMP loops of the oracle will use (1 without OpenMP)."""
     return int(lib().orc_num_threads())
+
+
+def has_openmp() -> bool:
+    """True if the oracle was compiled with OpenMP (its batch loops then honour the ``nthreads`` argument)."""
+    return bool(lib().orc_has_openmp())
 
 
 class EnvBatch:

@@ -517,6 +517,15 @@ int orc_num_threads(void)
 #endif
 }
 
+int orc_has_openmp(void)
+{
+#ifdef _OPENMP
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 /* Whole episodes (the closed loop above run to t1) for E environments, OpenMP-parallel. */
 long long orc_closed_loop(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *state_init,
                           int C, const double *cand, int cand_per_env, const double *w_critic,

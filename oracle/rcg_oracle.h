@@ -125,6 +125,7 @@ long long orc_env_interval(orc_env_t *envs, const orc_ctrl_t *c, const orc_sys_t
                            const double *cand, int cand_per_env, const double *w_critic,
                            double sampling_time, double t1, int nthreads, long long *evals_out);
 int       orc_num_threads(void);
+int       orc_has_openmp(void);
 
 #ifdef __cplusplus
 }

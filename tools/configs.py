@@ -1,0 +1,128 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs 3 and 4 on one GPU (closed loops with the critic in the loop) and the fp64-vs-fp32
+tolerance report of config 4.  One JSON line per result; used for profiles/ and DESIGN.md, not for the bench
+contract.
+
+    python tools/configs.py config3 [--envs 1048576] [--t1 0.3]     # 3wrobot RQL, 'quadratic' critic, Nactor=10
+    python tools/configs.py config4 [--envs 262144]  [--t1 10]      # 2tank SQL, critic buffer fitting, Nactor=8
+    python tools/configs.py fp32    [--envs 262144]  [--t1 10]      # config 4: fp64 vs fp32 tolerance report
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench_workload import synthetic_candidates, synthetic_states  # noqa: E402
+from rcognita_b200 import _C, ops  # noqa: E402
+from rcognita_b200.engine import ClosedLoopEngine  # noqa: E402
+
+CFG = {
+    "config3": dict(system="3wrobot", mode="RQL", cs="quadratic", N=10, dt=0.01, psm=2.0, pars=[10, 1],
+                    bnds=[[-300, 300], [-100, 100]], R1=[1, 10, 1, 0, 0, 0, 0], target=[], a_init=[]),
+    "config4": dict(system="2tank", mode="SQL", cs="quad-nomix", N=8, dt=0.1, psm=2.0, pars=[18.4, 24.4, 1.3, 1, 0.2],
+                    bnds=[[0, 1]], R1=[10, 10, 1], target=[0.5, 0.5], a_init=[0.5]),
+}
+
+
+def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_critic=None):
+    E = (E + 1023) // 1024 * 1024
+    x0 = synthetic_states(c["system"], 0, E, seed=0)
+    cand = synthetic_candidates(c["bnds"], c["N"], C, seed=1)
+    eng = ClosedLoopEngine(c["system"], x0, cand, pars=c["pars"], ctrl_bnds=c["bnds"], mode=c["mode"], Nactor=c["N"],
+                           dt=c["dt"], pred_step_size=c["dt"] * c["psm"], t1=t1, R1=c["R1"], observation_target=c["target"],
+                           critic_struct=c["cs"], critic_fit=critic_fit, w_critic=w_critic, Ncritic=4, buffer_size=10,
+                           action_init=c["a_init"], dtype=dtype)
+    for _ in range(3):
+        eng.run_interval()
+    torch.cuda.synchronize()
+    s0, n0 = int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k = eng.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps, samples = int(eng.nsteps.sum().item()) - s0, int(eng.nsamples.sum().item()) - n0
+    return eng, dict(E=E, C=C, intervals=k, ms=ms, env_steps_per_s=steps / ms * 1e3, actor_evals_per_s=samples * C / ms * 1e3,
+                     critic_fits_per_s=(samples / ms * 1e3) if critic_fit else 0.0, ms_per_interval=ms / max(k, 1))
+
+
+def run_config(name, a):
+    c = CFG[name]
+    eng, r = timed_closed_loop(c, a.envs, a.cands, a.t1)
+    res = eng.results()
+    r.update(config=name, system=c["system"], mode=c["mode"], critic=c["cs"], Nactor=c["N"], t1=a.t1, dtype="f64",
+             status_finished=int((res["status"] == _C.FINISHED).sum()), status_failed=int((res["status"] == _C.FAILED).sum()),
+             mean_return=float(res["accum"].mean()), mean_Jc=float(res["Jc"].mean()),
+             w_critic_mean=float(res["w_critic"].mean()), nfits_mean=float(res["nfits"].mean()))
+    print(json.dumps(r), flush=True)
+
+
+def pct(x):
+    x = np.asarray(x, dtype=np.float64)
+    return {"p50": float(np.percentile(x, 50)), "p99": float(np.percentile(x, 99)), "max": float(x.max())}
+
+
+def run_fp32_report(a):
+    """Config 4 in fp64 and fp32 on identical inputs: (i) one E x C actor-cost launch (J, arg-min agreement),
+    (ii) the closed loop with the critic weights pinned (trajectory / return divergence at t1).  _critic_cost
+    and the critic fit exist in fp64 only (the fit's Gram matrices need it), so J_c has no fp32 figure."""
+    c = CFG["config4"]
+    n, m = _C.SYS_DIMS[_C.SYS_IDS[c["system"]]]
+    E = (a.envs + 1023) // 1024 * 1024
+    C = a.cands
+    x0 = synthetic_states(c["system"], 0, E, seed=0)
+    cand = synthetic_candidates(c["bnds"], c["N"], C, seed=1)
+    w = np.array([11.0, 11.0, 1.0])
+    sysd = _C.make_system(c["system"], c["pars"], c["bnds"])
+    obj = _C.make_objective(n, m, mode=c["mode"], Nactor=c["N"], pred_step_size=c["dt"] * c["psm"], critic_struct=c["cs"],
+                            R1=c["R1"], observation_target=c["target"])
+    x64 = torch.as_tensor(x0.T.copy(), device="cuda")
+    c64 = torch.as_tensor(cand.T.copy(), device="cuda")
+    w64 = torch.as_tensor(w, device="cuda")
+    J64, am64, _ = ops.actor_cost(sysd, obj, x64, x64, c64, False, C, w_critic=w64)
+    J32, am32, _ = ops.actor_cost(sysd, obj, x64.float(), x64.float(), c64.float(), False, C, w_critic=w64.float())
+    relJ = ((J32.double() - J64).abs() / J64.abs().clamp_min(1e-300)).cpu().numpy().reshape(-1)
+    agree = float((am64 == am32).double().mean().item())
+    # where the arg-min differs: how much worse (in fp64 cost) is the fp32 pick
+    idx = torch.arange(E, device="cuda")
+    regret = ((J64[idx, am32.long()] - J64[idx, am64.long()]) / J64[idx, am64.long()].abs().clamp_min(1e-300)).cpu().numpy()
+    e64, r64 = timed_closed_loop(c, E, C, a.t1, critic_fit=False, w_critic=w)
+    e32, r32 = timed_closed_loop(c, E, C, a.t1, critic_fit=False, w_critic=w, dtype=torch.float32)
+    y64, y32 = e64.results(), e32.results()
+    rel_y = np.abs(y32["y"].astype(np.float64) - y64["y"]) / np.maximum(np.abs(y64["y"]), 1e-2)
+    rel_acc = np.abs(y32["accum"].astype(np.float64) - y64["accum"]) / np.abs(y64["accum"])
+    out = {"config": "config4-fp32-report", "E": E, "C": C, "t1": a.t1,
+           "actor_cost_rel_err_fp32_vs_fp64": pct(relJ), "argmin_agreement": agree, "argmin_regret_rel": pct(regret),
+           "closed_loop_state_rel_err_at_t1": pct(rel_y.reshape(-1)), "closed_loop_return_rel_err": pct(rel_acc),
+           "same_step_counts": float((y32["nsteps"] == y64["nsteps"]).mean()),
+           "fp64": {k: r64[k] for k in ("ms", "env_steps_per_s", "actor_evals_per_s")},
+           "fp32": {k: r32[k] for k in ("ms", "env_steps_per_s", "actor_evals_per_s")},
+           "critic_cost_fp32": None, "note": "_critic_cost / critic fit are fp64-only"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["config3", "config4", "fp32"])
+    ap.add_argument("--envs", type=int, default=0)
+    ap.add_argument("--cands", type=int, default=256)
+    ap.add_argument("--t1", type=float, default=0.0)
+    a = ap.parse_args()
+    if a.what == "config3":
+        a.envs, a.t1 = a.envs or 1 << 20, a.t1 or 0.3
+        run_config("config3", a)
+    elif a.what == "config4":
+        a.envs, a.t1 = a.envs or 262144, a.t1 or 10.0
+        run_config("config4", a)
+    else:
+        a.envs, a.t1 = a.envs or 262144, a.t1 or 10.0
+        run_fp32_report(a)
+
+
+if __name__ == "__main__":
+    main()
