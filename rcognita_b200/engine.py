@@ -37,7 +37,7 @@ class ClosedLoopEngine:
                  pred_step_size=None, t0=0.0, t1=10.0, first_step=1e-6, atol=1e-5, rtol=1e-3, gamma=1.0, R1=None,
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
-                 buffer_size=10, critic_period=None):
+                 buffer_size=10, critic_period=None, critic_fit_evals=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -82,6 +82,7 @@ class ClosedLoopEngine:
             else:
                 raise ValueError("candidates must be [C, N*m] or [E, C, N*m]")
             self.critic_fit = bool(critic_fit) and mode != "MPC"
+            self.critic_fit_evals = int(critic_fit_evals)      # 0: fit to convergence; > 0: work bound per environment
             self.critic_period = float(dt if critic_period is None else critic_period)
             self.buffer_size = int(buffer_size)
             self.w_bounds = (-1e3, 1e3) if critic_struct in ("quad-lin", "quad-mix") else (0.0, 1e3)   # controllers.py:1024-1039
@@ -219,7 +220,8 @@ class ClosedLoopEngine:
         # w_critic_prev (:1470-1471).  Sampling lanes whose critic clock did not fire take w_critic_prev (:1479),
         # which already equals their w_critic (both were written by their last refit, or are still ones).
         ops.critic_fit(self.obj, n, m, self.obs_buf, self.act_buf, self.w_prev, self.w_bounds[0], self.w_bounds[1],
-                       self.w, w_init=self.w_init, mask=self.critic_flag, update_prev=True, Jc_out=self.Jc)
+                       self.w, w_init=self.w_init, mask=self.critic_flag, max_evals=self.critic_fit_evals, update_prev=True,
+                       Jc_out=self.Jc)
         self.nfits += self.critic_flag
 
     def _actor_launch(self):

@@ -161,18 +161,19 @@ def critic_cost(obj, n, m, obs_buf, act_buf, w, w_prev, out=None):
     return out
 
 
-def critic_fit(obj, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w, w_init=None, mask=None, max_outer=0,
+def critic_fit(obj, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w, w_init=None, mask=None, max_evals=0,
                update_prev=False, Jc_out=None):
     """``CtrlOptPred._critic_optimizer``: bounded least-squares fit of ``_critic_cost`` per environment.
     Starts from ``w_init`` [dimc] (shared) or, if None, from the content of ``w`` [dimc, E]; the fitted weights
-    are written to ``w`` (and to ``w_prev`` when ``update_prev``) for the lanes with ``mask`` != 0."""
+    are written to ``w`` (and to ``w_prev`` when ``update_prev``) for the lanes with ``mask`` != 0.
+    ``max_evals`` > 0 bounds the work per environment (best iterate so far is returned); 0 = to convergence."""
     L, _, E = obs_buf.shape
     dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
     _C.check(_C.lib.rcg_critic_fit(C.byref(obj), n, m, E, _ptr(obs_buf, _F64, (L, n, E), "obs_buf"),
                                    _ptr(act_buf, _F64, (L, m, E), "act_buf"), _ptr(w_prev, _F64, (dimc, E), "w_prev"),
                                    float(w_min), float(w_max), _ptr(w_init, _F64, (dimc,), "w_init", optional=True),
                                    _ptr(w, _F64, (dimc, E), "w"), _ptr(mask, _I32, (E,), "mask", optional=True),
-                                   int(max_outer), int(bool(update_prev)),
+                                   int(max_evals), int(bool(update_prev)),
                                    _ptr(Jc_out, _F64, (E,), "Jc_out", optional=True), _stream()), "rcg_critic_fit")
     return w
 

@@ -28,17 +28,34 @@ CFG = {
 }
 
 
-def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_critic=None):
+def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_critic=None, fit_evals=0):
     E = (E + 1023) // 1024 * 1024
     x0 = synthetic_states(c["system"], 0, E, seed=0)
     cand = synthetic_candidates(c["bnds"], c["N"], C, seed=1)
     eng = ClosedLoopEngine(c["system"], x0, cand, pars=c["pars"], ctrl_bnds=c["bnds"], mode=c["mode"], Nactor=c["N"],
                            dt=c["dt"], pred_step_size=c["dt"] * c["psm"], t1=t1, R1=c["R1"], observation_target=c["target"],
                            critic_struct=c["cs"], critic_fit=critic_fit, w_critic=w_critic, Ncritic=4, buffer_size=10,
-                           action_init=c["a_init"], dtype=dtype)
+                           action_init=c["a_init"], dtype=dtype, critic_fit_evals=fit_evals)
     for _ in range(3):
         eng.run_interval()
     torch.cuda.synchronize()
+    phases = {}
+    if os.environ.get("RCG_PHASES"):
+        # per-phase CUDA-event timing (adds events between the launches; the totals below then include that overhead)
+        def wrap(obj, name, key):
+            fn = getattr(obj, name)
+
+            def timed(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                phases.setdefault(key, []).append((e0, e1))
+                return r
+            setattr(obj, name, timed)
+        import rcognita_b200.engine as engmod
+        for nm in ("rk45_advance", "push_buffers", "ctrl_sample", "critic_fit", "actor_cost"):
+            wrap(engmod.ops, nm, nm)
     s0, n0 = int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -47,15 +64,18 @@ def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_criti
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     steps, samples = int(eng.nsteps.sum().item()) - s0, int(eng.nsamples.sum().item()) - n0
+    if phases:
+        print(json.dumps({"phases_ms_per_interval": {k: sum(a.elapsed_time(b) for a, b in v) / max(k_, 1)
+                                                      for k, v in phases.items() for k_ in [len(v)]}}), flush=True)
     return eng, dict(E=E, C=C, intervals=k, ms=ms, env_steps_per_s=steps / ms * 1e3, actor_evals_per_s=samples * C / ms * 1e3,
                      critic_fits_per_s=(samples / ms * 1e3) if critic_fit else 0.0, ms_per_interval=ms / max(k, 1))
 
 
 def run_config(name, a):
     c = CFG[name]
-    eng, r = timed_closed_loop(c, a.envs, a.cands, a.t1)
+    eng, r = timed_closed_loop(c, a.envs, a.cands, a.t1, fit_evals=a.fit_evals)
     res = eng.results()
-    r.update(config=name, system=c["system"], mode=c["mode"], critic=c["cs"], Nactor=c["N"], t1=a.t1, dtype="f64",
+    r.update(config=name, critic_fit_evals=a.fit_evals, system=c["system"], mode=c["mode"], critic=c["cs"], Nactor=c["N"], t1=a.t1, dtype="f64",
              status_finished=int((res["status"] == _C.FINISHED).sum()), status_failed=int((res["status"] == _C.FAILED).sum()),
              mean_return=float(res["accum"].mean()), mean_Jc=float(res["Jc"].mean()),
              w_critic_mean=float(res["w_critic"].mean()), nfits_mean=float(res["nfits"].mean()))
@@ -112,6 +132,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--cands", type=int, default=256)
     ap.add_argument("--t1", type=float, default=0.0)
+    ap.add_argument("--fit-evals", type=int, default=0, help="work bound of the critic fit per environment (0 = to convergence)")
     a = ap.parse_args()
     if a.what == "config3":
         a.envs, a.t1 = a.envs or 1 << 20, a.t1 or 0.3
