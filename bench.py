@@ -180,7 +180,33 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- CUDA arm
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and the pinned host buffers it allocates afterwards) to the CPUs NVML reports as local to
+    its GPU: with 8 ranks on one host the per-step H2D/D2H traffic of the host-staged loop otherwise crosses NUMA
+    nodes.  Returns the previous affinity (restored before the CPU baseline), or None if NVML is unavailable."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        if not os.sched_getaffinity(0):
+            os.sched_setaffinity(0, prev)
+        return prev
+    except Exception:
+        return None
+
+
 def run_b200(args):
+    # Everything the libraries print (NCCL's version banner goes to stdout) is sent to stderr: stdout carries
+    # exactly one JSON line.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -195,6 +221,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (rcognita_b200 has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    prev_affinity = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -309,6 +336,8 @@ def run_b200(args):
             pass
 
     cpu = None
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)
     if world == 1 and not args.no_cpu_baseline:
         sample = cpu_sample_envs(args, host_threads())
         ev_s, st_s, ms, threads, done = cpu_closed_loop(args, sample, 400, 3, budget_s=15.0)
@@ -327,7 +356,8 @@ def run_b200(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": tot_launches, "roofline": roofline, "cpu_baseline": cpu,
         "mean_return_so_far": float(returns.mean().item()),
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
