@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="environments in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="environment blocks (streams) of the host-staged loop")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="environment blocks (streams) of the host-staged loop")
+    ap.add_argument("--no-graph", action="store_true", help="drive the host-staged loop from Python instead of a CUDA graph")
     return ap.parse_args()
 
 
@@ -282,6 +283,8 @@ def run_b200(args):
         loop = HostStagedLoop(SYSTEM, x0, cand, nchunks=args.e2e_chunks, device=dev, ctrl_bnds=BNDS, mode="MPC", Nactor=N,
                               dt=DT, t1=t1, R1=R1_DIAG, action_init=ACTION_INIT)
         del cand
+        if not args.no_graph:
+            loop.capture()
         for _ in range(3):
             loop.step()
         barrier()
@@ -301,7 +304,8 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                "ms_per_step": float(ms_e2e.item()) / K,
                "api": f"HostStagedLoop.step: pinned host lane state in and out every step, {args.e2e_chunks} env blocks on "
-                      "separate streams (copies overlap kernels); candidate sets resident on the device"}
+                      "separate streams (copies overlap kernels)" + ("" if args.no_graph else ", one CUDA-graph replay per step")
+                      + "; candidate sets resident on the device"}
         del loop
 
     if rank != 0:

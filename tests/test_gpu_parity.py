@@ -573,3 +573,31 @@ def test_errors_are_loud(rb):
     y, f, t, h, status, nfev, action = _sim_state(ops, _C, sysd, [X0["3wrobotNI"]])
     with pytest.raises(RuntimeError, match="max_step"):
         ops.rk45_step(sysd, sol, y, f, t, h, status, action)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_staged_loop_equals_resident_loop(rb, graph):
+    """engine.HostStagedLoop (lane state owned by pinned host memory, several environment blocks on their own
+    streams, optionally replayed as one CUDA graph per step) takes exactly the same steps as the device-resident
+    ClosedLoopEngine: identical state, clocks, counters and picks on every lane after every control interval."""
+    from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop
+    name, N, C_, E = "3wrobotNI", 6, 64, 1000
+    p = PRESET[name]
+    x0 = random_states(name, E, 71)
+    cand = random_cands(name, (E, C_), N, 72)
+    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.4, R1=p["R1_diag"])
+    ref = ClosedLoopEngine(name, x0, cand, **kw)
+    loop = HostStagedLoop(name, x0, cand, nchunks=3, **kw)
+    if graph:
+        loop.capture()
+        ref.run_interval()                      # capture() itself advances the loop by one warm-up interval
+    for k in range(12):
+        ref.run_interval()
+        h2d, d2h = loop.step()
+        torch.cuda.synchronize()
+        assert h2d > 0 and d2h > h2d
+        for f in ("y", "f", "state_sys", "action", "t", "h_abs", "ctrl_clock", "accum", "status", "nsteps", "nsamples",
+                  "nfev", "argmin", "Jmin", "sample_flag"):
+            got = loop.host_field(f).numpy()
+            want = getattr(ref, f).cpu().numpy()
+            assert np.array_equal(got, want, equal_nan=True), (k, f)
