@@ -1,0 +1,126 @@
+"""The presets' argument set (names, types, per-preset defaults of the reference's
+presets/main_*.py) and, on the GPU, the preset main loop end to end: CSV in the reference's format whose rows
+reproduce the live-reference episode."""
+import csv
+import math
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import load
+
+# flag -> (type, NI default, 3wrobot default, 2tank default)   -- presets/main_3wrobot_NI.py:55-161 and siblings
+APPENDIX_C = {
+    "ctrl_mode": (str, "nominal", "nominal", "MPC"),
+    "dt": (float, 0.01, 0.01, 0.1),
+    "t1": (float, 10.0, 10.0, 100.0),
+    "Nruns": (int, 1, 1, 1),
+    "state_init": (list, ["5", "5", "-3*pi/4"], ["5", "5", "-3*pi/4", "0", "0"], ["2", "-2"]),
+    "is_log_data": (bool, False, False, False),
+    "is_visualization": (bool, True, True, True),
+    "is_print_sim_step": (bool, True, True, True),
+    "is_est_model": (bool, False, False, False),
+    "model_est_stage": (float, 1.0, 1.0, 1.0),
+    "model_est_period_multiplier": (float, 1, 1, 1),
+    "model_order": (int, 5, 5, 5),
+    "prob_noise_pow": (float, False, False, False),
+    "action_manual": (list, [-5, -3], [-5, -3], [0.5]),
+    "Nactor": (int, 3, 5, 10),
+    "pred_step_size_multiplier": (float, 1.0, 2.0, 2.0),
+    "buffer_size": (int, 10, 10, 10),
+    "stage_obj_struct": (str, "quadratic", "quadratic", "quadratic"),
+    "R1_diag": (list, [1, 10, 1, 0, 0], [1, 10, 1, 0, 0, 0, 0], [10, 10, 1]),
+    "R2_diag": (list, [1, 10, 1, 0, 0], [1, 10, 1, 0, 0, 0, 0], [10, 10, 1]),
+    "Ncritic": (int, 4, 4, 4),
+    "gamma": (float, 1.0, 1.0, 1.0),
+    "critic_period_multiplier": (float, 1.0, 1.0, 1.0),
+    "critic_struct": (str, "quad-nomix", "quad-nomix", "quad-nomix"),
+    "actor_struct": (str, "quad-nomix", "quad-nomix", "quad-nomix"),
+}
+
+
+@pytest.mark.parametrize("col,system", [(1, "3wrobotNI"), (2, "3wrobot"), (3, "2tank")])
+def test_flag_set_and_defaults_match_the_reference_presets(col, system):
+    from rcognita_b200 import presets
+    parser = presets.make_parser(system)
+    args = vars(parser.parse_args([]))
+    for flag, spec in APPENDIX_C.items():
+        assert flag in args, flag
+        assert args[flag] == spec[col], (flag, args[flag], spec[col])
+    assert set(args) - set(APPENDIX_C) == {"num_envs", "num_candidates", "seed", "state_spread"}
+    # argparse type=bool quirk of the reference: any non-empty string is True, '' is False
+    a = parser.parse_args(["--is_visualization", "", "--is_log_data", "0"])
+    assert a.is_visualization is False and a.is_log_data is True
+    modes = {act.dest: act.choices for act in parser._actions}["ctrl_mode"]
+    assert ("nominal" in modes) == (system != "2tank") and {"manual", "MPC", "RQL", "SQL"} <= set(modes)
+
+
+def test_state_init_expressions():
+    from rcognita_b200 import presets
+    assert presets.parse_number("-3*pi/4") == -3 * math.pi / 4
+    assert presets.parse_number("5") == 5.0 and presets.parse_number("2**0.5") == 2 ** 0.5
+    for bad in ("__import__('os')", "pi.real", "a+1", "[1]"):
+        with pytest.raises((ValueError, SyntaxError)):
+            presets.parse_number(bad)
+
+
+def test_logger_rows_have_the_reference_column_order(tmp_path):
+    from rcognita_b200 import loggers
+    f = tmp_path / "a.csv"
+    loggers.Logger3WRobotNI().log_data_row(str(f), 0.5, 1, 2, 3, 10.0, 20.0, [7, 8])
+    loggers.Logger3WRobot().log_data_row(str(f), 0.5, 1, 2, 3, 4, 5, 10.0, 20.0, np.array([7, 8]))
+    loggers.Logger2Tank().log_data_row(str(f), 0.5, 1, 2, 0.3, 10.0, 20.0)
+    rows = list(csv.reader(open(f)))
+    assert [float(v) for v in rows[0]] == [0.5, 1, 2, 3, 10, 20, 7, 8]                 # rcognita/loggers.py:72-76
+    assert [float(v) for v in rows[1]] == [0.5, 1, 2, 3, 4, 5, 10, 20, 7, 8]           # :52-56
+    assert [float(v) for v in rows[2]] == [0.5, 1, 2, 0.3, 10, 20]                     # :90-94
+
+
+@pytest.mark.gpu
+def test_preset_main_reproduces_the_reference_episode(tmp_path):
+    """presets/main_3wrobot_NI.py --ctrl_mode MPC --Nactor 6 --t1 2 (defaults otherwise; candidate table = seed 1,
+    256 sequences, i.e. the table of the golden run): the CSV has the reference's 20 settings rows + column row, and
+    every data row [t, x, y, alpha, stage_obj, accum_obj, v, omega] equals the live-reference episode."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from rcognita_b200 import presets
+    g = load("closed_loop.json")["NI_MPC_N6"]
+    args = presets.make_parser("3wrobotNI").parse_args(["--ctrl_mode", "MPC", "--Nactor", "6", "--t1", "2.0", "--is_visualization", "",
+                                                        "--is_print_sim_step", "", "--is_log_data", "1"])
+    out = presets.run_headless("3wrobotNI", args, data_folder=str(tmp_path), quiet=True)
+    assert len(out["datafiles"]) == 1 and os.path.basename(out["datafiles"][0]).startswith("3wrobotNI__MPC__")
+    rows = list(csv.reader(open(out["datafiles"][0])))
+    assert rows[0] == ["System", "3wrobotNI"] and rows[1] == ["Controller", "MPC"] and rows[2] == ["dt", "0.01"]
+    assert [r[0] for r in rows[4:20]] == ['is_est_model', 'model_est_stage', 'model_est_period_multiplier', 'model_order',
+                                          'prob_noise_pow', 'Nactor', 'pred_step_size_multiplier', 'buffer_size',
+                                          'stage_obj_struct', 'R1_diag', 'R2_diag', 'Ncritic', 'gamma',
+                                          'critic_period_multiplier', 'critic_struct', 'actor_struct']
+    assert rows[20] == ['t [s]', 'x [m]', 'y [m]', 'alpha [rad]', 'stage_obj', 'accum_obj', 'v [m/s]', 'omega [rad/s]']
+    data = np.array([[float(v) for v in r] for r in rows[21:]])
+    ref = np.array(g["rows"])                                  # [t, x, y, th, a0, a1, accum, sampled]
+    assert data.shape[0] == ref.shape[0] == out["runs"][0]["steps"]
+    assert np.max(np.abs(data[:, 0] - ref[:, 0])) <= 1e-15 * 2.0
+    assert np.max(np.abs(data[:, 1:4] - ref[:, 1:4]) / np.maximum(np.abs(ref[:, 1:4]), 1e-2)) <= 1e-9
+    assert np.array_equal(data[:, 6:8], ref[:, 4:6])
+    assert np.max(np.abs(data[:, 5] - ref[:, 6]) / ref[:, 6]) <= 1e-9
+    # stage_obj column = x^2 + 10 y^2 + alpha^2 (R1_diag = [1, 10, 1, 0, 0])
+    so = ref[:, 1] ** 2 + 10 * ref[:, 2] ** 2 + ref[:, 3] ** 2
+    assert np.max(np.abs(data[:, 4] - so) / np.maximum(so, 1e-12)) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_preset_batched_rql_runs_and_logs(tmp_path):
+    torch = pytest.importorskip("torch")
+    from rcognita_b200 import presets
+    args = presets.make_parser("2tank").parse_args(["--ctrl_mode", "SQL", "--Nactor", "8", "--t1", "3.0", "--is_visualization", "",
+                                                    "--is_print_sim_step", "", "--is_log_data", "1", "--num_envs", "16",
+                                                    "--state_spread", "0.3", "--num_candidates", "32", "--Nruns", "2"])
+    out = presets.run_headless("2tank", args, data_folder=str(tmp_path), quiet=True)
+    assert len(out["runs"]) == 2 and len(out["datafiles"]) == 2
+    for run, f in zip(out["runs"], out["datafiles"]):
+        assert run["t"] >= 3.0 and len(run["accum_obj"]) == 16 and all(np.isfinite(run["accum_obj"]))
+        rows = list(csv.reader(open(f)))
+        assert rows[20] == ['t [s]', 'h1', 'h2', 'p', 'stage_obj', 'accum_obj'] and len(rows) == 21 + run["steps"]
+    assert out["runs"][0]["steps"] > 30
