@@ -174,6 +174,42 @@ int rcg_actor_cost_f32(const rcg_system_t *sys, const rcg_objective_t *obj, int6
                        float *J_out, int32_t *argmin_out, float *Jmin_out, float *action_out,
                        float *accum, double sampling_time, void *stream);
 
+/* ---- CtrlOptPred._actor_optimizer (rcognita/controllers.py:1330-1427) -------------------------------------
+ * The reference minimises _actor_cost over the action sequence with scipy's SLSQP (finite-difference gradients,
+ * Bounds(action_sqn_min, action_sqn_max), tol 1e-7, maxiter 300).  The batched form: one thread per
+ * (environment, start point); exact gradients by the adjoint of the Euler rollout; a projected limited-memory
+ * quasi-Newton iteration inside the box given by sys->lo/hi tiled over the horizon (controllers.py:968-971).
+ *   sqn [Nactor*m][E*S]         -- start points in, minimisers out; element (k, j, e, s) at ((k*m+j)*E + e)*S + s
+ *                                  (the layout of per-environment candidates).  S: power of two <= 32.
+ *   workspace                   -- device scratch of rcg_actor_opt_workspace_bytes() bytes (quasi-Newton memory).
+ *   mask[E] or NULL             -- environments with mask == 0 are skipped entirely.
+ *   max_iter, pg_tol, f_tol     -- stop after max_iter accepted iterations, when |P(x - g) - x|_inf <= pg_tol, or
+ *                                  when the cost moved by <= f_tol * max(|J|, 1) twice in a row.
+ *   J_out[E*S], iters_out[E*S], nfev_out[E*S] or NULL -- per start: final cost, accepted iterations (= gradient
+ *                                  evaluations - 1), cost evaluations spent in the line searches.
+ *   best_out[E], Jmin_out[E]    -- arg-min over the S starts of an environment (np.argmin order), or NULL.
+ *   action_out[m][E] or NULL    -- first action of the best minimiser (_actor_optimizer's return value, :1427).
+ *   accum[E] or NULL            -- += stage_obj(obs, action_best) * sampling_time (upd_accum_obj, :1093).
+ * The iteration is monotone: the returned cost is never above the cost of the (clipped) start point. */
+int64_t rcg_actor_opt_workspace_bytes(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S);
+int rcg_actor_opt(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S, const double *state_sys,
+                  const double *obs, double *sqn, const double *w_critic, int32_t w_per_env, const int32_t *mask,
+                  int32_t max_iter, double pg_tol, double f_tol, double *workspace, int64_t workspace_bytes,
+                  double *J_out, int32_t *iters_out, int32_t *nfev_out, int32_t *best_out, double *Jmin_out,
+                  double *action_out, double *accum, double sampling_time, void *stream);
+
+/* _actor_cost and its exact gradient w.r.t. the action sequence for E x S sequences (the adjoint sweep the
+ * optimiser uses; what SLSQP approximates by forward differences): J_out[E*S], grad_out[Nactor*m][E*S].
+ * `workspace` as for rcg_actor_opt (only read when the horizon/cost structure has no specialised kernel). */
+int rcg_actor_grad(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S, const double *state_sys,
+                   const double *obs, const double *sqn, const double *w_critic, int32_t w_per_env, double *workspace,
+                   int64_t workspace_bytes, double *J_out, double *grad_out, void *stream);
+
+/* Start points from an arg-min: sqn_out[i][e] = candidate idx[e] of environment e (cand laid out as for
+ * rcg_actor_cost; L = Nactor*m rows), for the lanes with mask != 0 and 0 <= idx[e] < C. */
+int rcg_gather_sqn(int32_t L, int64_t E, int32_t C, const double *cand, int32_t cand_per_env, const int32_t *idx,
+                   const int32_t *mask, double *sqn_out, void *stream);
+
 /* CtrlOptPred.stage_obj (rcognita/controllers.py:1063-1084): out[E] = stage_obj(obs, act);
  * if accum != NULL additionally accum[E] += out * scale (upd_accum_obj, :1086-1093). */
 int rcg_stage_obj(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs,

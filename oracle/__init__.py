@@ -63,14 +63,14 @@ class EnvT(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile ``librcg_oracle.so`` (gcc; OpenMP if the toolchain has it)."""
-    src = os.path.join(_HERE, "rcg_oracle.c")
+    srcs = [os.path.join(_HERE, "rcg_oracle.c"), os.path.join(_HERE, "rcg_oracle_opt.c")]
     hdr = os.path.join(_HERE, "rcg_oracle.h")
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(f) for f in srcs + [hdr])):
         return _LIB_PATH
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
     base = [gcc, "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-shared",
-            "-o", _LIB_PATH, src, "-lm"]
+            "-o", _LIB_PATH, *srcs, "-lm"]
     for extra in (["-fopenmp"], []):
         r = subprocess.run(base[:1] + extra + base[1:], capture_output=True, text=True)
         if r.returncode == 0:
@@ -101,6 +101,11 @@ def lib():
         L.orc_critic_cost.restype = C.c_double
         L.orc_actor_cost.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp]
         L.orc_actor_cost.restype = C.c_double
+        L.orc_actor_grad.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, dp]
+        L.orc_actor_grad.restype = C.c_double
+        L.orc_actor_opt.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
+                                    ip, ip]
+        L.orc_actor_opt.restype = C.c_double
         L.orc_argmin.argtypes = [dp, C.c_int]
         L.orc_argmin.restype = C.c_int
         L.orc_actor_cost_table.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, dp, dp, dp, dp, ip]
@@ -258,6 +263,29 @@ def actor_cost(c, s, action_sqn, observation, state_sys, w_critic=None):
     else:
         w, wp = _d(w_critic)
     return lib().orc_actor_cost(C.byref(c), C.byref(s), ap, op, xp, wp)
+
+
+def actor_grad(c, s, action_sqn, observation, state_sys, w_critic=None):
+    """(J, dJ/d action_sqn) by the adjoint of the Euler rollout (rcg_oracle_opt.c)."""
+    a, ap = _d(action_sqn)
+    o, op = _d(observation)
+    x, xp = _d(state_sys)
+    w, wp = (None, _null()) if w_critic is None else _d(w_critic)
+    g = np.zeros(a.size)
+    J = lib().orc_actor_grad(C.byref(c), C.byref(s), ap, op, xp, wp, g.ctypes.data_as(C.POINTER(C.c_double)))
+    return J, g
+
+
+def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_iter=100, pg_tol=1e-6, f_tol=1e-9):
+    """Bounded minimiser of ``_actor_cost`` (SPG, rcg_oracle_opt.c).  Returns (x, J, iters, nfev)."""
+    a = np.array(action_sqn_init, dtype=np.float64).reshape(-1).copy()
+    o, op = _d(observation)
+    x, xp = _d(state_sys)
+    w, wp = (None, _null()) if w_critic is None else _d(w_critic)
+    it, nf = C.c_int(0), C.c_int(0)
+    J = lib().orc_actor_opt(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp,
+                            int(max_iter), float(pg_tol), float(f_tol), C.byref(it), C.byref(nf))
+    return a, J, it.value, nf.value
 
 
 def actor_cost_table(c, s, cand, observation, state_sys, w_critic=None):

@@ -124,6 +124,13 @@ void      orc_env_init(orc_env_t *envs, const orc_sys_t *s, int E, const double 
 long long orc_env_interval(orc_env_t *envs, const orc_ctrl_t *c, const orc_sys_t *s, int E, int C,
                            const double *cand, int cand_per_env, const double *w_critic,
                            double sampling_time, double t1, int nthreads, long long *evals_out);
+/* rcg_oracle_opt.c: analytic gradient of _actor_cost (adjoint of the Euler rollout) and the bounded
+ * minimiser standing in for CtrlOptPred._actor_optimizer (ref: controllers.py:1330-1427). */
+double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *action_sqn, const double *observation,
+                      const double *state_sys, const double *w_critic, double *grad);
+double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
+                     const double *state_sys, const double *w_critic, int max_iter, double pg_tol, double f_tol,
+                     int *iters_out, int *nfev_out);
 int       orc_num_threads(void);
 int       orc_has_openmp(void);
 

@@ -1,0 +1,274 @@
+/*
+ * rcg_oracle_opt.c -- CPU ORACLE (test infrastructure, NOT product code), part 2:
+ * the analytic gradient of CtrlOptPred._actor_cost and the bounded minimiser that stands in for
+ * CtrlOptPred._actor_optimizer (ref: rcognita/controllers.py:1330-1427, scipy SLSQP with
+ * Bounds(action_sqn_min, action_sqn_max), tol 1e-7, maxiter 300).
+ *
+ * The reference differentiates _actor_cost by finite differences inside SLSQP; here the gradient is
+ * the exact adjoint (reverse sweep) of the Euler rollout of controllers.py:1290-1296, and the
+ * minimiser is a projected limited-memory quasi-Newton method (L-BFGS two-loop recursion on the free
+ * variables, projected Armijo backtracking).  This is a restatement
+ * of the ALGORITHM the CUDA path implements (rcognita_b200/csrc/actor_opt_impl.cuh), scalar and in
+ * the reference's row-major [Nactor, m] layout; it is pinned two ways in tests/test_oracle_golden.py:
+ * the gradient against central differences of orc_actor_cost (itself pinned to the live reference),
+ * and the minimum against the live reference's SLSQP results (tests/golden/actor_opt.json).
+ */
+#include <math.h>
+#include <string.h>
+
+#include "rcg_oracle.h"
+
+static double clipd(double v, double lo, double hi)
+{
+    v = (v < lo) ? lo : v;
+    return (v > hi) ? hi : v;
+}
+
+/* d stage_obj / d chi (ref: controllers.py:1063-1084): quadratic chi (R1 + R1^T);
+ * biquadratic adds 2 chi_i [(R2 + R2^T) chi^2]_i. */
+static void stage_obj_grad(const orc_ctrl_t *c, int p, const double *chi, double *gchi)
+{
+    for (int i = 0; i < p; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < p; ++j) acc += (c->R1[i * p + j] + c->R1[j * p + i]) * chi[j];
+        gchi[i] = acc;
+    }
+    if (c->stage_struct == ORC_STAGE_BIQUADRATIC) {
+        for (int i = 0; i < p; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < p; ++j) acc += (c->R2[i * p + j] + c->R2[j * p + i]) * (chi[j] * chi[j]);
+            gchi[i] += 2.0 * chi[i] * acc;
+        }
+    }
+}
+
+/* d _critic / d (obs, act) (ref: controllers.py:1192-1214; feature order of orc_critic). */
+static void critic_grad(const orc_ctrl_t *c, int n, int m, const double *obs, const double *act, const double *w,
+                        double *gobs, double *gact)
+{
+    const int p = n + m;
+    double chi[ORC_MAX_P], g[ORC_MAX_P];
+    int k = 0;
+    for (int i = 0; i < n; ++i) chi[i] = c->has_target ? obs[i] - c->target[i] : obs[i];
+    for (int j = 0; j < m; ++j) chi[n + j] = act[j];
+    for (int i = 0; i < p; ++i) g[i] = 0.0;
+    switch (c->critic_struct) {
+    case ORC_CRITIC_QUAD_LIN:
+    case ORC_CRITIC_QUADRATIC:
+        for (int i = 0; i < p; ++i)
+            for (int j = i; j < p; ++j) {
+                g[i] += w[k] * chi[j];
+                g[j] += w[k] * chi[i];
+                ++k;
+            }
+        if (c->critic_struct == ORC_CRITIC_QUAD_LIN)
+            for (int i = 0; i < p; ++i) g[i] += w[k++];
+        break;
+    case ORC_CRITIC_QUAD_NOMIX:
+        for (int i = 0; i < p; ++i) g[i] = 2.0 * w[k++] * chi[i];
+        break;
+    case ORC_CRITIC_QUAD_MIX:                       /* raw observation (:1212) */
+        for (int i = 0; i < n; ++i) g[i] = 2.0 * w[k++] * obs[i];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < m; ++j) {
+                g[i] += w[k] * act[j];
+                g[n + j] += w[k] * obs[i];
+                ++k;
+            }
+        for (int j = 0; j < m; ++j) g[n + j] += 2.0 * w[k++] * act[j];
+        break;
+    default:
+        break;
+    }
+    for (int i = 0; i < n; ++i) gobs[i] = g[i];
+    for (int j = 0; j < m; ++j) gact[j] = g[n + j];
+}
+
+/* lam <- lam + h * (d _state_dyn / d state)^T lam, and ga += h * (d _state_dyn / d action)^T lam, both at
+ * (x, a) with lam = lam_{k+1} on entry (ref for the dynamics: systems.py:308-323, :370-382, :412-419). */
+static void dyn_adjoint(const orc_sys_t *s, double h, const double *x, const double *a, double *lam, double *ga)
+{
+    if (s->sys_id == ORC_SYS_3WROBOT_NI) {
+        double sn, cs;
+        orc_sincos(x[2], &sn, &cs);
+        ga[0] += h * (cs * lam[0] + sn * lam[1]);
+        ga[1] += h * lam[2];
+        lam[2] += h * (a[0] * (cs * lam[1] - sn * lam[0]));
+    } else if (s->sys_id == ORC_SYS_3WROBOT) {
+        double sn, cs;
+        orc_sincos(x[2], &sn, &cs);
+        ga[0] += h * ((1.0 / s->pars[0]) * lam[3]);
+        ga[1] += h * ((1.0 / s->pars[1]) * lam[4]);
+        const double l2 = lam[2] + h * (x[3] * (cs * lam[1] - sn * lam[0]));
+        const double l3 = lam[3] + h * (cs * lam[0] + sn * lam[1]);
+        const double l4 = lam[4] + h * lam[2];
+        lam[2] = l2; lam[3] = l3; lam[4] = l4;
+    } else {
+        const double tau1 = s->pars[0], tau2 = s->pars[1], K1 = s->pars[2], K2 = s->pars[3], K3 = s->pars[4];
+        ga[0] += h * ((1.0 / tau1) * K1 * lam[0]);
+        const double l0 = lam[0] + h * (-(1.0 / tau1) * lam[0] + (1.0 / tau2) * K2 * lam[1]);
+        const double l1 = lam[1] + h * ((1.0 / tau2) * (-1.0 + 2.0 * K3 * x[1]) * lam[1]);
+        lam[0] = l0; lam[1] = l1;
+    }
+}
+
+/* _actor_cost and its gradient w.r.t. action_sqn ([Nactor, m] row-major).  Returns the cost exactly as
+ * orc_actor_cost computes it. */
+double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *action_sqn, const double *observation,
+                      const double *state_sys, const double *w_critic, double *grad)
+{
+    const int n = s->n, m = s->m, N = c->Nactor, p = n + m;
+    const double h = c->pred_step_size;
+    double X[ORC_MAX_NACTOR][ORC_MAX_N];       /* X[k] = predictor state before stage k's Euler step */
+    double d[ORC_MAX_N], lam[ORC_MAX_N], chi[ORC_MAX_P], gchi[ORC_MAX_P], gobs[ORC_MAX_N], gact[ORC_MAX_M];
+    for (int i = 0; i < n; ++i) X[0][i] = state_sys[i];
+    for (int k = 1; k < N; ++k) {
+        orc_state_dyn(s, X[k - 1], action_sqn + (k - 1) * m, d);
+        for (int i = 0; i < n; ++i) X[k][i] = X[k - 1][i] + h * d[i];
+    }
+    const double J = orc_actor_cost(c, s, action_sqn, observation, state_sys, w_critic);
+    for (int i = 0; i < n; ++i) lam[i] = 0.0;
+    for (int k = N - 1; k >= 0; --k) {
+        const double *obs = (k == 0) ? observation : X[k];      /* observation_sqn[0] = observation (:1290) */
+        const double *a = action_sqn + k * m;
+        double *ga = grad + k * m;
+        /* lam currently holds lam_{k+1}: dJ/dX[k+1] (zero for k = N-1) */
+        for (int j = 0; j < m; ++j) ga[j] = 0.0;
+        if (k < N - 1) dyn_adjoint(s, h, X[k], a, lam, ga);     /* lam <- (I + h A_k)^T lam_{k+1} */
+        const int use_critic = (c->mode == ORC_MODE_SQL) || (c->mode == ORC_MODE_RQL && k == N - 1);
+        if (use_critic) {
+            critic_grad(c, n, m, obs, a, w_critic, gobs, gact);
+        } else {
+            const double gk = pow(c->gamma, (double)k);
+            for (int i = 0; i < n; ++i) chi[i] = c->has_target ? obs[i] - c->target[i] : obs[i];
+            for (int j = 0; j < m; ++j) chi[n + j] = a[j];
+            stage_obj_grad(c, p, chi, gchi);
+            for (int i = 0; i < n; ++i) gobs[i] = gk * gchi[i];
+            for (int j = 0; j < m; ++j) gact[j] = gk * gchi[n + j];
+        }
+        for (int j = 0; j < m; ++j) ga[j] += gact[j];
+        if (k > 0)
+            for (int i = 0; i < n; ++i) lam[i] += gobs[i];       /* stage 0 reads the fixed observation */
+    }
+    return J;
+}
+
+/* Projected limited-memory quasi-Newton minimisation of _actor_cost over the box [lo, hi]^Nactor (lo/hi = the
+ * system's ctrl_bnds tiled like action_sqn_min/max, ref: controllers.py:968-971; unbounded if !has_bnds).
+ * x [Nactor*m]: start point in, minimiser out.  Returns the cost at the returned point; *iters_out = accepted
+ * iterations (= gradient evaluations after the first), *nfev_out = cost evaluations of the line searches.
+ *
+ *   x <- P(x); (J, g) at x
+ *   repeat: binding set B = { i : (x_i <= lo_i and g_i > 0) or (x_i >= hi_i and g_i < 0) }, free set F = rest
+ *           stop if |P(x - g) - x|_inf <= pg_tol
+ *           d_F = -H g_F by the L-BFGS two-loop recursion over the last ORC_OPT_MEM pairs (s, y), every inner
+ *                 product taken over F only (pairs with (s.y)_F <= 1e-10 |s|_F |y|_F are skipped), initial scaling
+ *                 (s.y)_F / (y.y)_F of the newest usable pair (w / |P(x - g) - x|_inf when there is none, w = the
+ *                 widest side of the box, 1 if unbounded: without curvature information the first trial step
+ *                 spans the box and the backtracking finds the scale); d_B = 0
+ *           if g.d >= 0: forget the pairs, d_F = -g_F w / |P(x - g) - x|_inf
+ *           projected backtracking: x+ = P(x + lambda d), lambda = 1, 1/2, ... until
+ *                 J(x+) <= J + 1e-4 g.(x+ - x)                      (monotone: the last iterate is the best)
+ *           remember s = x+ - x, y = g+ - g
+ *   stop also when the cost moved by <= f_tol * max(|J|, 1) twice in a row, when the line search fails, or after
+ *   max_iter iterations. */
+#define ORC_OPT_MEM 6
+#define ORC_OPT_LMAX (ORC_MAX_NACTOR * ORC_MAX_M)
+
+double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
+                     const double *state_sys, const double *w_critic, int max_iter, double pg_tol, double f_tol,
+                     int *iters_out, int *nfev_out)
+{
+    const int m = s->m, L = c->Nactor * m;
+    double lo[ORC_MAX_M], hi[ORC_MAX_M];
+    double g[ORC_OPT_LMAX], gn[ORC_OPT_LMAX], d[ORC_OPT_LMAX], xt[ORC_OPT_LMAX];
+    static _Thread_local double S[ORC_OPT_MEM][ORC_OPT_LMAX], Y[ORC_OPT_MEM][ORC_OPT_LMAX];
+    double al[ORC_OPT_MEM], sy[ORC_OPT_MEM];
+    int fr[ORC_OPT_LMAX];
+    int npairs = 0, head = 0;                   /* pairs live in slots (head - 1 - j) mod MEM, j = 0 newest */
+    int iters = 0, nfev = 0, stall = 0;
+    for (int j = 0; j < m; ++j) {
+        lo[j] = s->has_bnds ? s->lo[j] : -INFINITY;
+        hi[j] = s->has_bnds ? s->hi[j] : INFINITY;
+    }
+    /* first-step length when there is no curvature information: across the widest side of the box */
+    double step0 = 1.0;
+    if (s->has_bnds) {
+        step0 = 0.0;
+        for (int j = 0; j < m; ++j) step0 = fmax(step0, hi[j] - lo[j]);
+    }
+    for (int i = 0; i < L; ++i) x[i] = clipd(x[i], lo[i % m], hi[i % m]);
+    double J = orc_actor_grad(c, s, x, observation, state_sys, w_critic, g);
+    while (iters < max_iter) {
+        double pg = 0.0;
+        for (int i = 0; i < L; ++i) {
+            const double l = lo[i % m], u = hi[i % m];
+            fr[i] = !((x[i] <= l && g[i] > 0.0) || (x[i] >= u && g[i] < 0.0));
+            pg = fmax(pg, fabs(clipd(x[i] - g[i], l, u) - x[i]));
+        }
+        if (!(pg > pg_tol)) break;
+        /* two-loop recursion on the free set */
+        for (int i = 0; i < L; ++i) d[i] = fr[i] ? g[i] : 0.0;
+        double scale = step0 / pg;
+        int have_scale = 0;
+        for (int j = 0; j < npairs; ++j) {
+            const int k = (head - 1 - j + 2 * ORC_OPT_MEM) % ORC_OPT_MEM;
+            double a = 0.0, ss = 0.0, yy = 0.0, sq = 0.0;
+            for (int i = 0; i < L; ++i)
+                if (fr[i]) { a += S[k][i] * Y[k][i]; ss += S[k][i] * S[k][i]; yy += Y[k][i] * Y[k][i]; sq += S[k][i] * d[i]; }
+            sy[j] = (a > 1e-10 * sqrt(ss * yy)) ? a : 0.0;
+            if (sy[j] > 0.0) {
+                al[j] = sq / sy[j];
+                for (int i = 0; i < L; ++i) if (fr[i]) d[i] -= al[j] * Y[k][i];
+                if (!have_scale) { scale = sy[j] / yy; have_scale = 1; }
+            }
+        }
+        for (int i = 0; i < L; ++i) d[i] *= scale;
+        for (int j = npairs - 1; j >= 0; --j) {
+            if (!(sy[j] > 0.0)) continue;
+            const int k = (head - 1 - j + 2 * ORC_OPT_MEM) % ORC_OPT_MEM;
+            double yr = 0.0;
+            for (int i = 0; i < L; ++i) if (fr[i]) yr += Y[k][i] * d[i];
+            const double b = yr / sy[j];
+            for (int i = 0; i < L; ++i) if (fr[i]) d[i] += (al[j] - b) * S[k][i];
+        }
+        double gd = 0.0;
+        for (int i = 0; i < L; ++i) { d[i] = -d[i]; gd += g[i] * d[i]; }
+        if (!(gd < 0.0) || !isfinite(gd)) {
+            npairs = 0;
+            for (int i = 0; i < L; ++i) d[i] = fr[i] ? -g[i] * (step0 / pg) : 0.0;
+        }
+        /* projected backtracking line search */
+        double lam = 1.0, Jt = J;
+        int ok = 0;
+        for (int bt = 0; bt < 40; ++bt) {
+            double gs = 0.0;
+            for (int i = 0; i < L; ++i) {
+                xt[i] = clipd(x[i] + lam * d[i], lo[i % m], hi[i % m]);
+                gs += g[i] * (xt[i] - x[i]);
+            }
+            Jt = orc_actor_cost(c, s, xt, observation, state_sys, w_critic);
+            ++nfev;
+            if (Jt <= J + 1e-4 * gs) { ok = 1; break; }
+            lam *= 0.5;
+        }
+        if (!ok) break;
+        orc_actor_grad(c, s, xt, observation, state_sys, w_critic, gn);
+        ++iters;
+        for (int i = 0; i < L; ++i) { S[head][i] = xt[i] - x[i]; Y[head][i] = gn[i] - g[i]; }
+        head = (head + 1) % ORC_OPT_MEM;
+        if (npairs < ORC_OPT_MEM) ++npairs;
+        const double Jold = J;
+        J = Jt;
+        memcpy(x, xt, sizeof(double) * (size_t)L);
+        memcpy(g, gn, sizeof(double) * (size_t)L);
+        if (fabs(Jold - J) <= f_tol * fmax(fmax(fabs(Jold), fabs(J)), 1.0)) {
+            if (++stall >= 2) break;
+        } else {
+            stall = 0;
+        }
+    }
+    if (iters_out) *iters_out = iters;
+    if (nfev_out) *nfev_out = nfev;
+    return J;
+}

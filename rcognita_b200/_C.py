@@ -68,6 +68,12 @@ def _load():
         getattr(L, name).argtypes = [sysp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp, vp]
     for name in ("rcg_actor_cost", "rcg_actor_cost_f32"):
         getattr(L, name).argtypes = [sysp, objp, i64, i32, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, dbl, vp]
+    L.rcg_actor_opt_workspace_bytes.argtypes = [sysp, objp, i64, i32]
+    L.rcg_actor_opt_workspace_bytes.restype = C.c_int64
+    L.rcg_actor_opt.argtypes = ([sysp, objp, i64, i32, vp, vp, vp, vp, i32, vp, i32, dbl, dbl, vp, i64]
+                                + [vp] * 7 + [dbl, vp])
+    L.rcg_actor_grad.argtypes = [sysp, objp, i64, i32, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp]
+    L.rcg_gather_sqn.argtypes = [i32, i64, i32, vp, i32, vp, vp, vp, vp]
     L.rcg_stage_obj.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, dbl, vp]
     L.rcg_critic.argtypes = [objp, i32, i32, i64, vp, vp, vp, i32, vp, vp]
     L.rcg_critic_cost.argtypes = [objp, i32, i32, i64, i32, vp, vp, vp, vp, vp, vp]
@@ -83,7 +89,7 @@ EXPORTS = [
     "rcg_version", "rcg_last_error_string", "rcg_device_count", "rcg_dim_state", "rcg_dim_input", "rcg_dim_critic",
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
     "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_actor_cost", "rcg_actor_cost_f32",
-    "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
+    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_gather_sqn", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 
 

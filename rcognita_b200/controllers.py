@@ -58,14 +58,18 @@ def _owner_system(fn, attr):
 class CtrlOptPred:
     """rcognita/controllers.py:679-1493.  New keywords (all optional, after the reference's):
     ``candidates`` ``[C, Nactor*m]`` shared table or ``[E, C, Nactor*m]`` per-environment sets;
-    ``num_candidates`` / ``seed`` used when ``candidates`` is None."""
+    ``num_candidates`` / ``seed`` used when ``candidates`` is None; ``actor='opt'`` replaces the plain arg-min by
+    the batched bounded minimiser ``rcg_actor_opt`` (exact adjoint gradients, projected quasi-Newton, at most
+    ``opt_iters`` iterations -- the reference's SLSQP has maxiter 300) started from the arg-min candidate
+    (``opt_start='argmin'``) or from ``action_sqn_init`` like the reference (``opt_start='init'``)."""
 
     def __init__(self, dim_input, dim_output, mode='MPC', ctrl_bnds=[], action_init=[], t0=0, sampling_time=0.1,
                  Nactor=1, pred_step_size=0.1, sys_rhs=[], sys_out=[], state_sys=[], prob_noise_pow=1,
                  is_est_model=0, model_est_stage=1, model_est_period=0.1, buffer_size=20, model_order=3,
                  model_est_checks=0, gamma=1, Ncritic=4, critic_period=0.1, critic_struct='quad-nomix',
                  stage_obj_struct='quadratic', stage_obj_pars=[], observation_target=[],
-                 candidates=None, num_candidates=256, seed=1):
+                 candidates=None, num_candidates=256, seed=1, actor='candidates', opt_start='argmin', opt_iters=300,
+                 opt_pg_tol=1e-7, opt_f_tol=1e-12):
         if is_est_model:
             raise NotImplementedError("is_est_model=1 is outside the B200 hot path (needs sippy; dead code upstream)")
         if mode not in _C.MODES:
@@ -116,6 +120,10 @@ class CtrlOptPred:
         self._obj = _C.make_objective(n, m, mode=mode, Nactor=Nactor, pred_step_size=pred_step_size, gamma=gamma,
                                       Ncritic=Ncritic, buffer_size=buffer_size, critic_struct=critic_struct,
                                       stage_obj_struct=stage_obj_struct, R1=R1, R2=R2, observation_target=tgt)
+        if actor not in ('candidates', 'opt') or opt_start not in ('argmin', 'init'):
+            raise ValueError("actor must be 'candidates' or 'opt'; opt_start 'argmin' or 'init'")
+        self.actor, self.opt_start = actor, opt_start
+        self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
         # candidate action sequences of the enumerate-and-argmin actor
         L = Nactor * m
         if candidates is None:
@@ -164,6 +172,13 @@ class CtrlOptPred:
         self._argmin = torch.full((E,), -1, dtype=_I32, device=dev)
         self._Jmin = torch.full((E,), float("nan"), dtype=_F64, device=dev)
         self.num_samples = torch.zeros((E,), dtype=torch.int64, device=dev)
+        if self.actor == 'opt':
+            L = self.Nactor * m
+            self._sqn = torch.zeros((L, E), dtype=_F64, device=dev)
+            self._sqn_init = torch.as_tensor(self.action_sqn_init, device=dev)[:, None].expand(L, E).contiguous()
+            self._opt_ws, _ = ops._opt_workspace(self._sys._sysd, self._obj, E, 1, dev)
+            self.opt_iters_used = torch.zeros((E,), dtype=_I32, device=dev)
+            self.opt_nfev_used = torch.zeros((E,), dtype=_I32, device=dev)
 
     def _ensure(self, E, batched):
         if E != self._E:
@@ -293,8 +308,23 @@ class CtrlOptPred:
         the first action of the best sequence into ``action_curr`` for the lanes with ``mask`` != 0."""
         obs, batched = to_soa(observation, self.dim_output, self.device, "observation")
         self._ensure(obs.shape[1], batched)
+        w = self._w_critic if self.mode != 'MPC' else None
+        if self.actor == 'opt':
+            # bounded minimisation of _actor_cost (what SLSQP does in the reference), one thread per environment
+            if self.opt_start == 'argmin':
+                ops.actor_cost(self._sys._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
+                               self.num_candidates, w_critic=w, w_per_env=True, mask=mask, want_J=False,
+                               argmin_out=self._argmin, Jmin_out=self._Jmin)
+                ops.gather_sqn(self._cand, self._cand_per_env, self.num_candidates, self._argmin, self._sqn, mask=mask)
+            else:
+                self._sqn.copy_(self._sqn_init)                                      # my_action_sqn_init (:1383)
+            ops.actor_opt(self._sys._sysd, self._obj, self._state_sys, obs, self._sqn, S=1, w_critic=w, w_per_env=True,
+                          mask=mask, max_iter=self.opt_iters, pg_tol=self.opt_pg_tol, f_tol=self.opt_f_tol,
+                          workspace=self._opt_ws, Jmin_out=self._Jmin, action_out=self._action_curr,
+                          iters_out=self.opt_iters_used, nfev_out=self.opt_nfev_used, want_stats=False)
+            return self._out(self._action_curr)
         ops.actor_cost(self._sys._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
-                       self.num_candidates, w_critic=self._w_critic if self.mode != 'MPC' else None, w_per_env=True,
+                       self.num_candidates, w_critic=w, w_per_env=True,
                        mask=mask, want_J=False, argmin_out=self._argmin, Jmin_out=self._Jmin,
                        action_out=self._action_curr)
         return self._out(self._action_curr)

@@ -1,0 +1,6 @@
+// actor_opt_ni.cu -- instantiates the actor-optimiser kernels of actor_opt_impl.cuh for one system.
+#include "actor_opt_impl.cuh"
+
+namespace rcg {
+int launch_opt_ni(const OptLaunch<double> &L) { return launch_opt_sys<double, RCG_SYS_3WROBOT_NI>(L); }
+}  // namespace rcg

@@ -31,13 +31,20 @@ class ClosedLoopEngine:
     rcognita/simulator.py:150) and ``CtrlOptPred.sampling_time``; ``candidates`` is a shared
     table ``[C, Nactor*m]`` (rows = action sequences like the reference's ``action_sqn``) or a
     per-environment set ``[E, C, Nactor*m]``.
+
+    ``actor`` selects what stands in for ``_actor_optimizer`` (controllers.py:1330-1427): ``"candidates"`` =
+    enumerate-and-argmin over the candidate set; ``"opt"`` = the batched bounded minimiser ``rcg_actor_opt``
+    (exact adjoint gradients, projected quasi-Newton; at most ``opt_iters`` iterations per sample) started from the
+    arg-min candidate (``opt_start="argmin"``) or, like the reference, from ``action_sqn_init`` every time
+    (``opt_start="init"``; the candidate set is then unused and may be ``None``).
     """
 
     def __init__(self, system, state_init, candidates, *, pars=(), ctrl_bnds=None, mode="MPC", Nactor=6, dt=0.01,
                  pred_step_size=None, t0=0.0, t1=10.0, first_step=1e-6, atol=1e-5, rtol=1e-3, gamma=1.0, R1=None,
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
-                 buffer_size=10, critic_period=None, critic_fit_evals=0):
+                 buffer_size=10, critic_period=None, critic_fit_evals=0, actor="candidates", opt_start="argmin",
+                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -66,6 +73,16 @@ class ClosedLoopEngine:
             self.E = E = x0.shape[0]
             self.y0 = x0.t().contiguous()                                  # [n, E]
             L = Nactor * m
+            if actor not in ("candidates", "opt") or opt_start not in ("argmin", "init"):
+                raise ValueError("actor must be 'candidates' or 'opt'; opt_start 'argmin' or 'init'")
+            self.actor, self.opt_start = actor, opt_start
+            self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
+            if actor == "opt" and dtype != torch.float64:
+                raise ValueError("the actor optimiser runs in fp64")
+            if candidates is None:
+                if not (actor == "opt" and opt_start == "init"):
+                    raise ValueError("candidates are required unless actor='opt' with opt_start='init'")
+                candidates = np.zeros((1, L))
             cand = _as_dev(candidates, dtype, self.device)
             if cand.dim() == 2:
                 if cand.shape[1] != L:
@@ -146,6 +163,11 @@ class ClosedLoopEngine:
             self.critic_flag = torch.empty((E,), dtype=torch.int32, device=dev)
             self.Jc = torch.empty((E,), dtype=dt, device=dev)
             self.nfits = torch.empty((E,), dtype=torch.int32, device=dev)
+        if self.actor == "opt":
+            L = self.obj.Nactor * m
+            self.sqn = torch.zeros((L, E), dtype=dt, device=dev)
+            self.sqn_init = self.action_init.repeat(self.obj.Nactor)[:, None].expand(L, E).contiguous()   # rep_mat (:973-978)
+            self.opt_ws, _ = ops._opt_workspace(self.sysd, self.obj, E, 1, dev)
 
     def reset(self):
         """Documented intent of ``Simulator.reset`` + ``CtrlOptPred.reset``: restore y0, t0,
@@ -227,6 +249,19 @@ class ClosedLoopEngine:
     def _actor_launch(self):
         if self.critic_fit:
             self._critic_update()
+        if self.actor == "opt":
+            if self.opt_start == "argmin":
+                ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
+                               w_critic=self.w, w_per_env=self.w_per_env, mask=self.sample_flag, want_J=False,
+                               argmin_out=self.argmin, Jmin_out=self.Jmin)
+                ops.gather_sqn(self.cand, self.cand_per_env, self.C, self.argmin, self.sqn, mask=self.sample_flag)
+            else:
+                self.sqn.copy_(self.sqn_init)              # my_action_sqn_init (:1383), the same for every sample
+            ops.actor_opt(self.sysd, self.obj, self.state_sys, self.y, self.sqn, S=1, w_critic=self.w,
+                          w_per_env=self.w_per_env, mask=self.sample_flag, max_iter=self.opt_iters,
+                          pg_tol=self.opt_pg_tol, f_tol=self.opt_f_tol, workspace=self.opt_ws, Jmin_out=self.Jmin,
+                          action_out=self.action, accum=self.accum, sampling_time=self.sampling_time, want_stats=False)
+            return
         ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,
                        w_critic=self.w, w_per_env=self.w_per_env, mask=self.sample_flag, want_J=False,
                        argmin_out=self.argmin, Jmin_out=self.Jmin, action_out=self.action, accum=self.accum,

@@ -125,6 +125,75 @@ def actor_cost(sysd, obj, state_sys, obs, cand, cand_per_env, C_, w_critic=None,
     return J_out, argmin_out, Jmin_out
 
 
+def _opt_workspace(sysd, obj, E, S, device, workspace=None):
+    need = int(_C.lib.rcg_actor_opt_workspace_bytes(C.byref(sysd), C.byref(obj), E, S))
+    if need < 0:
+        raise ValueError("rcg_actor_opt_workspace_bytes: bad arguments")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need // 8, 1),), dtype=_F64, device=device)
+    return workspace, need
+
+
+def actor_grad(sysd, obj, state_sys, obs, sqn, S=1, w_critic=None, w_per_env=False, workspace=None):
+    """``_actor_cost`` and its exact gradient for E x S action sequences: ``sqn`` ``[N*m, E*S]`` ->
+    ``(J [E*S], grad [N*m, E*S])`` (adjoint of the Euler rollout; the reference's SLSQP uses forward differences)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = obs.shape[1]
+    L = obj.Nactor * m
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    wshape = None if w_critic is None else ((dimc, E) if w_per_env else (dimc,))
+    ws, nbytes = _opt_workspace(sysd, obj, E, S, obs.device, workspace)
+    J = torch.empty((E * S,), dtype=_F64, device=obs.device)
+    g = torch.empty((L, E * S), dtype=_F64, device=obs.device)
+    _C.check(_C.lib.rcg_actor_grad(C.byref(sysd), C.byref(obj), E, int(S), _ptr(state_sys, _F64, (n, E), "state_sys"),
+                                   _ptr(obs, _F64, (n, E), "obs"), _ptr(sqn, _F64, (L, E * S), "sqn"),
+                                   _ptr(w_critic, _F64, wshape, "w_critic", optional=True), int(bool(w_per_env)),
+                                   _ptr(ws), nbytes, _ptr(J), _ptr(g), _stream()), "rcg_actor_grad")
+    return J, g
+
+
+def actor_opt(sysd, obj, state_sys, obs, sqn, S=1, w_critic=None, w_per_env=False, mask=None, max_iter=300,
+              pg_tol=1e-7, f_tol=1e-12, workspace=None, J_out=None, iters_out=None, nfev_out=None, best_out=None,
+              Jmin_out=None, action_out=None, accum=None, sampling_time=0.0, want_stats=True):
+    """``CtrlOptPred._actor_optimizer``: bounded minimisation of ``_actor_cost`` from the E x S start points in
+    ``sqn`` ``[N*m, E*S]`` (overwritten with the minimisers).  Returns ``(J [E*S], iters [E*S], nfev [E*S])``
+    (``None`` each when ``want_stats`` is false and no output tensor is given)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = obs.shape[1]
+    L = obj.Nactor * m
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    wshape = None if w_critic is None else ((dimc, E) if w_per_env else (dimc,))
+    ws, nbytes = _opt_workspace(sysd, obj, E, S, obs.device, workspace)
+    if want_stats:
+        J_out = torch.empty((E * S,), dtype=_F64, device=obs.device) if J_out is None else J_out
+        iters_out = torch.zeros((E * S,), dtype=_I32, device=obs.device) if iters_out is None else iters_out
+        nfev_out = torch.zeros((E * S,), dtype=_I32, device=obs.device) if nfev_out is None else nfev_out
+    _C.check(_C.lib.rcg_actor_opt(C.byref(sysd), C.byref(obj), E, int(S), _ptr(state_sys, _F64, (n, E), "state_sys"),
+                                  _ptr(obs, _F64, (n, E), "obs"), _ptr(sqn, _F64, (L, E * S), "sqn"),
+                                  _ptr(w_critic, _F64, wshape, "w_critic", optional=True), int(bool(w_per_env)),
+                                  _ptr(mask, _I32, (E,), "mask", optional=True), int(max_iter), float(pg_tol),
+                                  float(f_tol), _ptr(ws), nbytes,
+                                  _ptr(J_out, _F64, (E * S,), "J_out", optional=True),
+                                  _ptr(iters_out, _I32, (E * S,), "iters_out", optional=True),
+                                  _ptr(nfev_out, _I32, (E * S,), "nfev_out", optional=True),
+                                  _ptr(best_out, _I32, (E,), "best_out", optional=True),
+                                  _ptr(Jmin_out, _F64, (E,), "Jmin_out", optional=True),
+                                  _ptr(action_out, _F64, (m, E), "action_out", optional=True),
+                                  _ptr(accum, _F64, (E,), "accum", optional=True), float(sampling_time), _stream()),
+             "rcg_actor_opt")
+    return J_out, iters_out, nfev_out
+
+
+def gather_sqn(cand, cand_per_env, C_, idx, out, mask=None):
+    """Start points of the optimiser from an arg-min: ``out[:, e]`` = candidate ``idx[e]`` of environment e."""
+    L, E = out.shape
+    ncol = E * C_ if cand_per_env else C_
+    _C.check(_C.lib.rcg_gather_sqn(int(L), E, int(C_), _ptr(cand, _F64, (L, ncol), "cand"), int(bool(cand_per_env)),
+                                   _ptr(idx, _I32, (E,), "idx"), _ptr(mask, _I32, (E,), "mask", optional=True),
+                                   _ptr(out, _F64, (L, E), "out"), _stream()), "rcg_gather_sqn")
+    return out
+
+
 def stage_obj(obj, n, m, obs, act, out=None, accum=None, scale=0.0, want_out=True):
     """``CtrlOptPred.stage_obj`` (+ fused ``upd_accum_obj`` when ``accum`` is given)."""
     E = obs.shape[1]

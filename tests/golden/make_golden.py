@@ -277,6 +277,67 @@ def gen_critic_fit():
         json.dump(out, fh)
     print("critic_fit.json", len(out), "cases; J_ref range", min(c["J_ref"] for c in out), max(c["J_ref"] for c in out))
 
+# --------------------------------------------------------------------------- actor optimiser (reference SLSQP as the bar)
+def gen_actor_opt():
+    """Reference `_actor_optimizer` (SLSQP on `_actor_cost`, controllers.py:1330-1427) on seeded problems.  The
+    method returns only the first action; `controllers.minimize` is wrapped to also capture the full minimiser
+    and its cost (the call itself is the reference's, unmodified).  The minimum found is the bar for the batched
+    projected-gradient optimiser (the minimiser need not be unique: the last action never enters an MPC cost)."""
+    out = []
+    rec = {}
+    orig_min = controllers.minimize
+
+    def wrapped(fun, x0, **kw):
+        res = orig_min(fun, x0, **kw)
+        rec["res"] = res
+        return res
+
+    controllers.minimize = wrapped
+    horizons = {"3wrobotNI": 6, "3wrobot": 10, "2tank": 8}
+    try:
+        for name, cfg in SYSTEMS.items():
+            n, m, p = cfg["n"], cfg["m"], cfg["n"] + cfg["m"]
+            my_sys = make_sys(name)
+            rng = np.random.default_rng(777 + n)
+            A = rng.normal(size=(p, p)); R1_dense = A @ A.T / p
+            N0 = horizons[name]
+            plan = []
+            for scale in (6.0, 6.0, 1.0, 0.2, 0.05, 0.01):                      # far from / near the goal
+                plan.append(dict(mode="MPC", cs="quad-nomix", N=N0, gamma=1.0, dense=False, scale=scale))
+            plan.append(dict(mode="MPC", cs="quad-nomix", N=3, gamma=0.9, dense=True, scale=2.0))
+            plan.append(dict(mode="MPC", cs="quad-nomix", N=12, gamma=0.95, dense=False, scale=0.5))
+            for mode in ("RQL", "SQL"):
+                for cs in ("quad-lin", "quadratic", "quad-nomix", "quad-mix"):
+                    plan.append(dict(mode=mode, cs=cs, N=N0, gamma=1.0, dense=False, scale=3.0))
+                    plan.append(dict(mode=mode, cs=cs, N=5, gamma=0.9, dense=False, scale=0.3))
+            for pl in plan:
+                tgt = cfg["target"]
+                x_sys = rng.uniform(-1, 1, size=n) * pl["scale"] + (np.array(tgt) if len(tgt) else 0.0)
+                ob = x_sys + rng.normal(size=n) * 0.005 * pl["scale"]
+                R1 = R1_dense if pl["dense"] else None
+                ctrl = make_ctrl(name, my_sys, pl["mode"], pl["N"], critic_struct=pl["cs"], gamma=pl["gamma"], R1=R1,
+                                 state_sys=x_sys)
+                if pl["cs"] in ("quad-lin", "quad-mix"):
+                    ctrl.w_critic = rng.uniform(-1, 2, size=ctrl.dim_critic)
+                else:
+                    ctrl.w_critic = rng.uniform(0, 2, size=ctrl.dim_critic)
+                a1 = ctrl._actor_optimizer(ob)
+                res = rec["res"]
+                x_ref = np.asarray(res.x, dtype=float)
+                out.append(dict(system=name, mode=pl["mode"], critic_struct=pl["cs"], N=pl["N"], gamma=pl["gamma"],
+                                R1=L(R1_dense if pl["dense"] else np.diag(np.array(cfg["R1_diag"], dtype=float))),
+                                target=list(tgt), pred_step=float(ctrl.pred_step_size), state_sys=L(x_sys), obs=L(ob),
+                                w=L(ctrl.w_critic), x_init=L(ctrl.action_sqn_init), x_ref=L(x_ref),
+                                J_ref=float(ctrl._actor_cost(x_ref, ob)),
+                                J_init=float(ctrl._actor_cost(np.asarray(ctrl.action_sqn_init, dtype=float), ob)),
+                                nit=int(res.nit), nfev=int(res.nfev), status=int(res.status), first_action=L(a1)))
+    finally:
+        controllers.minimize = orig_min
+    with open(os.path.join(HERE, "actor_opt.json"), "w") as fh:
+        json.dump(out, fh)
+    print("actor_opt.json", len(out), "cases; nfev", min(c["nfev"] for c in out), "..", max(c["nfev"] for c in out),
+          "status", sorted(set(c["status"] for c in out)))
+
 # --------------------------------------------------------------------------- config 1: preset-faithful SLSQP episode (App. A.2)
 def gen_config1():
     name = "3wrobotNI"
@@ -314,7 +375,7 @@ def gen_config1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit"]
+    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit", "actor_opt"]
     if "functions" in which:
         gen_functions()
     if "integrator" in which:
@@ -325,3 +386,5 @@ if __name__ == "__main__":
         gen_config1()
     if "critic_fit" in which:
         gen_critic_fit()
+    if "actor_opt" in which:
+        gen_actor_opt()

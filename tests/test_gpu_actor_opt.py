@@ -1,0 +1,298 @@
+"""GPU parity tests of the batched actor optimiser (rcg_actor_grad / rcg_actor_opt / rcg_gather_sqn), the stand-in
+for CtrlOptPred._actor_optimizer (rcognita/controllers.py:1330-1427).
+
+Bars: the adjoint gradient equals the oracle's analytic gradient to 1e-9 (relative to the gradient's largest entry)
+and the cost equals orc_actor_cost to 1e-9; the minimum found from the reference's own start point
+(action_sqn_init) is <= the live reference's SLSQP minimum on every committed golden problem (1e-7 relative slack
+= SLSQP's own tolerance); the CUDA iteration and the oracle's restatement of it end at the same cost; the result is
+feasible, never above the start cost, and invariant to batching.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from golden_util import DIMS, PRESET, load  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def rb():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    import rcognita_b200
+    from rcognita_b200 import _C, ops
+    torch.cuda.set_device(0)
+    return rcognita_b200, _C, ops
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda", dtype=dtype)
+
+
+def _descr(_C, c):
+    name = c["system"]
+    n, m = DIMS[name]
+    sysd = _C.make_system(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    obj = _C.make_objective(n, m, mode=c["mode"], Nactor=c["N"], pred_step_size=c["pred_step"], gamma=c["gamma"],
+                            critic_struct=c["critic_struct"], R1=np.array(c["R1"]), observation_target=c["target"])
+    s = oracle.make_sys(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    ct = oracle.make_ctrl(n, m, mode=c["mode"], Nactor=c["N"], pred_step_size=c["pred_step"], gamma=c["gamma"],
+                          critic_struct=c["critic_struct"], R1=np.array(c["R1"]), observation_target=c["target"])
+    return n, m, sysd, obj, s, ct
+
+
+GOLD = load("actor_opt.json")
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD)))
+def test_actor_opt_reaches_the_reference_slsqp_minimum(rb, idx):
+    """From action_sqn_init (the reference's start point) the batched optimiser must end at a cost <= SLSQP's."""
+    _, _C, ops = rb
+    c = GOLD[idx]
+    n, m, sysd, obj, s, ct = _descr(_C, c)
+    L = c["N"] * m
+    # lane 0: the golden problem; lanes 1..: the same problem from perturbed starts (exercise divergence)
+    E = 5
+    rng = np.random.default_rng(idx)
+    b = np.array(PRESET[c["system"]]["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], c["N"]), np.tile(b[:, 1], c["N"])
+    starts = np.stack([np.array(c["x_init"])] + [rng.uniform(lo, hi) for _ in range(E - 1)], axis=1)      # [L, E]
+    state = dev(np.tile(np.array(c["state_sys"])[:, None], (1, E)))
+    obs = dev(np.tile(np.array(c["obs"])[:, None], (1, E)))
+    w = dev(c["w"]) if c["mode"] != "MPC" else None
+    sqn = dev(starts)
+    J0, _ = ops.actor_grad(sysd, obj, state, obs, sqn, w_critic=w)
+    J, iters, nfev = ops.actor_opt(sysd, obj, state, obs, sqn, w_critic=w, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+    J, x = J.cpu().numpy(), sqn.cpu().numpy()
+    assert abs(J0[0].item() - c["J_init"]) <= 1e-9 * max(abs(c["J_init"]), 1.0)
+    # feasible, monotone
+    assert np.all(x >= lo[:, None]) and np.all(x <= hi[:, None])
+    assert np.all(J <= J0.cpu().numpy() + 1e-12 * np.abs(J0.cpu().numpy()))
+    # the returned cost is _actor_cost of the returned sequence (oracle = the reference's arithmetic)
+    for e in range(E):
+        Jo = oracle.actor_cost(ct, s, x[:, e], c["obs"], c["state_sys"], c["w"] if c["mode"] != "MPC" else None)
+        assert abs(J[e] - Jo) <= 1e-9 * max(abs(Jo), 1e-3), (e, J[e], Jo)
+    # the bar: the live reference's SLSQP minimum from the same start
+    tol = 1e-7 * max(abs(c["J_ref"]), 1.0)
+    assert J[0] <= c["J_ref"] + tol, f"J={J[0]!r} > SLSQP {c['J_ref']!r} (iters {iters[0].item()}, nfev {nfev[0].item()})"
+    # CUDA iteration vs the oracle's restatement of the same algorithm.  The two evaluate the heading trigonometry
+    # differently (rotation recurrence vs sincos per stage, ~1e-15 apart), so in flat ill-conditioned valleys the
+    # iterates separate after some dozens of steps and stop at slightly different points of the valley floor: the
+    # costs agree to 1e-3 of max(|J|, 1) there (1e-9 where the problem is well conditioned) and both meet the bar.
+    _, Jorc, it_o, _ = oracle.actor_opt(ct, s, c["x_init"], c["obs"], c["state_sys"],
+                                        c["w"] if c["mode"] != "MPC" else None, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+    assert Jorc <= c["J_ref"] + tol
+    well_conditioned = max(iters[0].item(), it_o) <= 30
+    assert abs(J[0] - Jorc) <= (1e-9 if well_conditioned else 1e-3) * max(abs(Jorc), 1.0), (J[0], Jorc, iters[0].item(), it_o)
+
+
+@pytest.mark.parametrize("name,mode,cs,N,dense", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, False), ("3wrobotNI", "RQL", "quad-lin", 6, False),
+    ("3wrobotNI", "SQL", "quad-mix", 7, False), ("3wrobotNI", "MPC", "quad-nomix", 4, True),
+    ("3wrobot", "RQL", "quadratic", 10, False), ("3wrobot", "SQL", "quad-lin", 5, False),
+    ("3wrobot", "MPC", "quad-nomix", 12, False), ("3wrobot", "RQL", "quad-mix", 3, True),
+    ("2tank", "SQL", "quad-nomix", 8, False), ("2tank", "RQL", "quadratic", 9, False),
+    ("2tank", "MPC", "quad-nomix", 8, True), ("2tank", "SQL", "quad-lin", 64, False),
+])
+def test_actor_grad_vs_oracle(rb, name, mode, cs, N, dense):
+    """Adjoint gradient == the oracle's analytic gradient (itself pinned to finite differences of the reference's
+    cost in tests/test_oracle_golden.py), specialised and generic kernels, S > 1, per-environment weights."""
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    p = n + m
+    rng = np.random.default_rng(abs(hash((name, mode, cs, N))) % 2**32)
+    E, S = 37, 4
+    R1 = np.diag(PRESET[name]["R1_diag"]).astype(float)
+    if dense:
+        A = rng.normal(size=(p, p)); R1 = A @ A.T / p
+    tgt = PRESET[name]["target"]
+    sysd = _C.make_system(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    kw = dict(mode=mode, Nactor=N, pred_step_size=PRESET[name]["dt"] * PRESET[name]["psm"], gamma=0.95,
+              critic_struct=cs, R1=R1, observation_target=tgt)
+    obj = _C.make_objective(n, m, **kw)
+    s = oracle.make_sys(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    ct = oracle.make_ctrl(n, m, **kw)
+    dimc = oracle.dim_critic(cs, n, m)
+    b = np.array(PRESET[name]["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+    x_sys = rng.uniform(-3, 3, size=(E, n))
+    ob = x_sys + rng.normal(size=(E, n)) * 0.01
+    W = rng.uniform(-1, 2, size=(E, dimc))
+    U = rng.uniform(lo, hi, size=(E, S, N * m))
+    sqn = dev(U.transpose(2, 0, 1).reshape(N * m, E * S))
+    J, g = ops.actor_grad(sysd, obj, dev(x_sys.T.copy()), dev(ob.T.copy()), sqn, S=S,
+                          w_critic=dev(W.T.copy()) if mode != "MPC" else None, w_per_env=True)
+    J, g = J.cpu().numpy().reshape(E, S), g.cpu().numpy().reshape(N * m, E, S)
+    for e in range(0, E, 3):
+        for k in range(S):
+            Jo, go = oracle.actor_grad(ct, s, U[e, k], ob[e], x_sys[e], W[e] if mode != "MPC" else None)
+            assert abs(J[e, k] - Jo) <= 1e-9 * max(abs(Jo), 1e-3)
+            assert np.max(np.abs(g[:, e, k] - go)) <= 1e-9 * max(np.max(np.abs(go)), 1e-3)
+
+
+def test_actor_opt_multi_start_mask_and_action_handover(rb):
+    """S starts per environment: best_out / Jmin_out = np.argmin over the starts' final costs, action_out = first
+    action of the best minimiser, accum += stage_obj * sampling_time; masked environments are untouched."""
+    _, _C, ops = rb
+    name, N = "3wrobotNI", 6
+    n, m = DIMS[name]
+    E, S = 70, 8
+    rng = np.random.default_rng(3)
+    sysd = _C.make_system(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    kw = dict(mode="MPC", Nactor=N, pred_step_size=0.01, gamma=1.0, R1=np.diag(PRESET[name]["R1_diag"]).astype(float))
+    obj = _C.make_objective(n, m, **kw)
+    ct = oracle.make_ctrl(n, m, **kw)
+    b = np.array(PRESET[name]["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+    x_sys = np.stack([rng.uniform(-1, 1, E), rng.uniform(-1, 1, E), rng.uniform(-np.pi, np.pi, E)], 1) * 0.3
+    U = rng.uniform(lo, hi, size=(E, S, N * m))
+    sqn = dev(U.transpose(2, 0, 1).reshape(N * m, E * S))
+    before = sqn.clone()
+    mask = torch.ones(E, dtype=torch.int32, device="cuda")
+    mask[5::7] = 0
+    best = torch.full((E,), -7, dtype=torch.int32, device="cuda")
+    Jmin = torch.full((E,), -7.0, dtype=torch.float64, device="cuda")
+    act = torch.full((m, E), -7.0, dtype=torch.float64, device="cuda")
+    accum = torch.zeros(E, dtype=torch.float64, device="cuda")
+    st = dev(x_sys.T.copy())
+    J, iters, nfev = ops.actor_opt(sysd, obj, st, st, sqn, S=S, mask=mask, max_iter=60, best_out=best, Jmin_out=Jmin,
+                                   action_out=act, accum=accum, sampling_time=0.01)
+    J = J.cpu().numpy().reshape(E, S)
+    x = sqn.cpu().numpy().reshape(N * m, E, S)
+    mk = mask.cpu().numpy().astype(bool)
+    assert np.array_equal(sqn.reshape(N * m, E, S)[:, ~mask.bool()].cpu().numpy(),
+                          before.reshape(N * m, E, S)[:, ~mask.bool()].cpu().numpy())
+    assert np.all(best.cpu().numpy()[~mk] == -7) and np.all(act.cpu().numpy()[:, ~mk] == -7.0)
+    for e in np.nonzero(mk)[0]:
+        bi = int(np.argmin(J[e]))
+        assert best[e].item() == bi
+        assert Jmin[e].item() == J[e, bi]
+        assert np.array_equal(act[:, e].cpu().numpy(), x[:m, e, bi])
+        so = oracle.stage_obj(ct, n, m, x_sys[e], x[:m, e, bi])
+        assert abs(accum[e].item() - so * 0.01) <= 1e-12 * max(abs(so), 1.0)
+    assert np.all(accum.cpu().numpy()[~mk] == 0.0)
+
+
+def test_actor_opt_batch_invariance_and_gather(rb):
+    """The minimiser of an environment does not depend on its neighbours (batch of 1 == lane of a big batch, bit
+    for bit), and rcg_gather_sqn picks the arg-min candidate as the start point."""
+    _, _C, ops = rb
+    name, N, C_ = "3wrobot", 10, 64
+    n, m = DIMS[name]
+    E = 300
+    rng = np.random.default_rng(11)
+    sysd = _C.make_system(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    obj = _C.make_objective(n, m, mode="RQL", Nactor=N, pred_step_size=0.02, gamma=1.0, critic_struct="quadratic",
+                            R1=np.diag(PRESET[name]["R1_diag"]).astype(float))
+    b = np.array(PRESET[name]["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+    x_sys = rng.uniform(-2, 2, size=(E, n))
+    st = dev(x_sys.T.copy())
+    w = dev(rng.uniform(0, 2, size=oracle.dim_critic("quadratic", n, m)))
+    cand = dev(rng.uniform(lo, hi, size=(C_, N * m)).T.copy())                       # shared table [L, C]
+    _, am, _ = ops.actor_cost(sysd, obj, st, st, cand, False, C_, w_critic=w, want_J=False)
+    sqn = torch.empty((N * m, E), dtype=torch.float64, device="cuda")
+    ops.gather_sqn(cand, False, C_, am, sqn)
+    assert torch.equal(sqn, cand[:, am.long()])
+    ref = sqn.clone()
+    J, iters, _ = ops.actor_opt(sysd, obj, st, st, sqn, w_critic=w, max_iter=40)
+    for e in (0, 17, 299):
+        one = ref[:, e:e + 1].clone()
+        J1, it1, _ = ops.actor_opt(sysd, obj, st[:, e:e + 1].contiguous(), st[:, e:e + 1].contiguous(), one, w_critic=w,
+                                   max_iter=40)
+        assert torch.equal(one[:, 0], sqn[:, e]) and J1[0].item() == J[e].item() and it1[0].item() == iters[e].item()
+
+
+def test_actor_opt_errors_are_loud(rb):
+    _, _C, ops = rb
+    name = "2tank"
+    n, m = DIMS[name]
+    sysd = _C.make_system(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    obj = _C.make_objective(n, m, mode="SQL", Nactor=8, R1=np.eye(3))
+    st = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+    sqn = torch.zeros((8, 4 * 3), dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="power of two"):
+        ops.actor_opt(sysd, obj, st, st, sqn, S=3, w_critic=torch.ones(3, dtype=torch.float64, device="cuda"))
+    sqn = torch.zeros((8, 4), dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="w_critic"):
+        ops.actor_opt(sysd, obj, st, st, sqn)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.actor_opt(sysd, obj, st.cpu(), st, sqn, w_critic=torch.ones(3, dtype=torch.float64, device="cuda"))
+
+
+def _oracle_loop_with_optimizer(s, ct, x0, action_init, dt, t1, N, m, max_iter):
+    """The headless main loop (presets/main_3wrobot_NI.py:415-440) for one environment with the oracle's pieces and
+    the restated minimiser as _actor_optimizer, started from action_sqn_init at every sample like the reference."""
+    r = oracle.Rk45(s, x0, 0.0, t1, dt / 2)
+    sqn_init = np.tile(action_init, N)
+    action, state_sys, clock, accum, steps, samples = np.array(action_init, dtype=float), np.array(x0, dtype=float), 0.0, 0.0, 0, 0
+    n = len(x0)
+    while True:
+        r.step()
+        steps += 1
+        t, obs = r.t, r.y
+        if t - clock >= dt:
+            clock = t
+            x, _, _, _ = oracle.actor_opt(ct, s, sqn_init, obs, state_sys, None, max_iter=max_iter, pg_tol=1e-7, f_tol=1e-12)
+            action = x[:m].copy()
+            samples += 1
+        r.receive_action(action)
+        state_sys = r.y
+        accum += oracle.stage_obj(ct, n, m, obs, action) * dt
+        if t >= t1:
+            return r.y, accum, steps, samples
+
+
+def test_closed_loop_with_optimizer_vs_oracle(rb):
+    """Engine with actor='opt', opt_start='init' (the reference's protocol: every sample minimises from
+    action_sqn_init) against the same loop assembled from the oracle: identical step and sample counts,
+    trajectories and accumulated objective to 1e-6 relative (north star: 1e-6 on trajectories)."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    name, N, dt, t1 = "3wrobotNI", 6, 0.01, 0.4
+    n, m = DIMS[name]
+    rng = np.random.default_rng(21)
+    E = 6
+    x0 = np.stack([rng.uniform(-6, 6, E), rng.uniform(-6, 6, E), rng.uniform(-np.pi, np.pi, E)], 1)
+    x0[-1] = [0.02, -0.01, 0.03]                                   # near the goal: interior minimisers
+    R1 = PRESET[name]["R1_diag"]
+    eng = ClosedLoopEngine(name, x0, None, ctrl_bnds=PRESET[name]["bnds"], mode="MPC", Nactor=N, dt=dt, t1=t1, R1=R1,
+                           actor="opt", opt_start="init", opt_iters=300)
+    eng.run()
+    got = eng.results()
+    s = oracle.make_sys(name, [], PRESET[name]["bnds"])
+    ct = oracle.make_ctrl(n, m, mode="MPC", Nactor=N, pred_step_size=dt, R1=R1)
+    for e in range(E):
+        y, accum, steps, samples = _oracle_loop_with_optimizer(s, ct, x0[e], [-2.5, -0.5], dt, t1, N, m, 300)
+        assert got["nsteps"][e] == steps and got["nsamples"][e] == samples
+        assert np.max(np.abs(got["y"][e] - y) / np.maximum(np.abs(y), 1e-2)) <= 1e-6, (e, got["y"][e], y)
+        assert abs(got["accum"][e] - accum) <= 1e-6 * abs(accum)
+
+
+def test_config1_episode_with_optimizer_matches_the_reference_slsqp_controller(rb):
+    """BASELINE config 1 (presets/main_3wrobot_NI.py, MPC, Nactor=6, dt=0.01, t1=10 from [5, 5, -3pi/4]): the live
+    reference with its SLSQP controller accumulates 71.3188 over 2004 solver steps
+    (tests/golden/config1_slsqp_episode.npz).  The batched optimiser as the controller must do as well: within 1e-3
+    relative from the reference's own start point, and no worse when warm-started from the arg-min candidate;
+    enumerate-and-argmin alone (256 random candidates) cannot (76.4)."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    g = np.load(__import__("os").path.join(__import__("golden_util").GOLDEN, "config1_slsqp_episode.npz"))
+    ref_accum, ref_steps = float(g["rows"][-1][7]), g["rows"].shape[0]
+    name, N = "3wrobotNI", 6
+    b = np.array(PRESET[name]["bnds"], dtype=float)
+    cand = np.random.default_rng(1).uniform(np.tile(b[:, 0], N), np.tile(b[:, 1], N), size=(256, 2 * N))
+    res = {}
+    for tag, kw in (("init", dict(actor="opt", opt_start="init")), ("argmin", dict(actor="opt", opt_start="argmin")),
+                    ("candidates", dict(actor="candidates"))):
+        eng = ClosedLoopEngine(name, np.array([[5, 5, -3 * np.pi / 4]]), cand, ctrl_bnds=PRESET[name]["bnds"], mode="MPC",
+                               Nactor=N, dt=0.01, t1=10.0, R1=PRESET[name]["R1_diag"], **kw)
+        eng.run()
+        r = eng.results()
+        res[tag] = (float(r["accum"][0]), int(r["nsteps"][0]), r["y"][0])
+    assert abs(res["init"][0] - ref_accum) <= 1e-3 * ref_accum, res
+    assert res["argmin"][0] <= ref_accum * (1 + 1e-4), res
+    assert abs(res["init"][1] - ref_steps) <= 0.01 * ref_steps and abs(res["argmin"][1] - ref_steps) <= 0.01 * ref_steps
+    assert np.max(np.abs(res["argmin"][2])) <= 0.02 and np.max(np.abs(res["init"][2])) <= 0.02      # parked at the origin
+    assert res["candidates"][0] > ref_accum * 1.03

@@ -226,3 +226,62 @@ def test_config1_slsqp_episode_replay(golden_dir):
         assert mixed_err(r.y, rows[k, 1:4], floor=1e-2) <= 1e-9, k
     assert r.nfev == 12025 and r.status == "finished"
     assert rel_err(acc, rows[-1, 7]) <= 1e-10
+
+
+# ------------------------------------------------------------------ actor optimiser (oracle/rcg_oracle_opt.c)
+
+def _opt_case(c):
+    name = c["system"]
+    n, m = DIMS[name]
+    s = oracle.make_sys(name, PRESET[name]["pars"], PRESET[name]["bnds"])
+    ct = oracle.make_ctrl(n, m, mode=c["mode"], Nactor=c["N"], pred_step_size=c["pred_step"], gamma=c["gamma"],
+                          critic_struct=c["critic_struct"], R1=np.array(c["R1"]), observation_target=c["target"])
+    w = c["w"] if c["mode"] != "MPC" else None
+    return s, ct, w
+
+
+def test_actor_opt_golden_costs_are_the_references():
+    """The oracle's _actor_cost reproduces the live reference's cost at SLSQP's minimiser and at the start."""
+    for c in load("actor_opt.json"):
+        s, ct, w = _opt_case(c)
+        for x, J in ((c["x_ref"], c["J_ref"]), (c["x_init"], c["J_init"])):
+            got = oracle.actor_cost(ct, s, x, c["obs"], c["state_sys"], w)
+            assert abs(got - J) <= 1e-9 * max(abs(J), 1e-6), (c["system"], c["mode"], got, J)
+
+
+def test_actor_grad_matches_finite_differences_of_the_reference_cost():
+    """Adjoint gradient vs Richardson-extrapolated central differences of orc_actor_cost (which is pinned to the
+    live reference): this is the derivative SLSQP approximates by forward differences."""
+    rng = np.random.default_rng(0)
+    for c in load("actor_opt.json"):
+        s, ct, w = _opt_case(c)
+        x = np.array(c["x_ref"]) + rng.normal(size=len(c["x_ref"])) * 0.1
+        J, g = oracle.actor_grad(ct, s, x, c["obs"], c["state_sys"], w)
+        f = lambda z: oracle.actor_cost(ct, s, z, c["obs"], c["state_sys"], w)       # noqa: E731
+        assert J == f(x)
+        gf = np.zeros_like(g)
+        for i in range(x.size):
+            h = 1e-3 * max(1.0, abs(x[i]))
+
+            def cd(hh):
+                xp, xm = x.copy(), x.copy()
+                xp[i] += hh
+                xm[i] -= hh
+                return (f(xp) - f(xm)) / (2 * hh)
+            gf[i] = (4 * cd(h / 2) - cd(h)) / 3
+        assert np.max(np.abs(g - gf)) <= 1e-7 * max(np.max(np.abs(gf)), 1e-6), (c["system"], c["mode"], c["critic_struct"])
+
+
+def test_actor_opt_oracle_reaches_the_reference_slsqp_minimum():
+    """From the reference's start point (action_sqn_init) the restated minimiser ends at or below the cost the live
+    reference's SLSQP reached, stays inside the box, and never goes above the start cost."""
+    for c in load("actor_opt.json"):
+        s, ct, w = _opt_case(c)
+        x, J, iters, nfev = oracle.actor_opt(ct, s, c["x_init"], c["obs"], c["state_sys"], w, max_iter=300,
+                                             pg_tol=1e-7, f_tol=1e-12)
+        b = np.array(PRESET[c["system"]]["bnds"], dtype=float)
+        lo, hi = np.tile(b[:, 0], c["N"]), np.tile(b[:, 1], c["N"])
+        assert np.all(x >= lo) and np.all(x <= hi)
+        assert J <= c["J_init"] + 1e-12 * abs(c["J_init"])
+        assert J <= c["J_ref"] + 1e-7 * max(abs(c["J_ref"]), 1.0), (c["system"], c["mode"], c["critic_struct"], c["N"], J, c["J_ref"])
+        assert J == oracle.actor_cost(ct, s, x, c["obs"], c["state_sys"], w)
