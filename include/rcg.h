@@ -210,6 +210,14 @@ int rcg_actor_grad(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t 
 int rcg_gather_sqn(int32_t L, int64_t E, int32_t C, const double *cand, int32_t cand_per_env, const int32_t *idx,
                    const int32_t *mask, double *sqn_out, void *stream);
 
+/* CtrlNominal3WRobotNI (rcognita/controllers.py:1758-1956), the nominal parking controller of Sys3WRobotNI and the
+ * default ctrl_mode of presets/main_3wrobot_NI.py: action[2][E] = clip(NH2ctrl_Cart(ctrl_gain * kappa(Cart2NH(obs))))
+ * for the lanes with mask != 0 (all lanes if mask is NULL; the sampling-clock test of compute_action is
+ * rcg_ctrl_sample / the sample_flag of rcg_rk45_advance).  If accum != NULL (obj required):
+ * accum[E] += stage_obj(obs, action) * sampling_time (upd_accum_obj, :1086-1093). */
+int rcg_nominal_ni(const rcg_system_t *sys, int64_t E, const double *obs, double ctrl_gain, const int32_t *mask,
+                   double *action, const rcg_objective_t *obj, double *accum, double sampling_time, void *stream);
+
 /* CtrlOptPred.stage_obj (rcognita/controllers.py:1063-1084): out[E] = stage_obj(obs, act);
  * if accum != NULL additionally accum[E] += out * scale (upd_accum_obj, :1086-1093). */
 int rcg_stage_obj(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs,

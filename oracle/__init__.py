@@ -106,6 +106,8 @@ def lib():
         L.orc_actor_opt.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                     ip, ip]
         L.orc_actor_opt.restype = C.c_double
+        L.orc_nominal_ni.argtypes = [C.c_double, C.POINTER(SysT), dp, dp]
+        L.orc_nominal_ni.restype = None
         L.orc_argmin.argtypes = [dp, C.c_int]
         L.orc_argmin.restype = C.c_int
         L.orc_actor_cost_table.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, dp, dp, dp, dp, ip]
@@ -286,6 +288,14 @@ def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_
     J = lib().orc_actor_opt(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp,
                             int(max_iter), float(pg_tol), float(f_tol), C.byref(it), C.byref(nf))
     return a, J, it.value, nf.value
+
+
+def nominal_ni(ctrl_gain, s, observation):
+    """CtrlNominal3WRobotNI: action for one observation (clock-free part of compute_action, with clipping)."""
+    o, op = _d(observation)
+    a = np.zeros(2)
+    lib().orc_nominal_ni(float(ctrl_gain), C.byref(s), op, a.ctypes.data_as(C.POINTER(C.c_double)))
+    return a
 
 
 def actor_cost_table(c, s, cand, observation, state_sys, w_critic=None):

@@ -272,3 +272,43 @@ double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const d
     if (nfev_out) *nfev_out = nfev;
     return J;
 }
+
+/* ------------------------------------------------- CtrlNominal3WRobotNI (nominal parking controller) */
+
+static double sgn(double v) { return (v > 0.0) ? 1.0 : (v < 0.0) ? -1.0 : v; }   /* np.sign: 0 -> 0, NaN -> NaN */
+
+/* ref: rcognita/controllers.py:1758-1956, CtrlNominal3WRobotNI.compute_action_vanila + the clipping of
+ * compute_action (:1915-1921): _Cart2NH (:1880-1893), _zeta (:1786-1834), _kappa (:1836-1853),
+ * uNI = ctrl_gain * kappa, _NH2ctrl_Cart (:1895-1905), then np.clip to ctrl_bnds if ctrl_bnds.any().
+ * Expressions are evaluated in Python's order; x**3 and |x|**(1/3) are libm pow() like numpy's scalar power. */
+void orc_nominal_ni(double ctrl_gain, const orc_sys_t *s, const double *obs, double *action)
+{
+    const double xc = obs[0], yc = obs[1], alpha = obs[2];
+    const double ca = cos(alpha), sa = sin(alpha);
+    double x[3], zeta[3];
+    x[0] = alpha;
+    x[1] = xc * ca + yc * sa;
+    x[2] = -2 * (yc * ca - xc * sa) - alpha * (xc * ca + yc * sa);
+    const double a2 = fabs(x[2]);
+    if (x[0] == 0 && x[1] == 0) {                                   /* nablaF with theta = 0 (:1814-1830) */
+        const double st = x[0] * 1.0 + x[1] * 0.0 + sqrt(a2);
+        zeta[0] = 4 * pow(x[0], 3) - 2 * pow(a2, 3) * 1.0 / pow(st, 3);
+        zeta[1] = 4 * pow(x[1], 3) - 2 * pow(a2, 3) * 0.0 / pow(st, 3);
+        zeta[2] = (3 * x[0] * 1.0 + 3 * x[1] * 0.0 + 2 * sqrt(a2)) * pow(x[2], 2) * sgn(x[2]) / pow(st, 3);
+    } else {                                                        /* nablaL (:1804-1810) */
+        const double r = sqrt(pow(x[0], 2) + pow(x[1], 2));
+        const double sigma = r + sqrt(a2);
+        zeta[0] = 4 * pow(x[0], 3) + pow(a2, 3) / pow(sigma, 3) * 1 / pow(r, 3) * 2 * x[0];
+        zeta[1] = 4 * pow(x[1], 3) + pow(a2, 3) / pow(sigma, 3) * 1 / pow(r, 3) * 2 * x[1];
+        zeta[2] = 3 * pow(a2, 2) * sgn(x[2]) + pow(a2, 3) / pow(sigma, 3) * 1 / sqrt(a2) * sgn(x[2]);
+    }
+    const double d0 = zeta[0] * 1.0 + zeta[1] * 0.0 + zeta[2] * x[1];          /* np.dot(zeta, G[:,0]) */
+    const double d1 = zeta[0] * 0.0 + zeta[1] * 1.0 + zeta[2] * (-x[0]);       /* np.dot(zeta, G[:,1]) */
+    const double k0 = -pow(fabs(d0), 1.0 / 3) * sgn(d0);
+    const double k1 = -pow(fabs(d1), 1.0 / 3) * sgn(d1);
+    const double u0 = ctrl_gain * k0, u1 = ctrl_gain * k1;
+    action[0] = u1 + 1.0 / 2 * u0 * (x[2] + x[0] * x[1]);
+    action[1] = u0;
+    if (s->has_bnds)
+        for (int k = 0; k < 2; ++k) action[k] = clipd(action[k], s->lo[k], s->hi[k]);
+}

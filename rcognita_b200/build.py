@@ -28,6 +28,7 @@ SOURCES = {
     "actor_ni_f32.cu": [], "actor_3w_f32.cu": [], "actor_2t_f32.cu": [],
     "actor_opt.cu": [], "actor_opt_ni.cu": [], "actor_opt_3w.cu": [], "actor_opt_2t.cu": [],
     "critic.cu": ["-fmad=false"],
+    "nominal.cu": ["-fmad=false"],
     "critic_fit.cu": [],
 }
 HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", "actor_opt_impl.cuh", os.path.join(INCLUDE, "rcg.h")]

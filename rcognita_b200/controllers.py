@@ -399,5 +399,69 @@ class CtrlNominal3WRobot(_OutOfScope):
     _what = "CtrlNominal3WRobot"
 
 
-class CtrlNominal3WRobotNI(_OutOfScope):
-    _what = "CtrlNominal3WRobotNI"
+class CtrlNominal3WRobotNI:
+    """rcognita/controllers.py:1758-1956: nominal parking controller of the non-holonomic integrator ("disassembled
+    subgradients"), the default ``ctrl_mode`` of presets/main_3wrobot_NI.py.  Closed form per sample; batched like
+    ``CtrlOptPred`` (``[3]`` or ``[E, 3]`` observations, numpy or CUDA tensors).  New optional keyword ``device``."""
+
+    def __init__(self, ctrl_gain=10, ctrl_bnds=[], t0=0, sampling_time=0.1, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CtrlNominal3WRobotNI needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ctrl_gain = ctrl_gain
+        self.ctrl_bnds = np.asarray(ctrl_bnds, dtype=np.float64).reshape(-1, 2) if len(np.atleast_1d(ctrl_bnds)) else np.zeros((0, 2))
+        self.t0 = t0
+        self.sampling_time = sampling_time
+        self._sysd = _C.make_system("3wrobotNI", [], self.ctrl_bnds)
+        self._sysd_unclipped = _C.make_system("3wrobotNI", [], None)
+        self._batched, self._numpy_io = False, True
+        self._alloc(1)
+
+    def _alloc(self, E):
+        self._E = E
+        self._ctrl_clock = torch.full((E,), float(self.t0), dtype=_F64, device=self.device)
+        self._action_curr = torch.zeros((2, E), dtype=_F64, device=self.device)               # np.zeros(2) (:1770)
+        self._mask = torch.zeros((E,), dtype=_I32, device=self.device)
+
+    def _ensure(self, E, batched):
+        if E != self._E:
+            if self._E > 1:
+                raise ValueError(f"controller holds {self._E} environments, got a batch of {E}")
+            self._alloc(E)
+        self._batched = self._batched or batched
+
+    action_curr = property(lambda self: from_soa(self._action_curr, self._batched, self._numpy_io))
+    ctrl_clock = property(lambda self: (float(self._ctrl_clock[0].item()) if not self._batched else
+                                        (self._ctrl_clock.cpu().numpy() if self._numpy_io else self._ctrl_clock)))
+
+    def reset(self, t0):
+        """:1772-1778."""
+        self._ctrl_clock.fill_(float(t0))
+        self._action_curr.zero_()
+
+    def compute_action(self, t, observation):
+        """:1907-1927: lanes whose clock fires get a new (clipped) action, the others hold ``action_curr``."""
+        self._numpy_io = not isinstance(observation, torch.Tensor)
+        obs, batched = to_soa(observation, 3, self.device, "observation")
+        self._ensure(obs.shape[1], batched)
+        E = self._E
+        if isinstance(t, torch.Tensor):
+            tt = t.to(device=self.device, dtype=_F64).reshape(-1)
+        else:
+            tt = torch.as_tensor(np.asarray(t, dtype=np.float64).reshape(-1), device=self.device)
+        if tt.numel() == 1 and E > 1:
+            tt = tt.expand(E)
+        ops.ctrl_sample(tt.contiguous(), self._ctrl_clock, float(self.sampling_time), mask_out=self._mask)
+        ops.nominal_ni(self._sysd, obs, self.ctrl_gain, self._action_curr, mask=self._mask)
+        return from_soa(self._action_curr, self._batched, self._numpy_io)
+
+    def compute_action_vanila(self, observation):
+        """:1929-1941: no clock and -- like the reference -- no clipping."""
+        self._numpy_io = not isinstance(observation, torch.Tensor)
+        obs, batched = to_soa(observation, 3, self.device, "observation")
+        self._ensure(obs.shape[1], batched)
+        ops.nominal_ni(self._sysd_unclipped, obs, self.ctrl_gain, self._action_curr)
+        return from_soa(self._action_curr, self._batched, self._numpy_io)
+
+    def compute_LF(self, observation):
+        raise NotImplementedError("compute_LF is a diagnostic outside the B200 hot path")

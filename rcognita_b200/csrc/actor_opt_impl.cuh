@@ -7,7 +7,7 @@
 //     emits dJ/da_k = d(stage term)/da_k + h (df/da)^T lambda_{k+1}  (~3 cost evaluations per gradient);
 //   * the minimiser is a projected limited-memory quasi-Newton method: L-BFGS two-loop recursion over the free
 //     variables (every inner product masked by the binding set of the box), projected Armijo backtracking,
-//     monotone -- see solve() below; the CPU checker restates the same algorithm (oracle/rcg_oracle_opt.c).
+//     monotone -- see solve() below; the CPU checker under tests/ restates the same algorithm.
 // Storage: with a compile-time horizon (NA > 0) the five working vectors and the rollout live in registers /
 // thread-local memory; the (s, y) pairs of the quasi-Newton memory always live in a caller-provided global
 // workspace laid out [slot][component][thread] (coalesced: consecutive threads = consecutive (env, start)
@@ -376,48 +376,47 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
             T scale = step0 / pg;
             bool have_scale = false;
             T al[kOptMem], sy[kOptMem];
-#pragma unroll
-            for (int j = 0; j < kOptMem; ++j) {
+            // the pair loops stay rolled (al/sy are indexed dynamically): unrolled, the kernel outgrows the
+            // instruction cache (ncu: stall_no_instruction was the top stall reason)
+#pragma unroll 1
+            for (int j = 0; j < npairs; ++j) {
+                int slot = head - 1 - j;
+                slot += (slot < 0) ? kOptMem : 0;
+                const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
+                T a = T(0), ss = T(0), yy = T(0), sq = T(0);
+#pragma unroll UL
+                for (int i = 0; i < L; ++i) {
+                    const T si = sp[(int64_t)i * nthreads], yi = yp[(int64_t)i * nthreads];
+                    if (is_free(i)) { a += si * yi; ss += si * si; yy += yi * yi; sq += si * mem.v(2, i); }
+                }
                 al[j] = T(0);
                 sy[j] = T(0);
-                if (j < npairs) {
-                    int slot = head - 1 - j;
-                    slot += (slot < 0) ? kOptMem : 0;
-                    T a = T(0), ss = T(0), yy = T(0), sq = T(0);
+                if (a > T(1e-10) * sqrt(ss * yy)) {
+                    sy[j] = a;
+                    al[j] = sq / a;
+                    const T alj = al[j];
 #pragma unroll UL
-                    for (int i = 0; i < L; ++i) {
-                        if (is_free(i)) {
-                            const T si = Sp(slot, i), yi = Yp(slot, i);
-                            a += si * yi; ss += si * si; yy += yi * yi; sq += si * mem.v(2, i);
-                        }
-                    }
-                    if (a > T(1e-10) * sqrt(ss * yy)) {
-                        sy[j] = a;
-                        al[j] = sq / a;
-#pragma unroll UL
-                        for (int i = 0; i < L; ++i)
-                            if (is_free(i)) mem.v(2, i) -= al[j] * Yp(slot, i);
-                        if (!have_scale) { scale = a / yy; have_scale = true; }
-                    }
+                    for (int i = 0; i < L; ++i)
+                        if (is_free(i)) mem.v(2, i) -= alj * yp[(int64_t)i * nthreads];
+                    if (!have_scale) { scale = a / yy; have_scale = true; }
                 }
             }
 #pragma unroll UL
             for (int i = 0; i < L; ++i) mem.v(2, i) *= scale;
-#pragma unroll
-            for (int jj = 0; jj < kOptMem; ++jj) {
-                const int j = kOptMem - 1 - jj;
-                if (j < npairs && sy[j] > T(0)) {
-                    int slot = head - 1 - j;
-                    slot += (slot < 0) ? kOptMem : 0;
-                    T yr = T(0);
+#pragma unroll 1
+            for (int j = npairs - 1; j >= 0; --j) {
+                if (!(sy[j] > T(0))) continue;
+                int slot = head - 1 - j;
+                slot += (slot < 0) ? kOptMem : 0;
+                const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
+                T yr = T(0);
 #pragma unroll UL
-                    for (int i = 0; i < L; ++i)
-                        if (is_free(i)) yr += Yp(slot, i) * mem.v(2, i);
-                    const T b = yr / sy[j];
+                for (int i = 0; i < L; ++i)
+                    if (is_free(i)) yr += yp[(int64_t)i * nthreads] * mem.v(2, i);
+                const T c = al[j] - yr / sy[j];
 #pragma unroll UL
-                    for (int i = 0; i < L; ++i)
-                        if (is_free(i)) mem.v(2, i) += (al[j] - b) * Sp(slot, i);
-                }
+                for (int i = 0; i < L; ++i)
+                    if (is_free(i)) mem.v(2, i) += c * sp[(int64_t)i * nthreads];
             }
             T gd = T(0);
 #pragma unroll UL

@@ -36,7 +36,9 @@ class ClosedLoopEngine:
     enumerate-and-argmin over the candidate set; ``"opt"`` = the batched bounded minimiser ``rcg_actor_opt``
     (exact adjoint gradients, projected quasi-Newton; at most ``opt_iters`` iterations per sample) started from the
     arg-min candidate (``opt_start="argmin"``) or, like the reference, from ``action_sqn_init`` every time
-    (``opt_start="init"``; the candidate set is then unused and may be ``None``).
+    (``opt_start="init"``; the candidate set is then unused and may be ``None``); ``"nominal"`` = the reference's
+    ``CtrlNominal3WRobotNI`` with ``ctrl_gain`` (Sys3WRobotNI only; ``action_init`` defaults to zeros like the
+    reference's ``action_curr``, candidates unused).
     """
 
     def __init__(self, system, state_init, candidates, *, pars=(), ctrl_bnds=None, mode="MPC", Nactor=6, dt=0.01,
@@ -44,7 +46,7 @@ class ClosedLoopEngine:
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
                  buffer_size=10, critic_period=None, critic_fit_evals=0, actor="candidates", opt_start="argmin",
-                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12):
+                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, ctrl_gain=0.5):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -73,15 +75,18 @@ class ClosedLoopEngine:
             self.E = E = x0.shape[0]
             self.y0 = x0.t().contiguous()                                  # [n, E]
             L = Nactor * m
-            if actor not in ("candidates", "opt") or opt_start not in ("argmin", "init"):
-                raise ValueError("actor must be 'candidates' or 'opt'; opt_start 'argmin' or 'init'")
+            if actor not in ("candidates", "opt", "nominal") or opt_start not in ("argmin", "init"):
+                raise ValueError("actor must be 'candidates', 'opt' or 'nominal'; opt_start 'argmin' or 'init'")
+            if actor == "nominal" and (system != "3wrobotNI" or dtype != torch.float64):
+                raise ValueError("the nominal controller is CtrlNominal3WRobotNI (Sys3WRobotNI, fp64)")
+            self.ctrl_gain = float(ctrl_gain)
             self.actor, self.opt_start = actor, opt_start
             self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
             if actor == "opt" and dtype != torch.float64:
                 raise ValueError("the actor optimiser runs in fp64")
             if candidates is None:
-                if not (actor == "opt" and opt_start == "init"):
-                    raise ValueError("candidates are required unless actor='opt' with opt_start='init'")
+                if not ((actor == "opt" and opt_start == "init") or actor == "nominal"):
+                    raise ValueError("candidates are required unless actor='opt' with opt_start='init' or actor='nominal'")
                 candidates = np.zeros((1, L))
             cand = _as_dev(candidates, dtype, self.device)
             if cand.dim() == 2:
@@ -124,6 +129,8 @@ class ClosedLoopEngine:
                 self.w, self.w_per_env = None, False
             lo = np.array([self.sysd.lo[k] for k in range(m)])
             a0 = lo / 10 if len(action_init) == 0 else np.asarray(action_init, dtype=np.float64).reshape(m)
+            if actor == "nominal" and len(action_init) == 0:
+                a0 = np.zeros(m)                                           # CtrlNominal3WRobotNI.action_curr (:1770)
             self.action_init = _as_dev(a0, dtype, self.device)             # controllers.py:973-978
             self._alloc()
             self.reset()
@@ -249,6 +256,10 @@ class ClosedLoopEngine:
     def _actor_launch(self):
         if self.critic_fit:
             self._critic_update()
+        if self.actor == "nominal":
+            ops.nominal_ni(self.sysd, self.y, self.ctrl_gain, self.action, mask=self.sample_flag, obj=self.obj,
+                           accum=self.accum, sampling_time=self.sampling_time)
+            return
         if self.actor == "opt":
             if self.opt_start == "argmin":
                 ops.actor_cost(self.sysd, self.obj, self.state_sys, self.y, self.cand, self.cand_per_env, self.C,

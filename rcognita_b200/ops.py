@@ -194,6 +194,18 @@ def gather_sqn(cand, cand_per_env, C_, idx, out, mask=None):
     return out
 
 
+def nominal_ni(sysd, obs, ctrl_gain, action, mask=None, obj=None, accum=None, sampling_time=0.0):
+    """``CtrlNominal3WRobotNI``: writes the nominal parking action into ``action`` [2, E] for the masked lanes
+    (+ fused ``upd_accum_obj`` when ``accum`` and ``obj`` are given)."""
+    E = obs.shape[1]
+    _C.check(_C.lib.rcg_nominal_ni(C.byref(sysd), E, _ptr(obs, _F64, (3, E), "obs"), float(ctrl_gain),
+                                   _ptr(mask, _I32, (E,), "mask", optional=True), _ptr(action, _F64, (2, E), "action"),
+                                   C.byref(obj) if obj is not None else None,
+                                   _ptr(accum, _F64, (E,), "accum", optional=True), float(sampling_time), _stream()),
+             "rcg_nominal_ni")
+    return action
+
+
 def stage_obj(obj, n, m, obs, act, out=None, accum=None, scale=0.0, want_out=True):
     """``CtrlOptPred.stage_obj`` (+ fused ``upd_accum_obj`` when ``accum`` is given)."""
     E = obs.shape[1]

@@ -4,9 +4,12 @@ the ``type=bool`` quirk (any non-empty string is True; pass '' for False).  New 
 ``--num_envs``, ``--num_candidates``, ``--seed``, ``--state_spread``.
 
 Differences: ``--is_visualization`` has no effect beyond a notice (the matplotlib animators are outside the hot
-path; the loop run is the headless one, presets/main_3wrobot_NI.py:411-462); ``--ctrl_mode nominal`` / ``JACS``
-raise (out-of-scope controllers); MPC / RQL / SQL use the candidate/arg-min actor and the bounded-least-squares
-critic fit of ``rcognita_b200.controllers``.  With ``--Nruns`` > 1 every run restarts from ``state_init``
+path; the loop run is the headless one, presets/main_3wrobot_NI.py:411-462); ``--ctrl_mode nominal`` runs the
+batched ``CtrlNominal3WRobotNI`` for Sys3WRobotNI and raises for Sys3WRobot, ``JACS`` raises (out-of-scope
+controllers); MPC / RQL / SQL use the candidate/arg-min actor (``--actor candidates``, default) or the batched
+bounded minimiser started from the arg-min candidate or from ``action_sqn_init`` (``--actor opt``,
+``--opt_start argmin|init``, ``--opt_iters``) and the bounded-least-squares critic fit of
+``rcognita_b200.controllers``.  With ``--Nruns`` > 1 every run restarts from ``state_init``
 (the documented intent of the reference's reset; its own code raises NameError there).
 """
 from __future__ import annotations
@@ -89,7 +92,7 @@ def make_parser(system: str) -> argparse.ArgumentParser:
     col = _COL[system]
     p = argparse.ArgumentParser(description=f"rcognita preset for {system} on the B200 engine (flags as in the reference preset)")
     p.add_argument('--ctrl_mode', metavar='ctrl_mode', type=str, choices=S["modes"], default=S["default_mode"],
-                   help='Control mode: manual constant action, MPC, RQL, SQL (nominal / JACS: out of scope here).')
+                   help='Control mode: manual constant action, nominal (Sys3WRobotNI), MPC, RQL, SQL (JACS: out of scope here).')
     for flag, typ, d_ni, d_3w, d_2t in _FLAGS:
         d = (d_ni, d_3w, d_2t)[col - 2]
         p.add_argument(flag, type=typ, default=d_ni if d is None else d, help=f"as in the reference preset (default %(default)s)")
@@ -103,6 +106,11 @@ def make_parser(system: str) -> argparse.ArgumentParser:
     p.add_argument('--num_envs', type=int, default=1, help='environments stepped in parallel (1 = the reference\'s shapes)')
     p.add_argument('--num_candidates', type=int, default=256, help='candidate action sequences of the arg-min actor')
     p.add_argument('--seed', type=int, default=1, help='seed of the candidate table (and of the initial-state spread)')
+    p.add_argument('--actor', type=str, default='candidates', choices=['candidates', 'opt'],
+                   help='stand-in for the SLSQP actor: arg-min over candidates, or the batched bounded minimiser')
+    p.add_argument('--opt_start', type=str, default='argmin', choices=['argmin', 'init'],
+                   help='start point of --actor opt: the arg-min candidate, or action_sqn_init like the reference')
+    p.add_argument('--opt_iters', type=int, default=300, help='iteration cap of --actor opt (reference SLSQP: maxiter 300)')
     p.add_argument('--state_spread', type=float, default=0.0,
                    help='std of the Gaussian spread of the initial states around state_init when num_envs > 1')
     return p
@@ -118,9 +126,9 @@ def build(system: str, args):
         raise AssertionError("t1 > dt > 0 is required")
     if state_init.size != n:
         raise AssertionError(f"state_init must have {n} entries")
-    if args.ctrl_mode in ('nominal', 'JACS'):
+    if args.ctrl_mode == 'JACS' or (args.ctrl_mode == 'nominal' and system != '3wrobotNI'):
         raise NotImplementedError(f"ctrl_mode {args.ctrl_mode!r} needs a controller outside the B200 hot path "
-                                  "(CtrlNominal*, CtrlRLStab); use the reference for it")
+                                  "(CtrlNominal3WRobot, CtrlRLStab); use the reference for it")
     pred_step_size = args.dt * args.pred_step_size_multiplier
     model_est_period = args.dt * args.model_est_period_multiplier
     critic_period = args.dt * args.critic_period_multiplier
@@ -143,12 +151,16 @@ def build(system: str, args):
                                       model_order=args.model_order, model_est_checks=0, gamma=args.gamma, Ncritic=args.Ncritic,
                                       critic_period=critic_period, critic_struct=args.critic_struct,
                                       stage_obj_struct=args.stage_obj_struct, stage_obj_pars=[R1, R2][:1 if args.stage_obj_struct == 'quadratic' else 2],
-                                      observation_target=S["target"], num_candidates=args.num_candidates, seed=args.seed)
+                                      observation_target=S["target"], num_candidates=args.num_candidates, seed=args.seed,
+                                      actor=args.actor, opt_start=args.opt_start, opt_iters=args.opt_iters)
     my_sim = simulator.Simulator(sys_type="diff_eqn", closed_loop_rhs=my_sys.closed_loop_rhs, sys_out=my_sys.out,
                                  state_init=x0, disturb_init=[], action_init=np.zeros(m), t0=0, t1=args.t1, dt=args.dt,
                                  max_step=args.dt / 2, first_step=1e-6, atol=1e-5, rtol=1e-3, is_disturb=0, is_dyn_ctrl=0)
     my_logger = getattr(loggers, S["logger"])()
-    return my_sys, my_ctrl, my_sim, my_logger, dict(state_init=state_init, x0=x0)
+    my_ctrl_nominal = None
+    if system == '3wrobotNI':          # presets/main_3wrobot_NI.py:235
+        my_ctrl_nominal = controllers.CtrlNominal3WRobotNI(ctrl_gain=0.5, ctrl_bnds=ctrl_bnds, t0=0, sampling_time=args.dt)
+    return my_sys, my_ctrl, my_sim, my_logger, dict(state_init=state_init, x0=x0, ctrl_nominal=my_ctrl_nominal)
 
 
 def write_csv_header(datafile, system, args, state_init):
@@ -201,6 +213,8 @@ def run_headless(system, args, data_folder=None, quiet=False):
         if run > 0:
             my_sim.reset()
             my_ctrl.reset(0)
+            if extra["ctrl_nominal"] is not None:
+                extra["ctrl_nominal"].reset(0)
             my_ctrl._accum.zero_()
         nsteps = 0
         while True:
@@ -209,7 +223,7 @@ def run_headless(system, args, data_folder=None, quiet=False):
                 accum_before = my_ctrl._accum.clone()
             my_sim.sim_step()
             t, state, observation, state_full = my_sim.get_sim_step_data()
-            action = controllers.ctrl_selector(t, observation, action_manual, None, my_ctrl, args.ctrl_mode)
+            action = controllers.ctrl_selector(t, observation, action_manual, extra["ctrl_nominal"], my_ctrl, args.ctrl_mode)
             my_sys.receive_action(action)
             my_ctrl.receive_sys_state(my_sys._state)
             my_ctrl.upd_accum_obj(observation, action)

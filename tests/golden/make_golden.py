@@ -338,6 +338,44 @@ def gen_actor_opt():
     print("actor_opt.json", len(out), "cases; nfev", min(c["nfev"] for c in out), "..", max(c["nfev"] for c in out),
           "status", sorted(set(c["status"] for c in out)))
 
+# --------------------------------------------------------------------------- nominal parking controller (NI)
+def gen_nominal():
+    """CtrlNominal3WRobotNI (controllers.py:1758-1956), the default ctrl_mode of presets/main_3wrobot_NI.py:
+    actions for seeded observations (incl. the xNI[0] = xNI[1] = 0 branch and out-of-bounds results) and the
+    preset-default closed loop (ctrl_gain 0.5 -- presets/main_3wrobot_NI.py:231 -- dt 0.01, t1 3)."""
+    name = "3wrobotNI"
+    cfg = SYSTEMS[name]
+    bn = np.array(cfg["bnds"], dtype=float)
+    rng = np.random.default_rng(99)
+    cases = []
+    for gain in (0.5, 10.0):
+        nom = controllers.CtrlNominal3WRobotNI(ctrl_gain=gain, ctrl_bnds=bn, t0=0, sampling_time=cfg["dt"])
+        obs_list = [rng.uniform([-10, -10, -np.pi], [10, 10, np.pi]) for _ in range(24)]
+        obs_list += [rng.uniform([-0.1, -0.1, -0.1], [0.1, 0.1, 0.1]) for _ in range(6)]
+        obs_list += [np.array([0.0, 1.5, 0.0]), np.array([0.0, -0.3, 0.0])]            # xNI[0] = xNI[1] = 0
+        for ob in obs_list:
+            act = nom.compute_action(1.0 + len(cases), ob)          # clock always fires: sampling_time elapsed
+            cases.append(dict(gain=gain, obs=L(ob), action=L(act)))
+    my_sys = make_sys(name)
+    sim = make_sim(name, my_sys, 3.0)
+    nom = controllers.CtrlNominal3WRobotNI(ctrl_gain=0.5, ctrl_bnds=bn, t0=0, sampling_time=cfg["dt"])
+    ctrl = make_ctrl(name, my_sys, "MPC", 3)                        # the preset's accumulator (upd_accum_obj)
+    rows = []
+    while True:
+        sim.sim_step()
+        t, state, observation, state_full = sim.get_sim_step_data()
+        action = controllers.ctrl_selector(t, observation, None, nom, ctrl, "nominal")
+        my_sys.receive_action(action)
+        ctrl.receive_sys_state(my_sys._state)
+        ctrl.upd_accum_obj(observation, action)
+        rows.append([t] + L(state_full) + L(action) + [float(ctrl.accum_obj_val)])
+        if t >= 3.0:
+            break
+    with open(os.path.join(HERE, "nominal.json"), "w") as fh:
+        json.dump(dict(cases=cases, episode=dict(gain=0.5, t1=3.0, x0=L(cfg["x0"]), rows=rows,
+                                                 nfev=int(sim.ODE_solver.nfev))), fh)
+    print("nominal.json", len(cases), "cases;", len(rows), "episode steps; final", rows[-1])
+
 # --------------------------------------------------------------------------- config 1: preset-faithful SLSQP episode (App. A.2)
 def gen_config1():
     name = "3wrobotNI"
@@ -375,7 +413,7 @@ def gen_config1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit", "actor_opt"]
+    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit", "actor_opt", "nominal"]
     if "functions" in which:
         gen_functions()
     if "integrator" in which:
@@ -388,3 +426,5 @@ if __name__ == "__main__":
         gen_critic_fit()
     if "actor_opt" in which:
         gen_actor_opt()
+    if "nominal" in which:
+        gen_nominal()

@@ -68,7 +68,7 @@ def test_ctrl_selector_dispatch():
 
 def test_out_of_scope_controllers_raise():
     from rcognita_b200 import controllers
-    for cls in (controllers.CtrlRLStab, controllers.CtrlNominal3WRobot, controllers.CtrlNominal3WRobotNI):
+    for cls in (controllers.CtrlRLStab, controllers.CtrlNominal3WRobot):
         with pytest.raises(NotImplementedError):
             cls()
 

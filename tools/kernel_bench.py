@@ -127,9 +127,53 @@ def critic_fit_point(system, cs, E, iters=5):
             "fits_per_s": E / ms * 1e3, "median_cost_ratio_fit_over_init": float((Jc / J0.clamp_min(1e-300)).median().item())}
 
 
+def actor_opt_point(system, mode, cs, N, E, state_scale=1.0, max_iter=300, iters=4):
+    """rcg_actor_opt (the batched stand-in for _actor_optimizer) from action_sqn_init for E environments.  States
+    are drawn from BOX scaled by `state_scale` around the target (small scale = near the goal = interior minimisers,
+    more iterations).  Reports solves/s and gradient (forward + adjoint sweep) evaluations/s."""
+    p = PRESET[system]
+    n, m = _C.SYS_DIMS[_C.SYS_IDS[system]]
+    sysd = _C.make_system(system, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], critic_struct=cs, R1=p["R1"],
+                            observation_target=p["target"])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = (torch.tensor(v, device="cuda", dtype=torch.float64) for v in BOX[system])
+    x = lo[:, None] + (hi - lo)[:, None] * torch.rand((n, E), device="cuda", dtype=torch.float64, generator=g)
+    scale = torch.full((n, 1), state_scale, device="cuda", dtype=torch.float64)
+    if system != "2tank":
+        scale[2] = 1.0                                    # headings stay uniform on the circle
+    x = x * scale
+    if p["target"]:
+        x = x + torch.tensor(p["target"], device="cuda", dtype=torch.float64)[:, None]
+    b = np.array(p["bnds"], dtype=np.float64)
+    init = torch.as_tensor(np.tile(b[:, 0] / 10, N), device="cuda")[:, None].expand(N * m, E).contiguous()
+    dimc = _C.dim_critic(cs, n, m)
+    w = None if mode == "MPC" else torch.rand((dimc,), device="cuda", dtype=torch.float64, generator=g)
+    ws, _ = ops._opt_workspace(sysd, obj, E, 1, x.device)
+    J = torch.empty((E,), device="cuda", dtype=torch.float64)
+    it = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    nf = torch.zeros((E,), device="cuda", dtype=torch.int32)
+    sqn = init.clone()
+
+    def fn():
+        sqn.copy_(init)
+        ops.actor_opt(sysd, obj, x, x, sqn, w_critic=w, max_iter=max_iter, workspace=ws, J_out=J, iters_out=it, nfev_out=nf)
+    ms = time_it(fn, iters, warm=2)
+    ms_copy = time_it(lambda: sqn.copy_(init), iters, warm=1)
+    ms -= ms_copy
+    itc, nfc = it.cpu().numpy(), nf.cpu().numpy()
+    J0, _ = ops.actor_grad(sysd, obj, x, x, init, w_critic=w)
+    return {"kernel": "actor_opt", "system": system, "mode": mode, "critic": cs, "Nactor": N, "E": E,
+            "state_scale": state_scale, "max_iter": max_iter, "ms": ms, "solves_per_s": E / ms * 1e3,
+            "iters_mean": float(itc.mean()), "iters_p50": float(np.median(itc)), "iters_p99": float(np.percentile(itc, 99)),
+            "iters_max": int(itc.max()), "linesearch_evals_mean": float(nfc.mean()),
+            "grad_evals_per_s": float(itc.sum() + E) / ms * 1e3, "cost_evals_per_s": float(nfc.sum()) / ms * 1e3,
+            "median_cost_ratio_opt_over_init": float((J / J0).median().item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "rk45ni", "critic", "all"])
+    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "rk45ni", "critic", "opt", "all"])
     a = ap.parse_args()
     pts = []
     if a.what in ("headline", "all"):
@@ -156,6 +200,14 @@ def main():
     if a.what in ("critic", "all"):
         pts += [lambda: critic_fit_point("2tank", "quad-nomix", 262144), lambda: critic_fit_point("3wrobot", "quadratic", 1 << 20),
                 lambda: critic_fit_point("3wrobotNI", "quad-lin", 262144)]
+    if a.what in ("opt", "all"):
+        pts += [lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 1.0),
+                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 0.05),
+                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 1 << 20, 0.05),
+                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 7, 65536, 0.05),        # generic (workspace) kernel
+                lambda: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 1.0),
+                lambda: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 0.05, max_iter=100),
+                lambda: actor_opt_point("2tank", "SQL", "quad-nomix", 8, 262144, 0.5)]
     for p in pts:
         print(json.dumps(p()), flush=True)
 
