@@ -90,6 +90,18 @@ typedef struct rcg_solver {
     double rtol, atol;
 } rcg_solver_t;
 
+/* Device-side trajectory ring (the rows of rcognita/loggers.py:41-94 for every environment): rows is
+ * [capacity][1 + n + 2 + m][E] = (t, state[n], stage_obj, accum_obj, action[m]) -- the reference's column order for
+ * Sys3WRobotNI and Sys3WRobot; Sys2Tank logs the action before stage_obj (loggers.py:90-94, reordered by the host).
+ * Lane e has written count[e] rows so far; row r of lane e sits at slot r % capacity.  Only solver steps whose
+ * per-lane index (nsteps) is a multiple of `every` are logged. */
+typedef struct rcg_log {
+    double  *rows;
+    int32_t *count;
+    int32_t  capacity;
+    int32_t  every;
+} rcg_log_t;
+
 int         rcg_version(void);
 const char *rcg_last_error_string(void);
 /* Number of CUDA devices visible, or a negative RCG_E* code (never touches a kernel). */
@@ -140,6 +152,18 @@ int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg
                      int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
                      double sampling_time, int32_t max_steps, double *state_sys, double *accum,
                      int32_t *sample_flag, int32_t *nsamples, void *stream);
+/* rcg_rk45_advance that also appends one row per logged held-action step to the trajectory ring (the row of a
+ * sampling step needs the controller's new action: the caller appends it with rcg_log_rows after the controller). */
+int rcg_rk45_advance_logged(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
+                            int64_t E, double *y, double *f, double *t, double *h_abs, int32_t *status,
+                            int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
+                            double sampling_time, int32_t max_steps, double *state_sys, double *accum,
+                            int32_t *sample_flag, int32_t *nsamples, const rcg_log_t *log, void *stream);
+/* Appends the current (t, y, stage_obj(y, action), accum, action) of the lanes with mask != 0 (all if NULL) whose
+ * nsteps[e] is a multiple of log->every (every lane if nsteps is NULL). */
+int rcg_log_rows(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *t, const double *y,
+                 const double *action, const double *accum, const int32_t *nsteps, const int32_t *mask,
+                 const rcg_log_t *log, void *stream);
 int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj,
                          int64_t E, float *y, float *f, double *t, double *h_abs, int32_t *status,
                          int32_t *nfev, int32_t *nsteps, float *action, double *ctrl_clock,

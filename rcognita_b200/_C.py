@@ -40,6 +40,10 @@ class RcgObjective(C.Structure):
                 ("target", C.c_double * MAX_N)]
 
 
+class RcgLog(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("count", C.c_void_p), ("capacity", C.c_int32), ("every", C.c_int32)]
+
+
 class RcgSolver(C.Structure):
     _fields_ = [("t_bound", C.c_double), ("max_step", C.c_double), ("rtol", C.c_double), ("atol", C.c_double)]
 
@@ -66,6 +70,9 @@ def _load():
         getattr(L, name).argtypes = [sysp, solp, i64] + [vp] * 7 + [vp]
     for name in ("rcg_rk45_advance", "rcg_rk45_advance_f32"):
         getattr(L, name).argtypes = [sysp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp, vp]
+    L.rcg_rk45_advance_logged.argtypes = ([sysp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp,
+                                                                                C.POINTER(RcgLog), vp])
+    L.rcg_log_rows.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, vp, vp, C.POINTER(RcgLog), vp]
     for name in ("rcg_actor_cost", "rcg_actor_cost_f32"):
         getattr(L, name).argtypes = [sysp, objp, i64, i32, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, dbl, vp]
     L.rcg_actor_opt_workspace_bytes.argtypes = [sysp, objp, i64, i32]
@@ -89,7 +96,7 @@ lib = _load()
 EXPORTS = [
     "rcg_version", "rcg_last_error_string", "rcg_device_count", "rcg_dim_state", "rcg_dim_input", "rcg_dim_critic",
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
-    "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_actor_cost", "rcg_actor_cost_f32",
+    "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_rk45_advance_logged", "rcg_log_rows", "rcg_actor_cost", "rcg_actor_cost_f32",
     "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 

@@ -150,14 +150,39 @@ __device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDe
 
 // CTRL = false: Simulator.sim_step (one accepted step per running lane).
 // CTRL = true : the fused loop body between two controller samples (see rcg_rk45_advance).
-template <typename T, int SYS, bool CTRL, bool RDIAG>
+// Trajectory ring of the logged variants (rcg_log_t): rows [capacity][1 + n + 2 + m][E] =
+// (t, state, stage_obj, accum_obj, action) per logged solver step and lane, written at slot count % capacity.
+struct LogDev {
+    double *rows;
+    int32_t *count;
+    int capacity, every;
+};
+
+template <typename T, int N, int M>
+__device__ __forceinline__ void log_row(const LogDev &G, int64_t E, int64_t e, int &cnt, double t, const T *y, T stage,
+                                        T accum, const T *a)
+{
+    constexpr int NC = 1 + N + 2 + M;
+    double *r = G.rows + ((int64_t)(cnt % G.capacity) * NC) * E + e;
+    r[0] = t;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[(int64_t)(1 + i) * E] = (double)y[i];
+    r[(int64_t)(1 + N) * E] = (double)stage;
+    r[(int64_t)(2 + N) * E] = (double)accum;
+#pragma unroll
+    for (int j = 0; j < M; ++j) r[(int64_t)(3 + N + j) * E] = (double)a[j];
+    ++cnt;
+}
+
+template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false>
 __global__ void __launch_bounds__(128, 4)
 rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
             const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
             int32_t *__restrict__ nfev_g, int32_t *__restrict__ nsteps_g, T *__restrict__ action_g,
             double *__restrict__ clock_g, double sampling_time, int max_steps, T *__restrict__ state_sys_g,
-            T *__restrict__ accum_g, int32_t *__restrict__ flag_g, int32_t *__restrict__ nsamples_g)
+            T *__restrict__ accum_g, int32_t *__restrict__ flag_g, int32_t *__restrict__ nsamples_g,
+            const __grid_constant__ LogDev G = LogDev{nullptr, nullptr, 0, 0})
 {
     constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +202,8 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
     double clock = CTRL ? clock_g[e] : 0.0;
     T acc = (CTRL && accum_g) ? accum_g[e] : T(0);
     int nf = 0, ns = 0, flag = 0;
+    int log_cnt = 0, step0 = 0;
+    if constexpr (LOG) { log_cnt = G.count[e]; step0 = nsteps_g[e]; }
 
     for (int it = 0; it < max_steps && st == RCG_RUNNING; ++it) {
         if (t == sol.t_bound) { st = RCG_FINISHED; break; }                    // base.py:192-197
@@ -195,9 +222,14 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
                 break;
             }
             // held action: compute_action returns action_curr (:1492-1493); upd_accum_obj (:1093)
-            acc += stage_obj<T, N, M, RDIAG>(O, y, a) * (T)sampling_time;
+            const T so = stage_obj<T, N, M, RDIAG>(O, y, a);
+            acc += so * (T)sampling_time;
+            if constexpr (LOG) {                   // the row of a held-action step; sampling steps: rcg_log_rows
+                if ((step0 + ns) % G.every == 0) log_row<T, N, M>(G, E, e, log_cnt, t, y, so, acc, a);
+            }
         }
     }
+    if constexpr (LOG) G.count[e] = log_cnt;
 
 #pragma unroll
     for (int i = 0; i < N; ++i) { y_g[i * E + e] = y[i]; f_g[i * E + e] = f[i]; }
@@ -221,6 +253,27 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
             for (int i = 0; i < N; ++i) state_sys_g[i * E + e] = flag ? yprev[i] : y[i];
         }
     }
+}
+
+// The row of a step on which the controller sampled (or of any step driven from the host): the action and the
+// accumulated objective are only known after the controller ran.
+template <int N, int M, bool RDIAG>
+__global__ void __launch_bounds__(256)
+log_rows_kernel(const __grid_constant__ ObjDev<double> O, const __grid_constant__ LogDev G, int64_t E,
+                const double *__restrict__ t_g, const double *__restrict__ y_g, const double *__restrict__ action_g,
+                const double *__restrict__ accum_g, const int32_t *__restrict__ nsteps_g, const int32_t *__restrict__ mask_g)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E || (mask_g && mask_g[e] == 0)) return;
+    if (nsteps_g && nsteps_g[e] % G.every != 0) return;
+    double y[N], a[M];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = y_g[i * E + e];
+#pragma unroll
+    for (int j = 0; j < M; ++j) a[j] = action_g[j * E + e];
+    int cnt = G.count[e];
+    log_row<double, N, M>(G, E, e, cnt, t_g[e], y, stage_obj<double, N, M, RDIAG>(O, y, a), accum_g[e], a);
+    G.count[e] = cnt;
 }
 
 template <typename T, int SYS, bool CLIP>
@@ -267,8 +320,22 @@ template <typename T, int SYS, bool CTRL>
 static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const SysDev<T> &S, const SolverDev &sol,
                             const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
                             int32_t *nfev, int32_t *nsteps, T *action, double *clock, double sampling_time,
-                            int max_steps, T *state_sys, T *accum, int32_t *flag, int32_t *nsamples)
+                            int max_steps, T *state_sys, T *accum, int32_t *flag, int32_t *nsamples,
+                            const LogDev *log = nullptr)
 {
+    if constexpr (CTRL) {
+        if (log) {
+            if (rdiag)
+                rk45_kernel<T, SYS, true, true, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                                           action, clock, sampling_time, max_steps, state_sys,
+                                                                           accum, flag, nsamples, *log);
+            else
+                rk45_kernel<T, SYS, true, false, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                                            action, clock, sampling_time, max_steps, state_sys,
+                                                                            accum, flag, nsamples, *log);
+            return;
+        }
+    }
     if (rdiag)
         rk45_kernel<T, SYS, CTRL, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
                                                              clock, sampling_time, max_steps, state_sys, accum, flag,
@@ -283,9 +350,17 @@ template <typename T, bool CTRL>
 static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solver_t *sol_h, const rcg_objective_t *obj,
                        int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
                        int32_t *nsteps, T *action, double *clock, double sampling_time, int max_steps,
-                       T *state_sys, T *accum, int32_t *flag, int32_t *nsamples, void *stream)
+                       T *state_sys, T *accum, int32_t *flag, int32_t *nsamples, void *stream,
+                       const rcg_log_t *log_h = nullptr)
 {
     RCG_REQUIRE(sys && sol_h && y && f && t && h_abs && status && action, "%s: null argument", what);
+    LogDev logd{nullptr, nullptr, 0, 0};
+    if (log_h) {
+        RCG_REQUIRE(CTRL && log_h->rows && log_h->count && nsteps && accum, "%s: log needs rows, count, nsteps and accum", what);
+        RCG_REQUIRE(log_h->capacity >= 1 && log_h->every >= 1, "%s: log capacity and every must be >= 1", what);
+        logd = LogDev{log_h->rows, log_h->count, log_h->capacity, log_h->every};
+    }
+    const LogDev *logp = log_h ? &logd : nullptr;
     const int n = sys_n(sys->sys_id), m = sys_m(sys->sys_id);
     RCG_REQUIRE(n > 0, "%s: unknown sys_id %d", what, sys->sys_id);
     RCG_REQUIRE(sol_h->max_step > 0, "%s: `max_step` must be positive.", what);    // scipy common.py:18-23
@@ -311,15 +386,15 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
     switch (sys->sys_id) {
     case RCG_SYS_3WROBOT_NI:
         launch_rk45_sys<T, RCG_SYS_3WROBOT_NI, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
+                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
         break;
     case RCG_SYS_3WROBOT:
         launch_rk45_sys<T, RCG_SYS_3WROBOT, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
+                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
         break;
     default:
         launch_rk45_sys<T, RCG_SYS_2TANK, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples);
+                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
         break;
     }
     return check_launch(what);
@@ -367,6 +442,41 @@ int rcg_rk45_advance(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg
     return rcg::launch_rk45<double, true>("rcg_rk45_advance", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
                                           action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
                                           nsamples, stream);
+}
+
+int rcg_log_rows(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *t, const double *y,
+                 const double *action, const double *accum, const int32_t *nsteps, const int32_t *mask,
+                 const rcg_log_t *log, void *stream)
+{
+    using namespace rcg;
+    RCG_REQUIRE(obj && t && y && action && accum && log && log->rows && log->count, "rcg_log_rows: null argument");
+    RCG_REQUIRE(log->capacity >= 1 && log->every >= 1, "rcg_log_rows: log capacity and every must be >= 1");
+    RCG_REQUIRE((n == 3 && m == 2) || (n == 5 && m == 2) || (n == 2 && m == 1), "rcg_log_rows: unsupported dims n=%d m=%d", n, m);
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    const ObjDev<double> O = make_obj_dev<double>(obj, n, m);
+    const LogDev G{log->rows, log->count, log->capacity, log->every};
+    const bool rd = obj->r_is_diag && is_diag(obj->R1, n + m) && (obj->stage_struct == RCG_STAGE_QUADRATIC || is_diag(obj->R2, n + m));
+    const unsigned grid = (unsigned)((E + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+#define RCG_LOG_CALL(NN, MM)                                                                                       \
+    if (rd) log_rows_kernel<NN, MM, true><<<grid, 256, 0, s>>>(O, G, E, t, y, action, accum, nsteps, mask);         \
+    else log_rows_kernel<NN, MM, false><<<grid, 256, 0, s>>>(O, G, E, t, y, action, accum, nsteps, mask);
+    if (n == 3) { RCG_LOG_CALL(3, 2) } else if (n == 5) { RCG_LOG_CALL(5, 2) } else { RCG_LOG_CALL(2, 1) }
+#undef RCG_LOG_CALL
+    return check_launch("rcg_log_rows");
+}
+
+int rcg_rk45_advance_logged(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,
+                            double *y, double *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                            int32_t *nsteps, double *action, double *ctrl_clock, double sampling_time, int32_t max_steps,
+                            double *state_sys, double *accum, int32_t *sample_flag, int32_t *nsamples,
+                            const rcg_log_t *log, void *stream)
+{
+    RCG_REQUIRE(log, "rcg_rk45_advance_logged: null log descriptor");
+    return rcg::launch_rk45<double, true>("rcg_rk45_advance_logged", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
+                                          action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
+                                          nsamples, stream, log);
 }
 
 int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,

@@ -39,6 +39,10 @@ class ClosedLoopEngine:
     (``opt_start="init"``; the candidate set is then unused and may be ``None``); ``"nominal"`` = the reference's
     ``CtrlNominal3WRobotNI`` with ``ctrl_gain`` (Sys3WRobotNI only; ``action_init`` defaults to zeros like the
     reference's ``action_curr``, candidates unused).
+
+    ``log_every`` > 0 keeps a device-side trajectory ring for EVERY environment: one row
+    (t, state, stage_obj, accum_obj, action -- the rows of rcognita/loggers.py) per ``log_every``-th solver step,
+    the last ``log_capacity`` rows per environment (``trajectory(e)``, ``shard.gather_trajectories``).
     """
 
     def __init__(self, system, state_init, candidates, *, pars=(), ctrl_bnds=None, mode="MPC", Nactor=6, dt=0.01,
@@ -46,7 +50,7 @@ class ClosedLoopEngine:
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
                  buffer_size=10, critic_period=None, critic_fit_evals=0, actor="candidates", opt_start="argmin",
-                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, ctrl_gain=0.5):
+                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, ctrl_gain=0.5, log_every=0, log_capacity=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -80,6 +84,9 @@ class ClosedLoopEngine:
             if actor == "nominal" and (system != "3wrobotNI" or dtype != torch.float64):
                 raise ValueError("the nominal controller is CtrlNominal3WRobotNI (Sys3WRobotNI, fp64)")
             self.ctrl_gain = float(ctrl_gain)
+            self.log_every, self.log_capacity = int(log_every), int(log_capacity)
+            if self.log_every > 0 and (self.log_capacity < 1 or dtype != torch.float64):
+                raise ValueError("trajectory logging needs log_capacity >= 1 and fp64")
             self.actor, self.opt_start = actor, opt_start
             self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
             if actor == "opt" and dtype != torch.float64:
@@ -170,6 +177,7 @@ class ClosedLoopEngine:
             self.critic_flag = torch.empty((E,), dtype=torch.int32, device=dev)
             self.Jc = torch.empty((E,), dtype=dt, device=dev)
             self.nfits = torch.empty((E,), dtype=torch.int32, device=dev)
+        self.log = ops.TrajectoryLog(n, m, E, self.log_capacity, self.log_every, dev) if self.log_every > 0 else None
         if self.actor == "opt":
             L = self.obj.Nactor * m
             self.sqn = torch.zeros((L, E), dtype=dt, device=dev)
@@ -202,6 +210,8 @@ class ClosedLoopEngine:
             self.critic_flag.zero_()
             self.Jc.zero_()
             self.nfits.zero_()
+        if self.log is not None:
+            self.log.reset()
         ops.rhs(self.sysd, self.y, self.action, out=self.f)               # RK45.__init__: f = fun(t0, y0)
         self.intervals = 0
         self._first_done = False
@@ -226,6 +236,8 @@ class ClosedLoopEngine:
             self.nsamples += self.sample_flag
             self._actor()                                   # state_sys is still y0 here
         self.state_sys.copy_(self.y)
+        if self.log is not None:
+            ops.log_rows(self.obj, self.n, self.m, self.log, self.t, self.y, self.action, self.accum, nsteps=self.nsteps)
         self._first_done = True
 
     def _actor(self):
@@ -285,8 +297,12 @@ class ClosedLoopEngine:
             self._first_step()
         ops.rk45_advance(self.sysd, self.sol, self.obj, self.y, self.f, self.t, self.h_abs, self.status, self.action,
                          self.ctrl_clock, self.sampling_time, max_steps, state_sys=self.state_sys, accum=self.accum,
-                         sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps, nsamples=self.nsamples)
+                         sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps, nsamples=self.nsamples,
+                         log=self.log)
         self._actor()
+        if self.log is not None:            # the row of the sampling step: its action is known only now
+            ops.log_rows(self.obj, self.n, self.m, self.log, self.t, self.y, self.action, self.accum, nsteps=self.nsteps,
+                         mask=self.sample_flag)
         self.intervals += 1
 
     def all_done(self) -> bool:
@@ -305,6 +321,17 @@ class ClosedLoopEngine:
                 self.run_interval()
                 k += 1
         return k
+
+    def trajectory(self, e=0):
+        """Logged rows of environment ``e`` in the reference's column order (rcognita/loggers.py:41-94), oldest
+        kept row first: NI t,x,y,alpha,stage_obj,accum_obj,v,omega; 3wrobot t,x,y,alpha,v,omega,stage_obj,accum_obj,F,M;
+        2tank t,h1,h2,p,stage_obj,accum_obj."""
+        if self.log is None:
+            raise RuntimeError("trajectory logging is off (log_every=0)")
+        rows = self.log.env_rows(e)
+        if self.sysd.sys_id == _C.SYS_IDS["2tank"]:
+            rows = rows[:, [0, 1, 2, 5, 3, 4]]
+        return rows
 
     def results(self):
         """Host copies in the reference's row layout: y [E,n], action [E,m], etc."""

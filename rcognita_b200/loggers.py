@@ -53,6 +53,15 @@ class Logger:
                 w.writerow([int(e)] + self._row(*args))
 
 
+    def log_trajectory(self, datafile, rows):
+        """Append a whole logged trajectory (``ClosedLoopEngine.trajectory(e)``: rows already in this logger's
+        column order) to a CSV in the reference's row format."""
+        with open(datafile, 'a', newline='') as outfile:
+            w = csv.writer(outfile)
+            for r in rows:
+                w.writerow([float(v) for v in r])
+
+
 class Logger3WRobot(Logger):
     """rcognita/loggers.py:36-56."""
     HEADER = ['t [s]', 'x [m]', 'y [m]', 'alpha [rad]', 'v [m/s]', 'omega [rad/s]', 'stage_obj', 'accum_obj', 'F [N]', 'M [N m]']

@@ -77,12 +77,58 @@ def rk45_step(sysd, sol, y, f, t, h_abs, status, action, nfev=None):
              "rcg_rk45_step")
 
 
+class TrajectoryLog:
+    """Device-side trajectory ring of ``rcg_rk45_advance_logged`` / ``rcg_log_rows``: ``rows`` [capacity, ncols, E]
+    with columns (t, state[n], stage_obj, accum_obj, action[m]); ``count`` [E] rows written per lane."""
+
+    def __init__(self, n, m, E, capacity, every=1, device=None):
+        self.n, self.m, self.E, self.capacity, self.every = n, m, E, int(capacity), int(every)
+        self.ncols = 1 + n + 2 + m
+        self.rows = torch.full((self.capacity, self.ncols, E), float("nan"), dtype=_F64, device=device)
+        self.count = torch.zeros((E,), dtype=_I32, device=device)
+        self.desc = _C.RcgLog(self.rows.data_ptr(), self.count.data_ptr(), self.capacity, self.every)
+
+    def reset(self):
+        self.rows.fill_(float("nan"))
+        self.count.zero_()
+
+    def env_rows(self, e):
+        """Chronological rows of environment ``e`` (oldest kept first) as a host array [rows, ncols]."""
+        c = int(self.count[e].item())
+        k = min(c, self.capacity)
+        idx = [(c - k + i) % self.capacity for i in range(k)]
+        return self.rows[idx, :, e].cpu().numpy()
+
+
+def log_rows(obj, n, m, log, t, y, action, accum, nsteps=None, mask=None):
+    """Append the current row of the masked lanes to the trajectory ring (``rcg_log_rows``)."""
+    E = y.shape[1]
+    _C.check(_C.lib.rcg_log_rows(C.byref(obj), n, m, E, _ptr(t, _F64, (E,), "t"), _ptr(y, _F64, (n, E), "y"),
+                                 _ptr(action, _F64, (m, E), "action"), _ptr(accum, _F64, (E,), "accum"),
+                                 _ptr(nsteps, _I32, (E,), "nsteps", optional=True),
+                                 _ptr(mask, _I32, (E,), "mask", optional=True), C.byref(log.desc), _stream()),
+             "rcg_log_rows")
+
+
 def rk45_advance(sysd, sol, obj, y, f, t, h_abs, status, action, ctrl_clock, sampling_time, max_steps,
-                 state_sys=None, accum=None, sample_flag=None, nfev=None, nsteps=None, nsamples=None):
-    """Fused loop body between two controller samples (see ``rcg_rk45_advance`` in rcg.h)."""
+                 state_sys=None, accum=None, sample_flag=None, nfev=None, nsteps=None, nsamples=None, log=None):
+    """Fused loop body between two controller samples (see ``rcg_rk45_advance`` in rcg.h); with ``log`` (a
+    ``TrajectoryLog``) the held-action steps are appended to the trajectory ring."""
     n, m = _C.SYS_DIMS[sysd.sys_id]
     E = y.shape[1]
     dt = y.dtype
+    if log is not None:
+        if dt != _F64:
+            raise TypeError("trajectory logging runs in fp64")
+        _C.check(_C.lib.rcg_rk45_advance_logged(
+            C.byref(sysd), C.byref(sol), C.byref(obj), E, _ptr(y, None, (n, E), "y"), _ptr(f, dt, (n, E), "f"),
+            _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),
+            _ptr(nfev, _I32, (E,), "nfev", optional=True), _ptr(nsteps, _I32, (E,), "nsteps"),
+            _ptr(action, dt, (m, E), "action"), _ptr(ctrl_clock, _F64, (E,), "ctrl_clock"), float(sampling_time),
+            int(max_steps), _ptr(state_sys, dt, (n, E), "state_sys", optional=True), _ptr(accum, dt, (E,), "accum"),
+            _ptr(sample_flag, _I32, (E,), "sample_flag", optional=True),
+            _ptr(nsamples, _I32, (E,), "nsamples", optional=True), C.byref(log.desc), _stream()), "rcg_rk45_advance_logged")
+        return
     fn = getattr(_C.lib, "rcg_rk45_advance" + _suffix(dt))
     _C.check(fn(C.byref(sysd), C.byref(sol), C.byref(obj), E, _ptr(y, None, (n, E), "y"), _ptr(f, dt, (n, E), "f"),
                 _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),

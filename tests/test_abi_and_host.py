@@ -166,6 +166,19 @@ full = bw.synthetic_states("3wrobotNI", 0, E, seed=0)
 assert ret.shape == (E,), ret.shape
 assert np.array_equal(ret.numpy(), full[:, 0] * 2.0 + full[:, 1])   # global env order, bit-exact
 assert tot.tolist() == [E, 7 * 3], tot.tolist()
+# trajectory rings: [capacity, ncols, E_local] per rank -> global environment order on rank 0
+cap, ncols = 4, 8
+rows = torch.from_numpy(np.arange(lo, hi, dtype=np.float64))[None, None, :] + torch.arange(cap * ncols, dtype=torch.float64).reshape(cap, ncols, 1) * 1e6
+cnt = torch.arange(lo, hi, dtype=torch.int32) % 7
+R, Cn = shard.gather_trajectories(rows, cnt)
+if rank == 0:
+    assert R.shape == (cap, ncols, E) and Cn.shape == (E,)
+    assert np.array_equal(R[2, 3].numpy(), np.arange(E) + (2 * ncols + 3) * 1e6)
+    assert np.array_equal(Cn.numpy(), np.arange(E) % 7)
+    e = 2050                                     # owned by rank 1; count 6 > capacity 4 -> wrapped ring
+    assert Cn[e] == 6 and np.array_equal(shard.ring_rows(R, Cn, e)[:, 0].numpy(), e + np.array([2, 3, 0, 1]) * ncols * 1e6)
+else:
+    assert R is None and Cn is None
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

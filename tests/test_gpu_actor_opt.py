@@ -357,3 +357,53 @@ def test_fused_engine_nominal_episode_golden(rb):
     assert np.max(np.abs(r["y"][0] - ref[-1, 1:4])) <= 1e-6 * np.max(np.abs(ref[-1, 1:4]))
     assert abs(r["accum"][0] - ref[-1, 6]) <= 1e-6 * ref[-1, 6]
     assert np.array_equal(r["y"][0], r["y"][1])
+
+
+@pytest.mark.parametrize("key", ["NI_MPC_N6_x1", "3wrobot_RQL_N10", "2tank_SQL_N8"])
+def test_device_trajectory_ring_golden(rb, key):
+    """log_every=1: the device-side ring of environment 0 holds one row per solver step, equal to the rows the live
+    reference's loop produced (t bit-exact; state, action, accum to 1e-9), in the reference's column order; the
+    stage_obj column equals the oracle's stage_obj of that row; other environments log independently."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    g = load("closed_loop.json")[key]
+    name = g["system"]
+    n, m = DIMS[name]
+    P = PRESET[name]
+    ref = np.array(g["rows"])                                   # t, state[n], action[m], accum, sampled
+    x0 = np.array([g["x0"], g["x0"], np.array(g["x0"]) * 0.9])
+    kw = dict(pars=P["pars"], ctrl_bnds=P["bnds"], mode=g["mode"], Nactor=g["Nactor"], dt=P["dt"],
+              pred_step_size=P["dt"] * P["psm"], t1=g["t1"], R1=P["R1_diag"], gamma=g["gamma"], critic_struct=g["critic_struct"],
+              observation_target=P["target"], action_init=g["action_init"], w_critic=g["w_fixed"])
+    eng = ClosedLoopEngine(name, x0, np.array(g["cand"]), log_every=1, log_capacity=ref.shape[0] + 8, **kw)
+    eng.run()
+    tr = eng.trajectory(0)
+    assert tr.shape == (ref.shape[0], 1 + n + 2 + m)
+    so_col, acc_col = (1 + n, 2 + n) if name != "2tank" else (4, 5)
+    act_cols = list(range(3 + n, 3 + n + m)) if name != "2tank" else [3]
+    assert np.array_equal(tr[:, 0], ref[:, 0])
+    assert np.max(np.abs(tr[:, 1:1 + n] - ref[:, 1:1 + n]) / np.maximum(np.abs(ref[:, 1:1 + n]), 1e-2)) <= 1e-9
+    assert np.max(np.abs(tr[:, act_cols] - ref[:, 1 + n:1 + n + m])) <= 1e-9 * np.max(np.abs(ref[:, 1 + n:1 + n + m]))
+    assert np.max(np.abs(tr[:, acc_col] - ref[:, 1 + n + m]) / np.maximum(np.abs(ref[:, 1 + n + m]), 1e-2)) <= 1e-9
+    ct = oracle.make_ctrl(n, m, mode=g["mode"], Nactor=g["Nactor"], R1=P["R1_diag"], observation_target=P["target"])
+    for r in tr[:: max(1, len(tr) // 40)]:
+        so = oracle.stage_obj(ct, n, m, r[1:1 + n], r[act_cols])
+        assert abs(r[so_col] - so) <= 1e-9 * max(abs(so), 1e-6)
+    assert np.array_equal(eng.trajectory(1), tr)
+    tr2 = eng.trajectory(2)
+    assert tr2.shape[0] == int(eng.results()["nsteps"][2]) and not np.array_equal(tr2[-1, 1:1 + n], tr[-1, 1:1 + n])
+
+
+def test_device_trajectory_ring_decimation_and_wraparound(rb):
+    """log_every=3 keeps the steps whose per-lane index is a multiple of 3; a ring shorter than the episode keeps
+    the most recent rows in order."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    g = load("closed_loop.json")["NI_MPC_N6_x1"]
+    P = PRESET["3wrobotNI"]
+    ref = np.array(g["rows"])
+    kw = dict(ctrl_bnds=P["bnds"], mode="MPC", Nactor=6, dt=0.01, t1=g["t1"], R1=P["R1_diag"], action_init=g["action_init"])
+    eng = ClosedLoopEngine("3wrobotNI", np.array([g["x0"]] * 2), np.array(g["cand"]), log_every=3, log_capacity=20, **kw)
+    eng.run()
+    tr = eng.trajectory(1)
+    want = ref[2::3][-20:]                                       # steps 3, 6, 9, ... (1-based), the last 20 of them
+    assert tr.shape[0] == 20 and np.array_equal(tr[:, 0], want[:, 0])
+    assert int(eng.log.count[0].item()) == ref.shape[0] // 3
