@@ -12,6 +12,7 @@
 // changing).  The iterate with the smallest J_c is returned, so the result is never worse than w_critic_init.
 // Parity is on the fitted COST against the reference's SLSQP result (tests/golden/critic_fit.json), never on
 // the weights (hard part 5).
+#include <cstdlib>
 #include <type_traits>
 
 #include "rcg_host.h"
@@ -27,17 +28,35 @@ struct GlobalWF {
     __device__ __forceinline__ T operator()(int i) const { return w[i * stride + idx]; }
 };
 
+// Lane of this thread: the thread index itself (masked), or -- second phase of a two-phase fit -- entry
+// `thread index` of the compacted list of environments whose first-phase budget ran out.  -1: nothing to do.
+__device__ __forceinline__ int64_t fit_lane(int64_t E, const int32_t *mask, const int32_t *lane_list, const int32_t *lane_count)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane_list) return (idx < *lane_count) ? (int64_t)lane_list[idx] : -1;
+    if (idx >= E || (mask && mask[idx] == 0)) return -1;
+    return idx;
+}
+// First phase: an environment that used up its budget is queued for the second phase and writes nothing.
+__device__ __forceinline__ bool fit_defer(bool exhausted, int64_t e, int32_t *todo_list, int32_t *todo_count)
+{
+    if (!todo_list || !exhausted) return false;
+    todo_list[atomicAdd(todo_count, 1)] = (int32_t)e;
+    return true;
+}
+
 template <int N, int M, int CS, bool RDIAG>
 __global__ void __launch_bounds__(128)
 critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const double *__restrict__ obs_buf,
                   const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
                   const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
-                  double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out)
+                  double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out,
+                  const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
+                  int32_t *__restrict__ todo_list, int32_t *__restrict__ todo_count)
 {
     constexpr int D = dim_critic_c(CS, N, M);
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    if (mask && mask[e] == 0) return;
+    const int64_t e = fit_lane(E, mask, lane_list, lane_count);
+    if (e < 0) return;
     const int K = O.Ncritic - 1;
 
     double Phi[kFitMaxK * D], b[kFitMaxK], lam[kFitMaxK], lt[kFitMaxK], F[kFitMaxK], dl[kFitMaxK];
@@ -82,6 +101,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
     double Jbest = cost(w0);
 
     const double J0 = Jbest;
+    int evals = 0;                                         // dual / Newton passes spent (budget: max_evals, 0 = none)
     if (K >= 1 && trace > 0 && isfinite(trace) && isfinite(bb)) {
         double mu = 0;
         auto zj = [&](const double *l, int j) {
@@ -99,7 +119,6 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
             }
             return s;
         };
-        int evals = 0;                                     // dual / Newton passes spent (budget: max_evals, 0 = none)
         for (int outer = 0; outer < max_outer && evals < max_evals; ++outer) {
             mu = mu_rel * trace / K;                       // continuation: the proximal weight shrinks 100x per stage
             mu_rel *= 1e-2;
@@ -182,6 +201,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
             }                                              // else: keep the centre, try the next (smaller) mu
         }
     }
+    if (fit_defer(evals >= max_evals, e, todo_list, todo_count)) return;
     for (int j = 0; j < D; ++j) w_g[j * E + e] = wb[j];
     if (update_prev)                                   // controllers.py:1471: w_critic_prev = w_critic
         for (int j = 0; j < D; ++j) wprev_g[j * E + e] = wb[j];
@@ -246,14 +266,15 @@ __global__ void __launch_bounds__(128)
 critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const double *__restrict__ obs_buf,
                    const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
                    const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
-                   double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out)
+                   double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out,
+                  const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
+                  int32_t *__restrict__ todo_list, int32_t *__restrict__ todo_count)
 {
     constexpr int D = dim_critic_c(CS, N, M), P = N + M;
     using FI = FeatIdx<CS, N, M>;
     extern __shared__ double fit_smem[];                   // [2][D][blockDim.x]
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    if (mask && mask[e] == 0) return;
+    const int64_t e = fit_lane(E, mask, lane_list, lane_count);
+    if (e < 0) return;
     const int K = O.Ncritic - 1;
     double *wa = fit_smem + threadIdx.x;                   // prox centre / best iterate
     double *wbuf = fit_smem + (size_t)D * blockDim.x + threadIdx.x;
@@ -321,8 +342,8 @@ critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const do
     double Jbest = 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
     const double J0 = Jbest;
 
+    int evals = 0;                                         // dual / Newton passes spent (budget: max_evals, 0 = none)
     if (K >= 1 && trace > 0 && isfinite(trace) && isfinite(bb)) {
-        int evals = 0;                                     // dual / Newton passes spent (budget: max_evals, 0 = none)
         for (int outer = 0; outer < max_outer && evals < max_evals; ++outer) {
             const double mu = mu_rel * trace / K;          // continuation: the proximal weight shrinks 100x per stage
             mu_rel *= 1e-2;
@@ -416,6 +437,7 @@ critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const do
             }                                              // else: keep the centre, try the next (smaller) mu
         }
     }
+    if (fit_defer(evals >= max_evals, e, todo_list, todo_count)) return;
     static_for<0, D>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         const double w = wa[j * ws];
@@ -458,8 +480,33 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     const int outer = 5;
     const double mu_rel = 1e-3;
     const int newton = 20;
-    const int evals = max_evals > 0 ? max_evals : 0x7fffffff;
     const bool fast = obj->Ncritic - 1 <= 3;
+    // Run-to-convergence fits of a large batch go in two phases.  A few per cent of in-loop problems need hundreds
+    // to thousands of dual evaluations while the rest finish within a few dozen; with one environment per lane every
+    // warp that holds one of them waits for it (ncu: 3.3 of 32 lanes active on average).  Phase 1 gives every
+    // environment kPhase1Budget evaluations; those that run out are queued (and write nothing), phase 2 restarts
+    // exactly them, packed densely into warps.  Each environment's result is what the single-phase kernel computes.
+    constexpr int kPhase1Budget = 32;
+    // Measured on B200 (profiles/r01_critic_fit_two_phase.txt): 23.0 -> 20.8 ms per 1 M fits of the 28-weight critic
+    // inside config 3's loop -- the rest of the tail is the serial dependency chain of the environments that run
+    // into the iteration caps, not idle lanes; for small critics the second launch costs more than it saves
+    // (2tank, 3 weights: 0.49 -> 0.55 ms), hence the dim_critic threshold.
+    const bool two_phase = max_evals <= 0 && E >= 4096 && dim_critic_c(obj->critic_struct, n, m) >= 10 &&
+                           getenv("RCG_FIT_ONE_PHASE") == nullptr;
+    int32_t *todo = nullptr;
+    if (two_phase) {
+        if (cudaMallocAsync((void **)&todo, (size_t)(E + 1) * sizeof(int32_t), s) != cudaSuccess) {
+            (void)cudaGetLastError();
+            todo = nullptr;                                // no pool on this device: single phase
+        } else {
+            cudaMemsetAsync(todo + E, 0, sizeof(int32_t), s);
+        }
+    }
+    const int nphases = todo ? 2 : 1;
+    for (int phase = 0; phase < nphases; ++phase) {
+        const int evals = (todo && phase == 0) ? kPhase1Budget : (max_evals > 0 ? max_evals : 0x7fffffff);
+        const int32_t *lane_list = (todo && phase == 1) ? todo : nullptr, *lane_count = (todo && phase == 1) ? todo + E : nullptr;
+        int32_t *todo_list = (todo && phase == 0) ? todo : nullptr, *todo_count = (todo && phase == 0) ? todo + E : nullptr;
 #define FIT3(NN, MM, CS, RD)                                                                                              \
     {                                                                                                                     \
         auto kern = critic_fit3_kernel<NN, MM, CS, RD>;                                                                   \
@@ -467,14 +514,16 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
         static bool configured = false;                                                                                   \
         if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; } \
         kern<<<grid, 128, smem, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mask, mu_rel, outer, newton,  \
-                                     evals, update_prev, Jc_out);                                                                \
+                                     evals, update_prev, Jc_out, lane_list, lane_count, todo_list, todo_count);                  \
     }
 #define FIT(NN, MM, CS)                                                                                                   \
     if (fast) { if (rd) FIT3(NN, MM, CS, true) else FIT3(NN, MM, CS, false) }                                             \
     else if (rd) critic_fit_kernel<NN, MM, CS, true><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, \
-                                                                     mask, mu_rel, outer, newton, evals, update_prev, Jc_out);                \
+                                                                     mask, mu_rel, outer, newton, evals, update_prev, Jc_out,      \
+                                                                     lane_list, lane_count, todo_list, todo_count);                \
     else critic_fit_kernel<NN, MM, CS, false><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w,  \
-                                                                   mask, mu_rel, outer, newton, evals, update_prev, Jc_out);
+                                                                   mask, mu_rel, outer, newton, evals, update_prev, Jc_out,        \
+                                                                   lane_list, lane_count, todo_list, todo_count);
 #define FITCS(NN, MM)                  \
     switch (obj->critic_struct) {      \
     case 0: FIT(NN, MM, 0) break;      \
@@ -482,9 +531,15 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     case 2: FIT(NN, MM, 2) break;      \
     default: FIT(NN, MM, 3) break;     \
     }
-    if (n == 3) { FITCS(3, 2) } else if (n == 5) { FITCS(5, 2) } else { FITCS(2, 1) }
+        if (n == 3) { FITCS(3, 2) } else if (n == 5) { FITCS(5, 2) } else { FITCS(2, 1) }
 #undef FITCS
 #undef FIT
 #undef FIT3
-    return check_launch("rcg_critic_fit");
+        if (int rc = check_launch("rcg_critic_fit")) {
+            if (todo) cudaFreeAsync(todo, s);
+            return rc;
+        }
+    }
+    if (todo) cudaFreeAsync(todo, s);
+    return 0;
 }
