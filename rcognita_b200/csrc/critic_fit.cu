@@ -495,6 +495,19 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
                            getenv("RCG_FIT_ONE_PHASE") == nullptr;
     int32_t *todo = nullptr;
     if (two_phase) {
+        // keep the stream-ordered pool's memory across synchronisation points (default: released at every sync,
+        // which would turn the per-call scratch into a real cudaMalloc / cudaFree pair)
+        static bool pool_configured = false;
+        if (!pool_configured) {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = (uint64_t)256 << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+            pool_configured = true;
+        }
         if (cudaMallocAsync((void **)&todo, (size_t)(E + 1) * sizeof(int32_t), s) != cudaSuccess) {
             (void)cudaGetLastError();
             todo = nullptr;                                // no pool on this device: single phase

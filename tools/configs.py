@@ -28,9 +28,24 @@ CFG = {
 }
 
 
-def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_critic=None, fit_evals=0):
+def dist_info():
+    """(rank, world) under torchrun (one process per GPU, NCCL), else (0, 1)."""
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            dist.init_process_group("nccl")
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_critic=None, fit_evals=0, lo=0, hi=None):
     E = (E + 1023) // 1024 * 1024
-    x0 = synthetic_states(c["system"], 0, E, seed=0)
+    if hi is not None:                         # this rank's contiguous block of the global batch (shard.shard_range)
+        x0 = synthetic_states(c["system"], lo, hi, seed=0)
+        E = hi - lo
+    else:
+        x0 = synthetic_states(c["system"], 0, E, seed=0)
     cand = synthetic_candidates(c["bnds"], c["N"], C, seed=1)
     eng = ClosedLoopEngine(c["system"], x0, cand, pars=c["pars"], ctrl_bnds=c["bnds"], mode=c["mode"], Nactor=c["N"],
                            dt=c["dt"], pred_step_size=c["dt"] * c["psm"], t1=t1, R1=c["R1"], observation_target=c["target"],
@@ -71,7 +86,34 @@ def timed_closed_loop(c, E, C, t1, critic_fit=True, dtype=torch.float64, w_criti
                      critic_fits_per_s=(samples / ms * 1e3) if critic_fit else 0.0, ms_per_interval=ms / max(k, 1))
 
 
+def run_config_sharded(name, a, rank, world):
+    """Strong scaling (BASELINE config 3: the 1 M environments sharded over 1/2/4/8 GPUs): every rank runs its
+    contiguous block, no per-step communication; time = max over ranks between two barriers; returns gathered."""
+    import torch.distributed as dist
+    from rcognita_b200 import shard
+    c = CFG[name]
+    Eg = (a.envs + 1023) // 1024 * 1024
+    lo, hi = shard.shard_range(Eg, rank, world)
+    dist.barrier()
+    eng, r = timed_closed_loop(c, Eg, a.cands, a.t1, fit_evals=a.fit_evals, lo=lo, hi=hi)
+    ms = torch.tensor([r["ms"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    counts = torch.tensor([int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())], dtype=torch.int64, device="cuda")
+    ret, tot = shard.gather_returns(eng.accum, counts)
+    if rank == 0:
+        msv = float(ms.item())
+        print(json.dumps(dict(config=name, n_gpus=world, scaling="strong", E_total=Eg, E_per_rank=hi - lo, C=a.cands, t1=a.t1,
+                              ms_max_over_ranks=msv, intervals=r["intervals"], ms_per_interval=msv / max(r["intervals"], 1),
+                              env_steps_total=int(tot[0].item()), mean_return=float(ret.mean().item()),
+                              returns_gathered=int(ret.numel()))), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_config(name, a):
+    rank, world = dist_info()
+    if world > 1:
+        return run_config_sharded(name, a, rank, world)
     c = CFG[name]
     eng, r = timed_closed_loop(c, a.envs, a.cands, a.t1, fit_evals=a.fit_evals)
     res = eng.results()
