@@ -174,8 +174,13 @@ __device__ __forceinline__ void log_row(const LogDev &G, int64_t E, int64_t e, i
     ++cnt;
 }
 
+// Resident 128-thread blocks per SM the register allocation is held to: the kernel is a chain of dependent FP64
+// operations per lane, so residency (warps to switch between) is what buys pipe utilisation.  NI fits 5 blocks
+// (96 registers) and 2tank 6 (74) without spilling; 3wrobot (35 state/stage doubles more) spills beyond 4.
+__host__ __device__ constexpr int rk45_min_blocks(int sys) { return sys == RCG_SYS_3WROBOT_NI ? 5 : sys == RCG_SYS_2TANK ? 6 : 4; }
+
 template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, rk45_min_blocks(SYS))
 rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
             const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
