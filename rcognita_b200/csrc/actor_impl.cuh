@@ -216,8 +216,17 @@ struct ActorArgs {
     int cand_per_env, w_per_env;
 };
 
+// Resident 256-thread blocks per SM the register allocation of the specialised kernels is held to (measured on
+// B200, shared candidate table = the FP64-bound case): 3wrobot at 2 blocks (128 registers, <= 96 B of spills)
+// instead of the 1 block its 162 registers allowed: 3.10 -> 2.64 ms for 262,144 x 256 RQL 'quadratic' N=10;
+// NI at 4 blocks (64 registers, spills) was slower than at 3 (0.298 vs 0.290 ms), so it stays at 3; 2tank fits 4.
+__host__ __device__ constexpr int actor_min_blocks(int sys, int na, bool rdiag)
+{
+    return (na > 0 && rdiag) ? (sys == RCG_SYS_3WROBOT_NI ? 3 : sys == RCG_SYS_3WROBOT ? 2 : 4) : 1;
+}
+
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
-__global__ void __launch_bounds__(kActorThreads)
+__global__ void __launch_bounds__(kActorThreads, actor_min_blocks(SYS, NA, RDIAG))
 actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ ObjDev<T> O,
                   const __grid_constant__ ActorArgs A, const T *__restrict__ state_sys_g, const T *__restrict__ obs_g,
                   const T *__restrict__ cand_g, const T *__restrict__ w_g, const int32_t *__restrict__ mask_g,
