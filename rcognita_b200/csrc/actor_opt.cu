@@ -40,6 +40,13 @@ static int opt_common(const char *what, const rcg_system_t *sys, const rcg_objec
     return 0;
 }
 
+// header (work queue + final costs) + per-thread storage for every launched thread (<= E*S rounded up to a block)
+static int64_t opt_ws_doubles(int na, int n, int m, bool generic, int64_t E, int S)
+{
+    const int64_t threads = (E * S + kOptThreads - 1) / kOptThreads * kOptThreads;
+    return kOptWsHeader + E * S + opt_ws_per_thread(na, n, m, generic) * threads;
+}
+
 static bool opt_is_generic(const rcg_objective_t *obj, int p)
 {
     const bool rdiag = obj->r_is_diag && is_diag(obj->R1, p) && obj->stage_struct == RCG_STAGE_QUADRATIC;
@@ -56,7 +63,7 @@ static int launch_opt(const char *what, const rcg_system_t *sys, const rcg_objec
     int n, m, shift;
     if (int rc = opt_common(what, sys, obj, E, S, state_sys, obs, sqn, w_critic, n, m, shift)) return rc;
     const bool generic = opt_is_generic(obj, n + m);
-    const int64_t need = grad_only && !generic ? 0 : opt_ws_per_thread(obj->Nactor, n, m, generic) * E * S * (int64_t)sizeof(double);
+    const int64_t need = grad_only && !generic ? 0 : opt_ws_doubles(obj->Nactor, n, m, generic, E, S) * (int64_t)sizeof(double);
     RCG_REQUIRE(need == 0 || (ws && ws_bytes >= need), "%s: workspace too small (%lld bytes given, %lld needed)", what,
                 (long long)ws_bytes, (long long)need);
     if (int rc = require_device()) return rc;
@@ -73,6 +80,12 @@ static int launch_opt(const char *what, const rcg_system_t *sys, const rcg_objec
     L.A.pg_tol = pg_tol;
     L.A.f_tol = f_tol;
     L.A.grad_only = grad_only;
+    L.A.dynamic = grad_only ? 0 : 1;
+    int dev = 0;
+    L.sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&L.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (L.A.dynamic) cudaMemsetAsync(ws, 0, kOptWsHeader * sizeof(double), (cudaStream_t)stream);      // work-queue counter
     L.state_sys = state_sys; L.obs = obs; L.w = w_critic; L.sqn = sqn; L.mask = mask; L.ws = ws;
     L.J = J_out; L.grad = grad_out; L.iters = iters_out; L.nfev = nfev_out; L.best = best_out; L.Jmin = Jmin_out;
     L.action = action_out; L.accum = accum;
@@ -100,7 +113,7 @@ int64_t rcg_actor_opt_workspace_bytes(const rcg_system_t *sys, const rcg_objecti
     if (!sys || !obj) return RCG_EINVAL;
     const int n = rcg::sys_n(sys->sys_id), m = rcg::sys_m(sys->sys_id);
     if (n <= 0 || obj->Nactor < 1 || obj->Nactor > RCG_MAX_NACTOR || E < 0 || S < 1) return RCG_EINVAL;
-    return rcg::opt_ws_per_thread(obj->Nactor, n, m, rcg::opt_is_generic(obj, n + m)) * E * S * (int64_t)sizeof(double);
+    return rcg::opt_ws_doubles(obj->Nactor, n, m, rcg::opt_is_generic(obj, n + m), E, S) * (int64_t)sizeof(double);
 }
 
 int rcg_actor_grad(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S, const double *state_sys,

@@ -161,12 +161,15 @@ struct OptGlobalMem {
     __device__ __forceinline__ T &C(int k) { return base[((int64_t)5 * L + (int64_t)NA * N + NA + k) * stride]; }
 };
 
-// workspace doubles per thread
+// Workspace layout (doubles): [0, 2) work-queue counter, [2, 2 + E*S) final cost per start (read by the select
+// kernel when S > 1), then the quasi-Newton pairs [2][kOptMem][L][TR] and -- generic kernel only -- the working
+// vectors and the rollout [5 L + Nactor (n + 2)][TR]; TR = launched threads <= E*S rounded up to a block.
 __host__ __device__ inline int64_t opt_ws_per_thread(int na_runtime, int n, int m, bool generic)
 {
     const int64_t L = (int64_t)na_runtime * m;
     return 2 * kOptMem * L + (generic ? 5 * L + (int64_t)na_runtime * (n + 2) : 0);
 }
+constexpr int64_t kOptWsHeader = 2;
 
 struct OptArgs {
     int64_t E;
@@ -175,8 +178,14 @@ struct OptArgs {
     int max_iter;
     double pg_tol, f_tol;
     int grad_only;                   // rcg_actor_grad: one value-and-gradient evaluation, no iteration
+    int dynamic;                     // lanes pull problems from the work queue (else: problem = thread index)
 };
 
+// One LANE per problem (environment, start point), persistent: a lane that finishes its problem pulls the next one
+// from a global counter, so the lanes of a warp stay busy although iteration counts differ by an order of magnitude
+// between problems (measured before this change: mean 17, p99 27, max 95 iterations near the goal -- every warp waited
+// for its slowest lane).  The body is a state machine -- one pass = one trial point: forward sweep, then either a
+// backtracking step or (accepted) the reverse sweep, the quasi-Newton update and the next trial point.
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
 __global__ void __launch_bounds__(kOptThreads)
 actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ ObjDev<T> O,
@@ -190,140 +199,161 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
     constexpr int DIMC = (MODE == RCG_MODE_MPC) ? 1 : dim_critic_c(CS, N, M);
     constexpr int LC = (NA > 0) ? NA * M : 1, NK = (NA > 0) ? NA : 1;
     constexpr int UK = (NA > 0) ? NA : 1, UL = (NA > 0) ? NA * M : 1;      // unroll factors (1 = keep the runtime loop)
-    constexpr int kNone = 0x7fffffff;
     const int na = (NA > 0) ? NA : O.Nactor;
     const int L = na * M;
     const int64_t E = A.E;
-    const int64_t nthreads = E << A.S_shift;
-    const int64_t tid = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
-    const int64_t e = tid >> A.S_shift;
-    const int sidx = (int)(tid & (A.S - 1));
-    const bool active = tid < nthreads && (mask_g == nullptr || mask_g[e] != 0);
+    const int64_t nprob = E << A.S_shift;
+    const int64_t col = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;    // this thread's workspace column
+    const int64_t TR = (int64_t)gridDim.x * kOptThreads;
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(ws_g);
+    T *Jscr = ws_g + kOptWsHeader;
 
-    T J = T(0);
-    T a_first[M];                    // first action of this thread's minimiser
+    // ---- box ----
+    const T h = O.pred_step_size;
+    T lo[M], hi[M], step0 = T(1);
 #pragma unroll
-    for (int j = 0; j < M; ++j) a_first[j] = T(0);
-    int iters = 0, nfev = 0;
-    if (active) {
-        // ---- per-environment constants ----
-        T x0[N], ob0[N], w[DIMC];
+    for (int j = 0; j < M; ++j) {
+        lo[j] = Sd.has_bnds ? Sd.lo[j] : -CUDART_INF;
+        hi[j] = Sd.has_bnds ? Sd.hi[j] : CUDART_INF;
+    }
+    if (Sd.has_bnds) {
+        step0 = T(0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) { x0[i] = state_sys_g[i * E + e]; ob0[i] = obs_g[i * E + e]; }
-        if constexpr (MODE != RCG_MODE_MPC) {
-#pragma unroll
-            for (int i = 0; i < DIMC; ++i) w[i] = A.w_per_env ? w_g[i * E + e] : w_g[i];
-        }
-        const RegW<T, DIMC> wacc{w};
-        T s0 = T(0), c0 = T(1);
-        if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
-        const T h = O.pred_step_size;
-        T lo[M], hi[M], step0 = T(1);
-#pragma unroll
-        for (int j = 0; j < M; ++j) {
-            lo[j] = Sd.has_bnds ? Sd.lo[j] : -CUDART_INF;
-            hi[j] = Sd.has_bnds ? Sd.hi[j] : CUDART_INF;
-        }
-        if (Sd.has_bnds) {
-            step0 = T(0);
-#pragma unroll
-            for (int j = 0; j < M; ++j) step0 = fmax(step0, hi[j] - lo[j]);
-        }
-        auto clip = [&](T v, int i) {
-            const T l = lo[i % M], u = hi[i % M];
-            v = (v < l) ? l : v;
-            return (v > u) ? u : v;
-        };
+        for (int j = 0; j < M; ++j) step0 = fmax(step0, hi[j] - lo[j]);
+    }
+    auto clip = [&](T v, int i) {
+        const T l = lo[i % M], u = hi[i % M];
+        v = (v < l) ? l : v;
+        return (v > u) ? u : v;
+    };
 
-        // ---- storage ----
-        using LMem = OptLocalMem<T, LC, NK, N>;
-        using GMem = OptGlobalMem<T, N>;
-        typename std::conditional<(NA > 0), LMem, GMem>::type mem;
-        T *pairs = ws_g + tid;                                         // [2][kOptMem][L][nthreads]
-        if constexpr (NA == 0) {
-            mem.base = ws_g + (int64_t)2 * kOptMem * L * nthreads + tid;
-            mem.stride = nthreads;
-            mem.L = L;
-            mem.NA = na;
-        }
-        auto Sp = [&](int slot, int i) -> T & { return pairs[((int64_t)slot * L + i) * nthreads]; };
-        auto Yp = [&](int slot, int i) -> T & { return pairs[((int64_t)(kOptMem + slot) * L + i) * nthreads]; };
+    // ---- storage ----
+    using LMem = OptLocalMem<T, LC, NK, N>;
+    using GMem = OptGlobalMem<T, N>;
+    typename std::conditional<(NA > 0), LMem, GMem>::type mem;
+    T *pairs = ws_g + kOptWsHeader + nprob + col;                      // [2][kOptMem][L][TR]
+    if constexpr (NA == 0) {
+        mem.base = ws_g + kOptWsHeader + nprob + (int64_t)2 * kOptMem * L * TR + col;
+        mem.stride = TR;
+        mem.L = L;
+        mem.NA = na;
+    }
+    auto Sp = [&](int slot, int i) -> T & { return pairs[((int64_t)slot * L + i) * TR]; };
+    auto Yp = [&](int slot, int i) -> T & { return pairs[((int64_t)(kOptMem + slot) * L + i) * TR]; };
 
-        // ---- forward sweep: cost of the sequence in vector `which`, keeps the rollout ----
-        auto forward = [&](int which) -> T {
-            T st[N], ob[N], sn = s0, cs = c0, Jc = T(0);
+    // ---- per-problem state ----
+    T x0[N], ob0[N], w[DIMC];
+    T s0 = T(0), c0 = T(1);
+    const RegW<T, DIMC> wacc{w};
+    int64_t p = -1, e = 0;
+    bool need = true, idle = false, first = true, taken = false;
+    int npairs = 0, head = 0, stall = 0, bt = 0, iters = 0, nfev = 0;
+    T lam_ls = T(1), gs = T(0), J = T(0);
+
+    // ---- forward sweep: cost of the sequence in vector `which`, keeps the rollout ----
+    auto forward = [&](int which) -> T {
+        T st[N], ob[N], sn = s0, cs = c0, Jc = T(0);
 #pragma unroll
-            for (int i = 0; i < N; ++i) { st[i] = x0[i]; ob[i] = ob0[i]; }
+        for (int i = 0; i < N; ++i) { st[i] = x0[i]; ob[i] = ob0[i]; }
 #pragma unroll UK
-            for (int k = 0; k < na; ++k) {
-                T a[M];
+        for (int k = 0; k < na; ++k) {
+            T a[M];
 #pragma unroll
-                for (int j = 0; j < M; ++j) a[j] = mem.v(which, k * M + j);
+            for (int j = 0; j < M; ++j) a[j] = mem.v(which, k * M + j);
 #pragma unroll
-                for (int i = 0; i < N; ++i) mem.X(k, i) = st[i];
-                mem.S(k) = sn;
-                mem.C(k) = cs;
-                const bool last = (k + 1 == na);
-                if constexpr (MODE == RCG_MODE_MPC) {
-                    Jc += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, a);
-                } else if constexpr (MODE == RCG_MODE_RQL) {
-                    if (!last) Jc += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, a);
-                    else Jc += critic<T, N, M, CS>(O, ob, a, wacc);
-                } else {
-                    Jc += critic<T, N, M, CS>(O, ob, a, wacc);
-                }
-                if (!last) {
-                    euler_step<T, SYS>(Sd, h, st, a, sn, cs);
-#pragma unroll
-                    for (int i = 0; i < N; ++i) ob[i] = st[i];
-                }
+            for (int i = 0; i < N; ++i) mem.X(k, i) = st[i];
+            mem.S(k) = sn;
+            mem.C(k) = cs;
+            const bool last = (k + 1 == na);
+            if constexpr (MODE == RCG_MODE_MPC) {
+                Jc += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, a);
+            } else if constexpr (MODE == RCG_MODE_RQL) {
+                if (!last) Jc += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, a);
+                else Jc += critic<T, N, M, CS>(O, ob, a, wacc);
+            } else {
+                Jc += critic<T, N, M, CS>(O, ob, a, wacc);
             }
-            return Jc;
-        };
-        // ---- reverse sweep: gradient of the last forward(which) into vector `gout` ----
-        auto backward = [&](int which, int gout) {
-            T lam[N];
+            if (!last) {
+                euler_step<T, SYS>(Sd, h, st, a, sn, cs);
 #pragma unroll
-            for (int i = 0; i < N; ++i) lam[i] = T(0);
+                for (int i = 0; i < N; ++i) ob[i] = st[i];
+            }
+        }
+        return Jc;
+    };
+    // ---- reverse sweep: gradient of the last forward(which) into vector `gout` ----
+    auto backward = [&](int which, int gout) {
+        T lam[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) lam[i] = T(0);
 #pragma unroll UK
-            for (int kk = 0; kk < na; ++kk) {
-                const int k = na - 1 - kk;
-                T a[M], xk[N], ob[N], ga[M], gobs[N], gact[M];
+        for (int kk = 0; kk < na; ++kk) {
+            const int k = na - 1 - kk;
+            T a[M], xk[N], ob[N], ga[M], gobs[N], gact[M];
 #pragma unroll
-                for (int j = 0; j < M; ++j) { a[j] = mem.v(which, k * M + j); ga[j] = T(0); }
+            for (int j = 0; j < M; ++j) { a[j] = mem.v(which, k * M + j); ga[j] = T(0); }
 #pragma unroll
-                for (int i = 0; i < N; ++i) { xk[i] = mem.X(k, i); ob[i] = (k == 0) ? ob0[i] : xk[i]; }
-                if (kk > 0) dyn_adjoint<T, SYS>(Sd, h, xk, a, mem.S(k), mem.C(k), lam, ga);
-                const bool use_critic = (MODE == RCG_MODE_SQL) || (MODE == RCG_MODE_RQL && kk == 0);
-                if (use_critic) {
-                    if constexpr (MODE != RCG_MODE_MPC) critic_grad<T, N, M, CS>(O, ob, a, wacc, gobs, gact);
-                } else {
-                    stage_obj_grad<T, N, M, RDIAG>(O, ob, a, O.gamma_pow[k], gobs, gact);
-                }
-#pragma unroll
-                for (int j = 0; j < M; ++j) mem.v(gout, k * M + j) = ga[j] + gact[j];
-                if (k > 0) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) lam[i] += gobs[i];
-                }
+            for (int i = 0; i < N; ++i) { xk[i] = mem.X(k, i); ob[i] = (k == 0) ? ob0[i] : xk[i]; }
+            if (kk > 0) dyn_adjoint<T, SYS>(Sd, h, xk, a, mem.S(k), mem.C(k), lam, ga);
+            const bool use_critic = (MODE == RCG_MODE_SQL) || (MODE == RCG_MODE_RQL && kk == 0);
+            if (use_critic) {
+                if constexpr (MODE != RCG_MODE_MPC) critic_grad<T, N, M, CS>(O, ob, a, wacc, gobs, gact);
+            } else {
+                stage_obj_grad<T, N, M, RDIAG>(O, ob, a, O.gamma_pow[k], gobs, gact);
             }
-        };
+#pragma unroll
+            for (int j = 0; j < M; ++j) mem.v(gout, k * M + j) = ga[j] + gact[j];
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) lam[i] += gobs[i];
+            }
+        }
+    };
 
-        // ---- solve(): projected L-BFGS, one pass of the loop = one trial point ----
-        // state machine: every pass evaluates the trial x_t (vector 3); the first pass accepts it unconditionally
-        T *col = sqn_g + tid;
-#pragma unroll UL
-        for (int i = 0; i < L; ++i) mem.v(3, i) = clip(col[(int64_t)i * nthreads], i);
-        bool first = true;
-        int npairs = 0, head = 0, stall = 0, bt = 0;
-        T lam_ls = T(1), gs = T(0), Jt;
 #pragma unroll 1
-        for (;;) {
-            Jt = forward(3);
-            if (!first) {
-                ++nfev;
-                if (!(Jt <= J + T(1e-4) * gs)) {                        // Armijo test failed: halve, or give up
-                    if (++bt >= kOptMaxBacktracks) break;
+    for (;;) {
+        if (need) {
+            // ---- next problem (environments with mask == 0 are skipped) ----
+#pragma unroll 1
+            for (;;) {
+                if (A.dynamic) p = (int64_t)atomicAdd(queue, 1ull);
+                else { p = taken ? nprob : col; taken = true; }
+                if (p >= nprob) { idle = true; break; }
+                e = p >> A.S_shift;
+                if (mask_g == nullptr || mask_g[e] != 0) break;
+            }
+            need = false;
+            if (!idle) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) { x0[i] = state_sys_g[i * E + e]; ob0[i] = obs_g[i * E + e]; }
+                if constexpr (MODE != RCG_MODE_MPC) {
+#pragma unroll
+                    for (int i = 0; i < DIMC; ++i) w[i] = A.w_per_env ? w_g[i * E + e] : w_g[i];
+                }
+                s0 = T(0);
+                c0 = T(1);
+                if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
+#pragma unroll UL
+                for (int i = 0; i < L; ++i) mem.v(3, i) = clip(sqn_g[(int64_t)i * nprob + p], i);
+                first = true;
+                npairs = 0; head = 0; stall = 0; bt = 0; iters = 0; nfev = 0;
+                lam_ls = T(1); gs = T(0); J = T(0);
+            }
+        }
+        if (__all_sync(0xffffffffu, idle)) break;
+        if (idle) continue;
+
+        // ---- one pass of the projected L-BFGS state machine: evaluate the trial point (vector 3) ----
+        bool finished = false;
+        const T Jt = forward(3);
+        bool accepted = true;
+        if (!first) {
+            ++nfev;
+            if (!(Jt <= J + T(1e-4) * gs)) {                            // Armijo test failed: halve, or give up
+                accepted = false;
+                if (++bt >= kOptMaxBacktracks) {
+                    finished = true;
+                } else {
                     lam_ls *= T(0.5);
                     gs = T(0);
 #pragma unroll UL
@@ -333,9 +363,10 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
                         mem.v(3, i) = xt;
                         gs += mem.v(1, i) * (xt - xi);
                     }
-                    continue;
                 }
             }
+        }
+        if (accepted) {
             backward(3, 4);
             bool stop = false;
             if (!first) {
@@ -355,8 +386,7 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
             }
             J = Jt;
             T pg = T(0);
-            uint64_t fr = 0;              // free-set bit mask (L <= 128: two words)
-            uint64_t fr_hi = 0;
+            uint64_t fr = 0, fr_hi = 0;   // free-set bit mask (L <= 128: two words)
 #pragma unroll UL
             for (int i = 0; i < L; ++i) {
                 const T xi = mem.v(3, i), gi = mem.v(4, i);
@@ -368,124 +398,145 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
                 pg = fmax(pg, fabs(clip(xi - gi, i) - xi));
             }
             first = false;
-            if (A.grad_only || stop || !(pg > A.pg_tol) || iters >= A.max_iter) break;
-            auto is_free = [&](int i) { return ((i < 64 ? (fr >> i) : (fr_hi >> (i - 64))) & 1ull) != 0; };
-            // two-loop recursion on the free set: d <- H g_F
+            if (A.grad_only || stop || !(pg > A.pg_tol) || iters >= A.max_iter) {
+                finished = true;
+            } else {
+                auto is_free = [&](int i) { return ((i < 64 ? (fr >> i) : (fr_hi >> (i - 64))) & 1ull) != 0; };
+                // two-loop recursion on the free set: d <- H g_F
 #pragma unroll UL
-            for (int i = 0; i < L; ++i) mem.v(2, i) = is_free(i) ? mem.v(1, i) : T(0);
-            T scale = step0 / pg;
-            bool have_scale = false;
-            T al[kOptMem], sy[kOptMem];
-            // the pair loops stay rolled (al/sy are indexed dynamically): unrolled, the kernel outgrows the
-            // instruction cache (ncu: stall_no_instruction was the top stall reason)
+                for (int i = 0; i < L; ++i) mem.v(2, i) = is_free(i) ? mem.v(1, i) : T(0);
+                T scale = step0 / pg;
+                bool have_scale = false;
+                T al[kOptMem], sy[kOptMem];
+                // the pair loops stay rolled (al/sy are indexed dynamically): unrolled, the kernel outgrows the
+                // instruction cache (ncu: stall_no_instruction was the top stall reason)
 #pragma unroll 1
-            for (int j = 0; j < npairs; ++j) {
-                int slot = head - 1 - j;
-                slot += (slot < 0) ? kOptMem : 0;
-                const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
-                T a = T(0), ss = T(0), yy = T(0), sq = T(0);
+                for (int j = 0; j < npairs; ++j) {
+                    int slot = head - 1 - j;
+                    slot += (slot < 0) ? kOptMem : 0;
+                    const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
+                    T a = T(0), ss = T(0), yy = T(0), sq = T(0);
 #pragma unroll UL
-                for (int i = 0; i < L; ++i) {
-                    const T si = sp[(int64_t)i * nthreads], yi = yp[(int64_t)i * nthreads];
-                    if (is_free(i)) { a += si * yi; ss += si * si; yy += yi * yi; sq += si * mem.v(2, i); }
+                    for (int i = 0; i < L; ++i) {
+                        const T si = sp[(int64_t)i * TR], yi = yp[(int64_t)i * TR];
+                        if (is_free(i)) { a += si * yi; ss += si * si; yy += yi * yi; sq += si * mem.v(2, i); }
+                    }
+                    al[j] = T(0);
+                    sy[j] = T(0);
+                    if (a > T(1e-10) * sqrt(ss * yy)) {
+                        sy[j] = a;
+                        al[j] = sq / a;
+                        const T alj = al[j];
+#pragma unroll UL
+                        for (int i = 0; i < L; ++i)
+                            if (is_free(i)) mem.v(2, i) -= alj * yp[(int64_t)i * TR];
+                        if (!have_scale) { scale = a / yy; have_scale = true; }
+                    }
                 }
-                al[j] = T(0);
-                sy[j] = T(0);
-                if (a > T(1e-10) * sqrt(ss * yy)) {
-                    sy[j] = a;
-                    al[j] = sq / a;
-                    const T alj = al[j];
+#pragma unroll UL
+                for (int i = 0; i < L; ++i) mem.v(2, i) *= scale;
+#pragma unroll 1
+                for (int j = npairs - 1; j >= 0; --j) {
+                    if (!(sy[j] > T(0))) continue;
+                    int slot = head - 1 - j;
+                    slot += (slot < 0) ? kOptMem : 0;
+                    const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
+                    T yr = T(0);
 #pragma unroll UL
                     for (int i = 0; i < L; ++i)
-                        if (is_free(i)) mem.v(2, i) -= alj * yp[(int64_t)i * nthreads];
-                    if (!have_scale) { scale = a / yy; have_scale = true; }
+                        if (is_free(i)) yr += yp[(int64_t)i * TR] * mem.v(2, i);
+                    const T c = al[j] - yr / sy[j];
+#pragma unroll UL
+                    for (int i = 0; i < L; ++i)
+                        if (is_free(i)) mem.v(2, i) += c * sp[(int64_t)i * TR];
+                }
+                T gd = T(0);
+#pragma unroll UL
+                for (int i = 0; i < L; ++i) {
+                    const T di = -mem.v(2, i);
+                    mem.v(2, i) = di;
+                    gd += mem.v(1, i) * di;
+                }
+                if (!(gd < T(0)) || !isfinite(gd)) {                      // not a descent direction: restart
+                    npairs = 0;
+#pragma unroll UL
+                    for (int i = 0; i < L; ++i) mem.v(2, i) = is_free(i) ? -mem.v(1, i) * (step0 / pg) : T(0);
+                }
+                lam_ls = T(1);
+                bt = 0;
+                gs = T(0);
+#pragma unroll UL
+                for (int i = 0; i < L; ++i) {
+                    const T xi = mem.v(0, i);
+                    const T xt = clip(xi + mem.v(2, i), i);
+                    mem.v(3, i) = xt;
+                    gs += mem.v(1, i) * (xt - xi);
                 }
             }
-#pragma unroll UL
-            for (int i = 0; i < L; ++i) mem.v(2, i) *= scale;
-#pragma unroll 1
-            for (int j = npairs - 1; j >= 0; --j) {
-                if (!(sy[j] > T(0))) continue;
-                int slot = head - 1 - j;
-                slot += (slot < 0) ? kOptMem : 0;
-                const T *sp = &Sp(slot, 0), *yp = &Yp(slot, 0);
-                T yr = T(0);
-#pragma unroll UL
-                for (int i = 0; i < L; ++i)
-                    if (is_free(i)) yr += yp[(int64_t)i * nthreads] * mem.v(2, i);
-                const T c = al[j] - yr / sy[j];
-#pragma unroll UL
-                for (int i = 0; i < L; ++i)
-                    if (is_free(i)) mem.v(2, i) += c * sp[(int64_t)i * nthreads];
-            }
-            T gd = T(0);
-#pragma unroll UL
-            for (int i = 0; i < L; ++i) {
-                const T di = -mem.v(2, i);
-                mem.v(2, i) = di;
-                gd += mem.v(1, i) * di;
-            }
-            if (!(gd < T(0)) || !isfinite(gd)) {                          // not a descent direction: restart
-                npairs = 0;
-#pragma unroll UL
-                for (int i = 0; i < L; ++i) mem.v(2, i) = is_free(i) ? -mem.v(1, i) * (step0 / pg) : T(0);
-            }
-            lam_ls = T(1);
-            bt = 0;
-            gs = T(0);
-#pragma unroll UL
-            for (int i = 0; i < L; ++i) {
-                const T xi = mem.v(0, i);
-                const T xt = clip(xi + mem.v(2, i), i);
-                mem.v(3, i) = xt;
-                gs += mem.v(1, i) * (xt - xi);
-            }
         }
-        // vector 0 = the minimiser (monotone: last accepted iterate), vector 1 its gradient
-        if (!A.grad_only) {
+        if (finished) {
+            // vector 0 = the minimiser (monotone: last accepted iterate), vector 1 its gradient, J its cost
+            if (!A.grad_only) {
 #pragma unroll UL
-            for (int i = 0; i < L; ++i) col[(int64_t)i * nthreads] = mem.v(0, i);
-        } else if (grad_g) {
+                for (int i = 0; i < L; ++i) sqn_g[(int64_t)i * nprob + p] = mem.v(0, i);
+                Jscr[p] = J;
+            } else if (grad_g) {
 #pragma unroll UL
-            for (int i = 0; i < L; ++i) grad_g[(int64_t)i * nthreads + tid] = mem.v(1, i);
-        }
+                for (int i = 0; i < L; ++i) grad_g[(int64_t)i * nprob + p] = mem.v(1, i);
+            }
+            if (J_g) J_g[p] = J;
+            if (iters_g) iters_g[p] = iters;
+            if (nfev_g) nfev_g[p] = nfev;
+            if (!A.grad_only && A.S == 1) {
+                // _actor_optimizer returns action_sqn[:dim_input] (:1427); upd_accum_obj of the sampling step (:1093)
+                if (best_g) best_g[e] = 0;
+                if (Jmin_g) Jmin_g[e] = J;
+                T act[M];
 #pragma unroll
-        for (int j = 0; j < M; ++j) a_first[j] = mem.v(0, j);
-        if (J_g) J_g[tid] = J;
-        if (iters_g) iters_g[tid] = iters;
-        if (nfev_g) nfev_g[tid] = nfev;
+                for (int j = 0; j < M; ++j) act[j] = mem.v(0, j);
+                if (action_g) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
+                }
+                if (accum_g) accum_g[e] += stage_obj<T, N, M, RDIAG, RDIAG>(O, ob0, act) * sampling_time;
+            }
+            need = true;
+        }
     }
-    if (A.grad_only) return;
+}
 
-    // ---- best start per environment (np.argmin order over the S starts), action hand-over ----
-    T bestJ = J;
-    int bestI = active ? sidx : kNone;
-    for (int off = A.S >> 1; off > 0; off >>= 1) {
-        const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
-        const int oI = __shfl_xor_sync(0xffffffffu, bestI, off);
-        if (oI != kNone && (bestI == kNone || argmin_better(oJ, oI, bestJ, bestI))) { bestJ = oJ; bestI = oI; }
+// S > 1: best start per environment (np.argmin order over the final costs), action hand-over, upd_accum_obj.
+template <typename T, int SYS, bool RDIAG>
+__global__ void __launch_bounds__(256)
+actor_opt_select_kernel(const __grid_constant__ ObjDev<T> O, int64_t E, int S, const T *__restrict__ obs_g,
+                        const T *__restrict__ sqn_g, const T *__restrict__ Jscr, const int32_t *__restrict__ mask_g,
+                        int32_t *__restrict__ best_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
+                        T *__restrict__ accum_g, T sampling_time)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E || (mask_g && mask_g[e] == 0)) return;
+    const int64_t nprob = E * S;
+    T bestJ = Jscr[e * S];
+    int bestI = 0;
+    for (int s = 1; s < S; ++s) {
+        const T Js = Jscr[e * S + s];
+        if (argmin_better(Js, s, bestJ, bestI)) { bestJ = Js; bestI = s; }
     }
-    // _actor_optimizer returns action_sqn[:dim_input] (:1427): fetch it from the winning lane
-    T act[M];
-    {
-        const int src = ((threadIdx.x & 31) & ~(A.S - 1)) + ((bestI == kNone) ? 0 : bestI);
+    if (best_g) best_g[e] = bestI;
+    if (Jmin_g) Jmin_g[e] = bestJ;
+    if (action_g || accum_g) {
+        T act[M], ob[N];
 #pragma unroll
-        for (int j = 0; j < M; ++j) act[j] = __shfl_sync(0xffffffffu, a_first[j], src);
-    }
-    if (active && sidx == 0 && bestI != kNone) {
-        if (best_g) best_g[e] = bestI;
-        if (Jmin_g) Jmin_g[e] = bestJ;
-        if (action_g || accum_g) {
-            T ob[N];
-            if (action_g) {
+        for (int j = 0; j < M; ++j) act[j] = sqn_g[(int64_t)j * nprob + e * S + bestI];
+        if (action_g) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
-            }
-            if (accum_g) {
+            for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
+        }
+        if (accum_g) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) ob[i] = obs_g[i * E + e];
-                accum_g[e] += stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, act) * sampling_time;
-            }
+            for (int i = 0; i < N; ++i) ob[i] = obs_g[i * E + e];
+            accum_g[e] += stage_obj<T, N, M, RDIAG, RDIAG>(O, ob, act) * sampling_time;
         }
     }
 }
@@ -505,6 +556,7 @@ struct OptLaunch {
     bool rdiag;
     int mode, cs;
     unsigned grid;
+    int sms;
     cudaStream_t stream;
 };
 
@@ -514,9 +566,22 @@ __host__ inline bool opt_horizon_specialised(int na) { return na == 3 || na == 5
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
 static void launch_opt_one(const OptLaunch<T> &L)
 {
-    actor_opt_kernel<T, SYS, MODE, CS, RDIAG, NA><<<L.grid, kOptThreads, 0, L.stream>>>(
-        L.S, L.O, L.A, L.state_sys, L.obs, L.sqn, L.w, L.mask, L.ws, L.J, L.grad, L.iters, L.nfev, L.best, L.Jmin,
-        L.action, L.accum, L.sampling_time);
+    auto kern = actor_opt_kernel<T, SYS, MODE, CS, RDIAG, NA>;
+    unsigned grid = L.grid;                                  // one thread per problem ...
+    if (L.A.dynamic) {                                       // ... or a persistent grid pulling from the work queue
+        static int occ = 0;                                  // per instantiation
+        if (occ == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOptThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+        }
+        const unsigned resident = (unsigned)(L.sms * occ);
+        if (grid > resident) grid = resident;
+    }
+    kern<<<grid, kOptThreads, 0, L.stream>>>(L.S, L.O, L.A, L.state_sys, L.obs, L.sqn, L.w, L.mask, L.ws, L.J, L.grad, L.iters,
+                                             L.nfev, L.best, L.Jmin, L.action, L.accum, L.sampling_time);
+    if (L.A.dynamic && L.A.S > 1 && (L.best || L.Jmin || L.action || L.accum)) {
+        actor_opt_select_kernel<T, SYS, RDIAG><<<(unsigned)((L.A.E + 255) / 256), 256, 0, L.stream>>>(
+            L.O, L.A.E, L.A.S, L.obs, L.sqn, L.ws + kOptWsHeader, L.mask, L.best, L.Jmin, L.action, L.accum, L.sampling_time);
+    }
 }
 
 template <typename T, int SYS, int MODE, int CS>

@@ -124,6 +124,39 @@ def run_config(name, a):
     print(json.dumps(r), flush=True)
 
 
+def run_config2_actors(a):
+    """BASELINE config 2 (3wrobot_NI MPC Nactor=6, 65,536 envs x 256 per-environment candidates) with the three
+    stand-ins for _actor_optimizer: arg-min over the candidates, the batched minimiser warm-started from the arg-min
+    candidate, and the minimiser started from action_sqn_init like the reference.  Same initial states; reports
+    time per control interval and the mean accumulated objective (closed-loop quality) at t1."""
+    from bench_workload import synthetic_candidates as sc
+    E = (a.envs + 1023) // 1024 * 1024
+    bn = [[-25.0, 25.0], [-5.0, 5.0]]
+    x0 = synthetic_states("3wrobotNI", 0, E, seed=0)
+    cand = torch.as_tensor(sc(bn, 6, a.cands, seed=1, env_range=(0, E)), device="cuda")
+    for tag, kw in (("candidates", dict(actor="candidates")), ("opt_argmin", dict(actor="opt", opt_start="argmin")),
+                    ("opt_init", dict(actor="opt", opt_start="init"))):
+        eng = ClosedLoopEngine("3wrobotNI", x0, cand, ctrl_bnds=bn, mode="MPC", Nactor=6, dt=0.01, t1=a.t1,
+                               R1=[1, 10, 1, 0, 0], **kw)
+        for _ in range(3):
+            eng.run_interval()
+        torch.cuda.synchronize()
+        s0 = int(eng.nsamples.sum().item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k = eng.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        res = eng.results()
+        samples = int(eng.nsamples.sum().item()) - s0
+        print(json.dumps(dict(config="config2", actor=tag, E=E, C=a.cands, t1=a.t1, intervals=k, ms_per_interval=ms / max(k, 1),
+                              controller_samples_per_s=samples / ms * 1e3, mean_return=float(res["accum"].mean()),
+                              median_return=float(np.median(res["accum"])),
+                              mean_final_distance=float(np.sqrt((res["y"][:, :2] ** 2).sum(1)).mean()))), flush=True)
+        del eng
+
+
 def pct(x):
     x = np.asarray(x, dtype=np.float64)
     return {"p50": float(np.percentile(x, 50)), "p99": float(np.percentile(x, 99)), "max": float(x.max())}
@@ -170,13 +203,16 @@ def run_fp32_report(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["config3", "config4", "fp32"])
+    ap.add_argument("what", choices=["config2", "config3", "config4", "fp32"])
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--cands", type=int, default=256)
     ap.add_argument("--t1", type=float, default=0.0)
     ap.add_argument("--fit-evals", type=int, default=0, help="work bound of the critic fit per environment (0 = to convergence)")
     a = ap.parse_args()
-    if a.what == "config3":
+    if a.what == "config2":
+        a.envs, a.t1 = a.envs or 65536, a.t1 or 2.0
+        run_config2_actors(a)
+    elif a.what == "config3":
         a.envs, a.t1 = a.envs or 1 << 20, a.t1 or 0.3
         run_config("config3", a)
     elif a.what == "config4":
