@@ -186,6 +186,8 @@ struct OptArgs {
 // between problems (measured before this change: mean 17, p99 27, max 95 iterations near the goal -- every warp waited
 // for its slowest lane).  The body is a state machine -- one pass = one trial point: forward sweep, then either a
 // backtracking step or (accepted) the reverse sweep, the quasi-Newton update and the next trial point.
+// No residency target: holding the kernel to 3 or 4 blocks per SM (168 / 128 registers, 0.3-0.8 KB of spills) was
+// measured 2x SLOWER for 3wrobot_NI N=6 (1.56 -> 3.4 ms per 65,536 solves) and only 8 % faster for 3wrobot N=10.
 template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
 __global__ void __launch_bounds__(kOptThreads)
 actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ ObjDev<T> O,
