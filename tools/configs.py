@@ -134,8 +134,13 @@ def run_config2_actors(a):
     bn = [[-25.0, 25.0], [-5.0, 5.0]]
     x0 = synthetic_states("3wrobotNI", 0, E, seed=0)
     cand = torch.as_tensor(sc(bn, 6, a.cands, seed=1, env_range=(0, E)), device="cuda")
-    for tag, kw in (("candidates", dict(actor="candidates")), ("opt_argmin", dict(actor="opt", opt_start="argmin")),
-                    ("opt_init", dict(actor="opt", opt_start="init"))):
+    variants = [("candidates", dict(actor="candidates")), ("opt_argmin", dict(actor="opt", opt_start="argmin")),
+                ("opt_init", dict(actor="opt", opt_start="init"))]
+    if a.opt_sweep:          # stopping-rule sweep of the minimiser (pg_tol, f_tol, iteration cap)
+        variants = [(f"opt_init pg={pg:g} f={ft:g} it={it}", dict(actor="opt", opt_start="init", opt_pg_tol=pg, opt_f_tol=ft, opt_iters=it))
+                    for pg, ft, it in ((1e-7, 1e-12, 300), (1e-6, 1e-10, 300), (1e-5, 1e-9, 300), (1e-4, 1e-8, 300),
+                                       (1e-3, 1e-7, 300), (1e-7, 1e-12, 20), (1e-7, 1e-12, 10), (1e-5, 1e-9, 20))]
+    for tag, kw in variants:
         eng = ClosedLoopEngine("3wrobotNI", x0, cand, ctrl_bnds=bn, mode="MPC", Nactor=6, dt=0.01, t1=a.t1,
                                R1=[1, 10, 1, 0, 0], **kw)
         for _ in range(3):
@@ -207,6 +212,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--cands", type=int, default=256)
     ap.add_argument("--t1", type=float, default=0.0)
+    ap.add_argument("--opt-sweep", action="store_true", help="config2: sweep the minimiser's stopping rule")
     ap.add_argument("--fit-evals", type=int, default=0, help="work bound of the critic fit per environment (0 = to convergence)")
     a = ap.parse_args()
     if a.what == "config2":
