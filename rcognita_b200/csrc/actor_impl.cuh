@@ -49,6 +49,20 @@ __device__ __forceinline__ void sincos_small(double x, double *s, double *c)
     *s = fma(x * z, ps, x);
     *c = fma(z * z, pc, fma(z, -0.5, 1.0));
 }
+// |x| <= 1/8 (the predictor's heading increment h * omega: 0.05 rad at the presets' bounds): the two highest-order
+// terms of each polynomial are below 2^-70 relative and are dropped -- 4 of the 16 FP64 instructions of a rotation.
+__device__ __forceinline__ void sincos_tiny(double x, double *s, double *c)
+{
+    const double z = x * x;
+    double ps = kSinC[2], pc = kCosC[2];
+#pragma unroll
+    for (int i = 3; i < 6; ++i) {
+        ps = fma(ps, z, kSinC[i]);
+        pc = fma(pc, z, kCosC[i]);
+    }
+    *s = fma(x * z, ps, x);
+    *c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
 
 static __device__ __noinline__ double2 sincos_full(double x)
 {
@@ -58,11 +72,15 @@ static __device__ __noinline__ double2 sincos_full(double x)
 }
 
 // (s, c) = (sin, cos)(theta_old) on entry; (sin, cos)(theta_new) on exit, theta_new = theta_old + delta.
+// TINY: try the truncated polynomials first (measured: 0.309 -> 0.304 ms on the NI headline launch; for 3wrobot the
+// extra path costs registers under its 128-register cap and was slower, 2.64 -> 2.88 ms, so it is NI-only).
+template <bool TINY = false>
 __device__ __forceinline__ void rotate_trig(double theta_new, double delta, double &s, double &c)
 {
     if (fabs(delta) <= 0.78539816339744830962) {
         double sd, cd;
-        sincos_small(delta, &sd, &cd);
+        if (TINY && fabs(delta) <= 0.125) sincos_tiny(delta, &sd, &cd);
+        else sincos_small(delta, &sd, &cd);
         const double cn = fma(c, cd, -(s * sd));
         const double sn = fma(s, cd, c * sd);
         s = sn;
@@ -76,6 +94,7 @@ __device__ __forceinline__ void rotate_trig(double theta_new, double delta, doub
 // fp32 twin: same rotation with single-precision minimax kernels (Cephes sinf/cosf coefficients,
 // < 1 ulp on [-pi/4, pi/4]); the accumulated rotation error (~1e-7 per stage) is inside the fp32
 // tolerance of the path (tests: 2e-5 relative on costs).
+template <bool TINY = false>
 __device__ __forceinline__ void rotate_trig(float theta_new, float delta, float &s, float &c)
 {
     if (fabsf(delta) <= 0.78539816f) {
@@ -102,7 +121,7 @@ __device__ __forceinline__ void euler_step(const SysDev<T> &S, T h, T *x, const 
         x[0] = x[0] + h * (a[0] * c);
         x[1] = x[1] + h * (a[0] * s);
         x[2] = x[2] + d;
-        rotate_trig(x[2], d, s, c);
+        rotate_trig<true>(x[2], d, s, c);
     } else if constexpr (SYS == RCG_SYS_3WROBOT) {       // systems.py:308-323
         const T d = h * x[4];
         x[0] = x[0] + h * (x[3] * c);
@@ -110,7 +129,7 @@ __device__ __forceinline__ void euler_step(const SysDev<T> &S, T h, T *x, const 
         x[2] = x[2] + d;
         x[3] = x[3] + h * ((T(1) / S.pars[0]) * a[0]);
         x[4] = x[4] + h * ((T(1) / S.pars[1]) * a[1]);
-        rotate_trig(x[2], d, s, c);
+        rotate_trig<false>(x[2], d, s, c);
     } else {                                             // systems.py:412-419
         T d[2];
         state_dyn<T, SYS>(S, x, a, d);
