@@ -66,6 +66,10 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     L.O = make_obj_dev<T>(obj, n, m);
     // fast kernels: diagonal R1 and the 'quadratic' structure (every preset); otherwise the general ones
     L.rdiag = obj->r_is_diag && is_diag(obj->R1, n + m) && obj->stage_struct == RCG_STAGE_QUADRATIC;
+    // lean objective (every robot preset): no target, gamma = 1, zero weight on the action entries of diagonal R1
+    L.lean = L.rdiag && !obj->has_target && getenv("RCG_ACTOR_NO_LEAN") == nullptr;
+    for (int k = 0; k < obj->Nactor && L.lean; ++k) L.lean = (obj->gamma_pow[k] == 1.0);
+    for (int j = n; j < n + m && L.lean; ++j) L.lean = (obj->R1[j * (n + m) + j] == 0.0);
     int seg = 32, shift = 5;
     while (shift > 0 && (seg >> 1) >= C) { seg >>= 1; --shift; }      // smallest power of two >= C, capped at 32
     const int epw = 32 / seg;

@@ -21,6 +21,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <math_constants.h>
 
 #include "rcg_host.h"
 
@@ -148,7 +149,17 @@ struct RegW {
 // preset); the general kernels (RDIAG = false) take dense R1/R2 and branch on the structure.
 // ActorEval holds the running state of one _actor_cost evaluation (rollout state, cached heading
 // trigonometry, accumulated cost); stage(k) adds the cost of stage k and advances the predictor.
-template <typename T, int SYS, int MODE, int CS, bool RDIAG>
+// Non-finite test on the integer pipe (the FP64 pipe is the busy one): exponent bits all ones.
+__device__ __forceinline__ int nonfinite_bits(double v) { return ((__double2hiint(v) & 0x7ff00000) == 0x7ff00000) ? 1 : 0; }
+__device__ __forceinline__ int nonfinite_bits(float v) { return ((__float_as_int(v) & 0x7f800000) == 0x7f800000) ? 1 : 0; }
+
+// LEAN = the presets' objective shape, decided on the host: diagonal R1 whose ACTION entries are zero, no
+// observation_target, gamma = 1.  Then  gamma**k * ((chi - 0) R chi)  reduces to the n observation terms: the target
+// subtraction, the two zero-weight action terms and the multiplication by 1 are exact no-ops for finite inputs and
+// are dropped -- 9 of the ~40 FP64 instructions of a 3wrobot_NI stage (the TMA kernel is co-limited by FP64 issue).
+// The one thing 0 * a * a does for the reference is to turn a non-finite action into a NaN cost; the lean kernels
+// keep that with an integer-pipe test on the loaded actions (`bad`), so results are identical bit for bit.
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, bool LEAN = false>
 struct ActorEval {
     static constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
     static constexpr int DIMC = dim_critic_c(CS, N, M);
@@ -166,13 +177,27 @@ struct ActorEval {
         for (int i = 0; i < N; ++i) { state[i] = x0[i]; obs[i] = ob0[i]; }    // controllers.py:1290-1291
     }
 
+    __device__ __forceinline__ T stage_obj_lean(const T *ob) const
+    {
+        constexpr int P = N + M;
+        T out = T(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) out += (ob[i] * O.R1[i * P + i]) * ob[i];
+        return out;
+    }
+
     __device__ __forceinline__ void stage(int k, bool last, const T *a)
     {
         if constexpr (MODE == RCG_MODE_MPC) {
-            J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);          // :1305-1306
+            if constexpr (LEAN) J += stage_obj_lean(obs);
+            else J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);     // :1305-1306
         } else if constexpr (MODE == RCG_MODE_RQL) {
-            if (!last) J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a);   // :1308-1309
-            else J += critic<T, N, M, CS>(O, obs, a, w);                                // :1310
+            if (!last) {
+                if constexpr (LEAN) J += stage_obj_lean(obs);
+                else J += O.gamma_pow[k] * stage_obj<T, N, M, RDIAG, RDIAG>(O, obs, a); // :1308-1309
+            } else {
+                J += critic<T, N, M, CS>(O, obs, a, w);                                 // :1310
+            }
         } else {
             J += critic<T, N, M, CS>(O, obs, a, w);                                     // :1312-1326
         }
@@ -186,20 +211,27 @@ struct ActorEval {
 
 // One _actor_cost evaluation.  `cp` points at component 0 of this lane's candidate, `ld` is the
 // distance between consecutive components.  NA > 0: compile-time horizon, fully unrolled.
-template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA, bool LEAN = false>
 __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T> &O, const T *x0, const T *ob0, T s0,
                                              T c0, const T *__restrict__ cp, int64_t ld, const T *w_r)
 {
     constexpr int M = SysDim<SYS>::m;
-    ActorEval<T, SYS, MODE, CS, RDIAG> ev(S, O, x0, ob0, s0, c0, w_r);
+    ActorEval<T, SYS, MODE, CS, RDIAG, LEAN> ev(S, O, x0, ob0, s0, c0, w_r);
     if constexpr (NA > 0) {
         T a[NA][M];
+        int bad = 0;
 #pragma unroll
         for (int k = 0; k < NA; ++k)
 #pragma unroll
-            for (int j = 0; j < M; ++j) a[k][j] = __ldg(cp + (int64_t)(k * M + j) * ld);
+            for (int j = 0; j < M; ++j) {
+                a[k][j] = __ldg(cp + (int64_t)(k * M + j) * ld);
+                if constexpr (LEAN) bad |= nonfinite_bits(a[k][j]);
+            }
 #pragma unroll
         for (int k = 0; k < NA; ++k) ev.stage(k, k + 1 == NA, a[k]);
+        if constexpr (LEAN) {
+            if (bad) ev.J = (T)CUDART_NAN;                               // 0 * non-finite action = NaN in the reference
+        }
     } else {
         // runtime horizon: chunks of CH stages, the next chunk's actions are in flight while the
         // current chunk is evaluated
@@ -244,7 +276,7 @@ __host__ __device__ constexpr int actor_min_blocks(int sys, int na, bool rdiag)
     return (na > 0 && rdiag) ? (sys == RCG_SYS_3WROBOT_NI ? 3 : sys == RCG_SYS_3WROBOT ? 2 : 4) : 1;
 }
 
-template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA, bool LEAN = false>
 __global__ void __launch_bounds__(kActorThreads, actor_min_blocks(SYS, NA, RDIAG))
 actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ ObjDev<T> O,
                   const __grid_constant__ ActorArgs A, const T *__restrict__ state_sys_g, const T *__restrict__ obs_g,
@@ -281,7 +313,7 @@ actor_cost_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ O
             if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
             const T *cbase = cand_g + (A.cand_per_env ? e * (int64_t)C : 0);
             for (int c = cl; c < C; c += seg) {
-                const T J = actor_cost_lane<T, SYS, MODE, CS, RDIAG, NA>(S, O, x0, ob, s0, c0, cbase + c, ld, w);
+                const T J = actor_cost_lane<T, SYS, MODE, CS, RDIAG, NA, LEAN>(S, O, x0, ob, s0, c0, cbase + c, ld, w);
                 if (J_g) J_g[e * (int64_t)C + c] = J;
                 if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
             }
@@ -370,7 +402,7 @@ __host__ __device__ constexpr int tma_smem_bytes() { return kActorWarps * tma_st
 template <typename T, int L>
 __host__ __device__ constexpr int tma_min_ctas() { return (225 * 1024 / (tma_smem_bytes<T, L>() + 1024)) >= 3 ? 3 : 2; }
 
-template <typename T, int SYS, int MODE, int CS, int NA>
+template <typename T, int SYS, int MODE, int CS, int NA, bool LEAN = false>
 __global__ void __launch_bounds__(kActorThreads, tma_min_ctas<T, NA * SysDim<SYS>::m>())
 actor_cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SysDev<T> S,
                       const __grid_constant__ ObjDev<T> O, const __grid_constant__ ActorArgs A,
@@ -464,20 +496,24 @@ actor_cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             const int c = cl + ci * seg;
             const bool valid = active && c < C;
             T a[NA][M];
+            int bad = 0;
             {
                 const T *src = ring + (size_t)stage * BOX + lane;
 #pragma unroll
                 for (int k = 0; k < NA; ++k)
 #pragma unroll
-                    for (int j = 0; j < M; ++j) a[k][j] = src[(k * M + j) * 32];
+                    for (int j = 0; j < M; ++j) {
+                        a[k][j] = src[(k * M + j) * 32];
+                        if constexpr (LEAN) bad |= nonfinite_bits(a[k][j]);
+                    }
             }
             __syncwarp();                                          // every lane has copied its column out
             if (lane == 0) issue(stage);                           // refill the slot
             if (valid) {
-                ActorEval<T, SYS, MODE, CS, true> ev(S, O, x0, ob, s0, c0, w);
+                ActorEval<T, SYS, MODE, CS, true, LEAN> ev(S, O, x0, ob, s0, c0, w);
 #pragma unroll
                 for (int k = 0; k < NA; ++k) ev.stage(k, k + 1 == NA, a[k]);
-                const T J = ev.J;
+                const T J = (LEAN && bad) ? (T)CUDART_NAN : ev.J;
                 if (J_g) J_g[e * (int64_t)C + c] = J;
                 if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
             }
@@ -518,6 +554,7 @@ struct ActorLaunch {
     T *Jmin, *action, *accum;
     T sampling_time;
     bool rdiag;
+    bool lean;                 // diagonal R1 with zero action entries, no target, gamma = 1 (ActorEval LEAN)
     int mode, cs;
     unsigned grid;
     int sms;
@@ -527,13 +564,13 @@ struct ActorLaunch {
     cudaStream_t stream;
 };
 
-template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA>
+template <typename T, int SYS, int MODE, int CS, bool RDIAG, int NA, bool LEAN = false>
 static void launch_actor_one(const ActorLaunch<T> &L)
 {
     if constexpr (RDIAG && NA > 0) {
         if (L.use_tma) {
             constexpr int LL = NA * SysDim<SYS>::m;
-            auto kern = actor_cost_tma_kernel<T, SYS, MODE, CS, NA>;
+            auto kern = actor_cost_tma_kernel<T, SYS, MODE, CS, NA, LEAN>;
             const size_t smem = (size_t)tma_smem_bytes<T, LL>();
             static bool configured = false;                   // per instantiation
             if (!configured) {
@@ -547,7 +584,7 @@ static void launch_actor_one(const ActorLaunch<T> &L)
             return;
         }
     }
-    actor_cost_kernel<T, SYS, MODE, CS, RDIAG, NA><<<L.grid, kActorThreads, 0, L.stream>>>(
+    actor_cost_kernel<T, SYS, MODE, CS, RDIAG, NA, LEAN><<<L.grid, kActorThreads, 0, L.stream>>>(
         L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J, L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
 }
 
@@ -557,6 +594,18 @@ template <typename T, int SYS, int MODE, int CS>
 static void launch_actor_mc(const ActorLaunch<T> &L)
 {
     if (!L.rdiag) { launch_actor_one<T, SYS, MODE, CS, false, 0>(L); return; }
+    if constexpr (MODE != RCG_MODE_SQL) {            // SQL has no stage_obj term: nothing to lean out
+        if (L.lean) {
+            switch (L.O.Nactor) {
+            case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3, true>(L); return;
+            case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5, true>(L); return;
+            case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6, true>(L); return;
+            case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8, true>(L); return;
+            case 10: launch_actor_one<T, SYS, MODE, CS, true, 10, true>(L); return;
+            default: break;
+            }
+        }
+    }
     switch (L.O.Nactor) {
     case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3>(L); return;
     case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5>(L); return;

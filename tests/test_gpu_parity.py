@@ -304,6 +304,20 @@ def test_argmin_ties_and_nan(rb):
     cand3[401, 2] = np.nan
     J, am, Jmin = ops.actor_cost(sysd, obj, x, x, dev(cand3.T.copy()), False, C_)
     assert int(am[0]) == 401 and np.isnan(Jmin[0].item())
+    # a non-finite value in the LAST action never enters the dynamics and carries zero weight, yet the reference's
+    # 0 * a * a makes the cost NaN: the lean kernels (zero action weights dropped) must keep that, per-env candidates too
+    s = oracle.make_sys("3wrobotNI", p["pars"], p["bnds"])
+    ct = oracle.make_ctrl(3, 2, mode="MPC", Nactor=N, pred_step_size=0.01, R1=p["R1_diag"])
+    for bad in (np.nan, np.inf, -np.inf):
+        cand4 = cand2[:640].copy()
+        cand4[77, -1] = bad
+        cand4[500, -2] = bad
+        assert np.isnan(oracle.actor_cost(ct, s, cand4[77], X0["3wrobotNI"], X0["3wrobotNI"]))
+        for per_env in (False, True):
+            J, am, Jmin = ops.actor_cost(sysd, obj, x, x, dev(cand4.T.copy()), per_env, 640)
+            Jh = J.cpu().numpy()[0]
+            assert np.isnan(Jh[77]) and np.isnan(Jh[500]) and np.isfinite(np.delete(Jh, [77, 500])).all()
+            assert int(am[0]) == 77 and np.isnan(Jmin[0].item())
 
 
 @pytest.mark.parametrize("name", SYSTEMS)
