@@ -55,8 +55,11 @@ def actor_point(system, mode, cs, N, E, C, per_env, dtype=torch.float64, iters=1
     am = torch.empty((E,), device="cuda", dtype=torch.int32)
     jm = torch.empty((E,), device="cuda", dtype=dtype)
     act = torch.empty((m, E), device="cuda", dtype=dtype)
+    inloop = bool(os.environ.get("RCG_KB_INLOOP"))          # the in-loop call shape: sampling mask + upd_accum_obj epilogue
+    mask = torch.ones((E,), device="cuda", dtype=torch.int32) if inloop else None
+    accum = torch.zeros((E,), device="cuda", dtype=dtype) if inloop else None
     fn = lambda: ops.actor_cost(sysd, obj, x, x, cand, per_env, C, w_critic=w, want_J=False, argmin_out=am, Jmin_out=jm,
-                                action_out=act)
+                                action_out=act, mask=mask, accum=accum, sampling_time=0.01)
     ms = time_it(fn, iters)
     evals = E * C
     bytes_eval = (N * m * cand.element_size() + cand.element_size()) if per_env else cand.element_size()
