@@ -205,7 +205,11 @@ int rcg_actor_cost_f32(const rcg_system_t *sys, const rcg_objective_t *obj, int6
  * quasi-Newton iteration inside the box given by sys->lo/hi tiled over the horizon (controllers.py:968-971).
  *   sqn [Nactor*m][E*S]         -- start points in, minimisers out; element (k, j, e, s) at ((k*m+j)*E + e)*S + s
  *                                  (the layout of per-environment candidates).  S: power of two <= 32.
- *   workspace                   -- device scratch of rcg_actor_opt_workspace_bytes() bytes (quasi-Newton memory).
+ *   workspace                   -- device scratch of rcg_actor_opt_workspace_bytes() bytes: a work-queue counter (the
+ *                                  kernel is a persistent grid whose lanes pull the next problem when theirs is
+ *                                  done), the final cost per start, and the quasi-Newton memory of the resident
+ *                                  threads.  Its content is meaningless between calls; concurrent calls on
+ *                                  different streams need separate workspaces.
  *   mask[E] or NULL             -- environments with mask == 0 are skipped entirely.
  *   max_iter, pg_tol, f_tol     -- stop after max_iter accepted iterations, when |P(x - g) - x|_inf <= pg_tol, or
  *                                  when the cost moved by <= f_tol * max(|J|, 1) twice in a row.
