@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="environment blocks (streams) of the host-staged loop")
+    ap.add_argument("--no-opt", action="store_true", help="skip the extra block that times the closed loop with the batched actor optimiser")
     ap.add_argument("--no-graph", action="store_true", help="drive the host-staged loop from Python instead of a CUDA graph")
     return ap.parse_args()
 
@@ -308,6 +309,33 @@ def run_b200(args):
                       + "; candidate sets resident on the device"}
         del loop
 
+    # ---- extra (N = 1): the same closed loop with the batched bounded minimiser standing in for the SLSQP
+    #      _actor_optimizer instead of enumerate-and-argmin; reported beside the headline, not part of it
+    actor_opt = None
+    if world == 1 and not args.no_opt:
+        K2 = min(K, 200)
+        eng2 = ClosedLoopEngine(SYSTEM, x0, None, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
+                                action_init=ACTION_INIT, device=dev, actor="opt", opt_start="init", opt_pg_tol=1e-4,
+                                opt_f_tol=1e-8)
+        for _ in range(W):
+            eng2.run_interval()
+        torch.cuda.synchronize()
+        n0, st0 = int(eng2.nsamples.sum().item()), int(eng2.nsteps.sum().item())
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(K2):
+            eng2.run_interval()
+        a1.record()
+        torch.cuda.synchronize()
+        ms_opt = a0.elapsed_time(a1)
+        actor_opt = {"ms_per_step": ms_opt / K2, "steps": K2,
+                     "solves_per_s": (int(eng2.nsamples.sum().item()) - n0) / (ms_opt * 1e-3),
+                     "env_steps_per_s": (int(eng2.nsteps.sum().item()) - st0) / (ms_opt * 1e-3),
+                     "api": "ClosedLoopEngine(actor='opt', opt_start='init', opt_pg_tol=1e-4, opt_f_tol=1e-8): rcg_rk45_advance + "
+                            "rcg_actor_opt (exact adjoint gradient, projected L-BFGS from action_sqn_init, one bounded "
+                            "minimisation of _actor_cost per environment and control interval)"}
+        del eng2
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,7 +386,7 @@ def run_b200(args):
                          if not args.shared_cands else "shared table: cache-resident by design",
                    "sharding": f"{world} x contiguous env blocks, no per-step communication"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": tot_launches, "roofline": roofline, "cpu_baseline": cpu,
-        "mean_return_so_far": float(returns.mean().item()),
+        "actor_optimizer": actor_opt, "mean_return_so_far": float(returns.mean().item()),
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -224,7 +224,7 @@ def test_actor_opt_errors_are_loud(rb):
         ops.actor_opt(sysd, obj, st.cpu(), st, sqn, w_critic=torch.ones(3, dtype=torch.float64, device="cuda"))
 
 
-def _oracle_loop_with_optimizer(s, ct, x0, action_init, dt, t1, N, m, max_iter):
+def _oracle_loop_with_optimizer(s, ct, x0, action_init, dt, t1, N, m, max_iter, w=None):
     """The headless main loop (presets/main_3wrobot_NI.py:415-440) for one environment with the oracle's pieces and
     the restated minimiser as _actor_optimizer, started from action_sqn_init at every sample like the reference."""
     r = oracle.RK45(s, x0, 0.0, t1, dt / 2)
@@ -237,7 +237,7 @@ def _oracle_loop_with_optimizer(s, ct, x0, action_init, dt, t1, N, m, max_iter):
         t, obs = r.t, r.y
         if t - clock >= dt:
             clock = t
-            x, _, _, _ = oracle.actor_opt(ct, s, sqn_init, obs, state_sys, None, max_iter=max_iter, pg_tol=1e-7, f_tol=1e-12)
+            x, _, _, _ = oracle.actor_opt(ct, s, sqn_init, obs, state_sys, w, max_iter=max_iter, pg_tol=1e-7, f_tol=1e-12)
             action = x[:m].copy()
             samples += 1
         r.receive_action(action)
@@ -407,3 +407,29 @@ def test_device_trajectory_ring_decimation_and_wraparound(rb):
     want = ref[2::3][-20:]                                       # steps 3, 6, 9, ... (1-based), the last 20 of them
     assert tr.shape[0] == 20 and np.array_equal(tr[:, 0], want[:, 0])
     assert int(eng.log.count[0].item()) == ref.shape[0] // 3
+
+
+def test_closed_loop_with_optimizer_vs_oracle_2tank_sql(rb):
+    """Same as above for Sys2Tank, SQL with a fixed 'quad-nomix' critic and an observation target (the general,
+    non-lean objective; 1-D action box [0, 1]): engine with actor='opt' vs the loop assembled from the oracle."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    name, N, dt, t1 = "2tank", 8, 0.1, 3.0
+    n, m = DIMS[name]
+    P = PRESET[name]
+    rng = np.random.default_rng(5)
+    E = 5
+    x0 = rng.uniform(-2, 2, size=(E, n))
+    w = np.array([11.0, 11.0, 1.0])
+    kw = dict(mode="SQL", Nactor=N, pred_step_size=dt * P["psm"], critic_struct="quad-nomix", R1=P["R1_diag"],
+              observation_target=P["target"])
+    eng = ClosedLoopEngine(name, x0, None, pars=P["pars"], ctrl_bnds=P["bnds"], dt=dt, t1=t1, w_critic=w, action_init=[0.5],
+                           actor="opt", opt_start="init", opt_iters=300, **kw)
+    eng.run()
+    got = eng.results()
+    s = oracle.make_sys(name, P["pars"], P["bnds"])
+    ct = oracle.make_ctrl(n, m, **kw)
+    for e in range(E):
+        y, accum, steps, samples = _oracle_loop_with_optimizer(s, ct, x0[e], [0.5], dt, t1, N, m, 300, w=w)
+        assert got["nsteps"][e] == steps and got["nsamples"][e] == samples
+        assert np.max(np.abs(got["y"][e] - y) / np.maximum(np.abs(y), 1e-2)) <= 1e-6, (e, got["y"][e], y)
+        assert abs(got["accum"][e] - accum) <= 1e-6 * abs(accum)
