@@ -48,7 +48,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
                         int32_t w_per_env, const int32_t *mask, T *J_out, int32_t *argmin_out, T *Jmin_out,
                         T *action_out, T *accum, double sampling_time, void *stream)
 {
-    RCG_REQUIRE(sys && obj && state_sys && obs && cand, "%s: null argument", what);
+    RCG_REQUIRE(sys && obj && (E <= 0 || (state_sys && obs && cand)), "%s: null argument", what);
     const int n = sys_n(sys->sys_id), m = sys_m(sys->sys_id);
     RCG_REQUIRE(n > 0, "%s: unknown sys_id %d", what, sys->sys_id);
     RCG_REQUIRE(obj->mode >= RCG_MODE_MPC && obj->mode <= RCG_MODE_SQL, "%s: unknown mode %d", what, obj->mode);
@@ -57,7 +57,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     RCG_REQUIRE(obj->Nactor >= 1 && obj->Nactor <= RCG_MAX_NACTOR, "%s: Nactor %d out of range [1, %d]", what,
                 obj->Nactor, RCG_MAX_NACTOR);
     RCG_REQUIRE(C >= 1, "%s: C must be >= 1", what);
-    RCG_REQUIRE(obj->mode == RCG_MODE_MPC || w_critic, "%s: w_critic is required in RQL/SQL mode", what);
+    RCG_REQUIRE(obj->mode == RCG_MODE_MPC || w_critic || E <= 0, "%s: w_critic is required in RQL/SQL mode", what);
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;
 

@@ -24,7 +24,7 @@ static int opt_common(const char *what, const rcg_system_t *sys, const rcg_objec
                       const double *state_sys, const double *obs, double *sqn, const double *w_critic, int &n, int &m,
                       int &shift)
 {
-    RCG_REQUIRE(sys && obj && state_sys && obs && sqn, "%s: null argument", what);
+    RCG_REQUIRE(sys && obj && (E <= 0 || (state_sys && obs && sqn)), "%s: null argument", what);
     n = sys_n(sys->sys_id);
     m = sys_m(sys->sys_id);
     RCG_REQUIRE(n > 0, "%s: unknown sys_id %d", what, sys->sys_id);
@@ -34,7 +34,7 @@ static int opt_common(const char *what, const rcg_system_t *sys, const rcg_objec
     RCG_REQUIRE(obj->Nactor >= 1 && obj->Nactor <= RCG_MAX_NACTOR, "%s: Nactor %d out of range [1, %d]", what,
                 obj->Nactor, RCG_MAX_NACTOR);
     RCG_REQUIRE(S >= 1 && S <= 32 && (S & (S - 1)) == 0, "%s: S must be a power of two in [1, 32], got %d", what, S);
-    RCG_REQUIRE(obj->mode == RCG_MODE_MPC || w_critic, "%s: w_critic is required in RQL/SQL mode", what);
+    RCG_REQUIRE(obj->mode == RCG_MODE_MPC || w_critic || E <= 0, "%s: w_critic is required in RQL/SQL mode", what);
     shift = 0;
     while ((1 << shift) < S) ++shift;
     return 0;
@@ -64,7 +64,7 @@ static int launch_opt(const char *what, const rcg_system_t *sys, const rcg_objec
     if (int rc = opt_common(what, sys, obj, E, S, state_sys, obs, sqn, w_critic, n, m, shift)) return rc;
     const bool generic = opt_is_generic(obj, n + m);
     const int64_t need = grad_only && !generic ? 0 : opt_ws_doubles(obj->Nactor, n, m, generic, E, S) * (int64_t)sizeof(double);
-    RCG_REQUIRE(need == 0 || (ws && ws_bytes >= need), "%s: workspace too small (%lld bytes given, %lld needed)", what,
+    RCG_REQUIRE(need == 0 || E <= 0 || (ws && ws_bytes >= need), "%s: workspace too small (%lld bytes given, %lld needed)", what,
                 (long long)ws_bytes, (long long)need);
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;
@@ -140,7 +140,7 @@ int rcg_actor_opt(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E
 int rcg_gather_sqn(int32_t L, int64_t E, int32_t C, const double *cand, int32_t cand_per_env, const int32_t *idx,
                    const int32_t *mask, double *sqn_out, void *stream)
 {
-    RCG_REQUIRE(cand && idx && sqn_out, "rcg_gather_sqn: null argument");
+    RCG_REQUIRE(E <= 0 || (cand && idx && sqn_out), "rcg_gather_sqn: null argument");
     RCG_REQUIRE(L >= 1 && C >= 1, "rcg_gather_sqn: L and C must be >= 1");
     if (int rc = rcg::require_device()) return rc;
     if (E <= 0) return 0;

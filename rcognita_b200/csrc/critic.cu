@@ -130,7 +130,7 @@ int rcg_stage_obj(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, c
                   double *out, double *accum, double scale, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obj && obs && act && (out || accum), "rcg_stage_obj: null argument");
+    RCG_REQUIRE(obj && (E <= 0 || (obs && act && (out || accum))), "rcg_stage_obj: null argument");
     RCG_REQUIRE(dims_ok(n, m), "rcg_stage_obj: unsupported dims n=%d m=%d", n, m);
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;
@@ -150,7 +150,7 @@ int rcg_critic(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, cons
                const double *w, int32_t w_per_env, double *out, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obj && obs && act && w && out, "rcg_critic: null argument");
+    RCG_REQUIRE(obj && (E <= 0 || (obs && act && w && out)), "rcg_critic: null argument");
     RCG_REQUIRE(dims_ok(n, m), "rcg_critic: unsupported dims n=%d m=%d", n, m);
     RCG_REQUIRE(obj->critic_struct >= 0 && obj->critic_struct <= 3, "rcg_critic: unknown critic_struct %d",
                 obj->critic_struct);
@@ -175,7 +175,7 @@ int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E,
                     const double *act_buf, const double *w, const double *w_prev, double *Jc_out, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obj && obs_buf && act_buf && w && w_prev && Jc_out, "rcg_critic_cost: null argument");
+    RCG_REQUIRE(obj && (E <= 0 || (obs_buf && act_buf && w && w_prev && Jc_out)), "rcg_critic_cost: null argument");
     RCG_REQUIRE(dims_ok(n, m), "rcg_critic_cost: unsupported dims n=%d m=%d", n, m);
     RCG_REQUIRE(obj->critic_struct >= 0 && obj->critic_struct <= 3, "rcg_critic_cost: unknown critic_struct %d",
                 obj->critic_struct);
@@ -208,7 +208,7 @@ int rcg_ctrl_sample(int64_t E, const double *t, double *clock, double period, co
                     void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(t && clock && mask_out, "rcg_ctrl_sample: null argument");
+    RCG_REQUIRE(E <= 0 || (t && clock && mask_out), "rcg_ctrl_sample: null argument");
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;
     ctrl_sample_kernel<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(E, t, clock, period, in_mask, mask_out);
@@ -219,7 +219,7 @@ int rcg_push_buffers(int32_t n, int32_t m, int32_t buffer_size, int64_t E, doubl
                      const double *obs, const double *act, const int32_t *mask, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obs_buf && act_buf && obs && act, "rcg_push_buffers: null argument");
+    RCG_REQUIRE(E <= 0 || (obs_buf && act_buf && obs && act), "rcg_push_buffers: null argument");
     RCG_REQUIRE(n >= 1 && m >= 1 && buffer_size >= 1, "rcg_push_buffers: bad dims");
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;

@@ -460,7 +460,7 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
                               void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obj && obs_buf && act_buf && w_prev && w, "rcg_critic_fit: null argument");
+    RCG_REQUIRE(obj && (E <= 0 || (obs_buf && act_buf && w_prev && w)), "rcg_critic_fit: null argument");
     RCG_REQUIRE((n == 3 && m == 2) || (n == 5 && m == 2) || (n == 2 && m == 1), "rcg_critic_fit: unsupported dims n=%d m=%d", n, m);
     RCG_REQUIRE(obj->critic_struct >= 0 && obj->critic_struct <= 3, "rcg_critic_fit: unknown critic_struct %d",
                 obj->critic_struct);

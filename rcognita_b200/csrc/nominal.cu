@@ -68,7 +68,7 @@ extern "C" int rcg_nominal_ni(const rcg_system_t *sys, int64_t E, const double *
                               double sampling_time, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(sys && obs && action, "rcg_nominal_ni: null argument");
+    RCG_REQUIRE(sys && (E <= 0 || (obs && action)), "rcg_nominal_ni: null argument");
     RCG_REQUIRE(sys->sys_id == RCG_SYS_3WROBOT_NI, "rcg_nominal_ni: the nominal controller is defined for Sys3WRobotNI "
                 "(sys_id %d given)", sys->sys_id);
     RCG_REQUIRE(!accum || obj, "rcg_nominal_ni: accum needs the objective descriptor (stage_obj)");

@@ -306,7 +306,7 @@ rhs_kernel(const __grid_constant__ SysDev<T> S, int64_t E, const T *__restrict__
 template <typename T, bool CLIP>
 static int launch_rhs(const rcg_system_t *sys, int64_t E, const T *y, T *action, T *f_out, void *stream)
 {
-    RCG_REQUIRE(sys && y && action && f_out, "rcg_rhs: null argument");
+    RCG_REQUIRE(sys && (E <= 0 || (y && action && f_out)), "rcg_rhs: null argument");
     RCG_REQUIRE(sys_n(sys->sys_id) > 0, "rcg_rhs: unknown sys_id %d", sys->sys_id);
     if (int rc = require_device()) return rc;
     if (E <= 0) return 0;
@@ -358,10 +358,10 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
                        T *state_sys, T *accum, int32_t *flag, int32_t *nsamples, void *stream,
                        const rcg_log_t *log_h = nullptr)
 {
-    RCG_REQUIRE(sys && sol_h && y && f && t && h_abs && status && action, "%s: null argument", what);
+    RCG_REQUIRE(sys && sol_h && (E <= 0 || (y && f && t && h_abs && status && action)), "%s: null argument", what);
     LogDev logd{nullptr, nullptr, 0, 0};
     if (log_h) {
-        RCG_REQUIRE(CTRL && log_h->rows && log_h->count && nsteps && accum, "%s: log needs rows, count, nsteps and accum", what);
+        RCG_REQUIRE(CTRL && (E <= 0 || (log_h->rows && log_h->count && nsteps && accum)), "%s: log needs rows, count, nsteps and accum", what);
         RCG_REQUIRE(log_h->capacity >= 1 && log_h->every >= 1, "%s: log capacity and every must be >= 1", what);
         logd = LogDev{log_h->rows, log_h->count, log_h->capacity, log_h->every};
     }
@@ -370,7 +370,7 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
     RCG_REQUIRE(n > 0, "%s: unknown sys_id %d", what, sys->sys_id);
     RCG_REQUIRE(sol_h->max_step > 0, "%s: `max_step` must be positive.", what);    // scipy common.py:18-23
     if (CTRL) {
-        RCG_REQUIRE(obj && clock, "%s: objective and ctrl_clock are required", what);
+        RCG_REQUIRE(obj && (clock || E <= 0), "%s: objective and ctrl_clock are required", what);
         RCG_REQUIRE(max_steps > 0, "%s: max_steps must be positive", what);
     }
     if (int rc = require_device()) return rc;
@@ -454,7 +454,7 @@ int rcg_log_rows(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, co
                  const rcg_log_t *log, void *stream)
 {
     using namespace rcg;
-    RCG_REQUIRE(obj && t && y && action && accum && log && log->rows && log->count, "rcg_log_rows: null argument");
+    RCG_REQUIRE(obj && log && (E <= 0 || (t && y && action && accum && log->rows && log->count)), "rcg_log_rows: null argument");
     RCG_REQUIRE(log->capacity >= 1 && log->every >= 1, "rcg_log_rows: log capacity and every must be >= 1");
     RCG_REQUIRE((n == 3 && m == 2) || (n == 5 && m == 2) || (n == 2 && m == 1), "rcg_log_rows: unsupported dims n=%d m=%d", n, m);
     if (int rc = require_device()) return rc;

@@ -433,3 +433,44 @@ def test_closed_loop_with_optimizer_vs_oracle_2tank_sql(rb):
         assert got["nsteps"][e] == steps and got["nsamples"][e] == samples
         assert np.max(np.abs(got["y"][e] - y) / np.maximum(np.abs(y), 1e-2)) <= 1e-6, (e, got["y"][e], y)
         assert abs(got["accum"][e] - accum) <= 1e-6 * abs(accum)
+
+
+def test_actor_opt_edge_cases(rb):
+    """Nactor = 1 (no Euler step at all), one environment with 32 starts, max_iter = 0 (the clipped start point and
+    its cost come back), starts outside the box (projected first), and an empty batch."""
+    _, _C, ops = rb
+    name = "3wrobotNI"
+    n, m = DIMS[name]
+    bn = PRESET[name]["bnds"]
+    sysd = _C.make_system(name, [], bn)
+    s = oracle.make_sys(name, [], bn)
+    R1 = np.diag([1.0, 10.0, 1.0, 0.5, 0.25])                        # non-zero action weights: interior minimiser
+    x = dev(np.array([[1.0], [-2.0], [0.3]]))
+    # Nactor = 1: J = stage_obj(obs, a) -> minimiser a = 0
+    obj1 = _C.make_objective(n, m, mode="MPC", Nactor=1, pred_step_size=0.01, R1=R1)
+    sq = dev(np.array([[7.0], [-3.0]]))
+    J, it, nf = ops.actor_opt(sysd, obj1, x, x, sq, max_iter=50)
+    assert torch.all(sq.abs() <= 1e-6) and abs(J[0].item() - (1 + 40 + 0.09)) <= 1e-9
+    # 32 starts of one environment, some far outside the box; max_iter = 0 returns the projected starts
+    N = 6
+    kw = dict(mode="MPC", Nactor=N, pred_step_size=0.01, R1=R1)
+    obj = _C.make_objective(n, m, **kw)
+    ct = oracle.make_ctrl(n, m, **kw)
+    rng = np.random.default_rng(0)
+    U = rng.uniform(-60, 60, size=(32, N * m))
+    lo, hi = np.tile([-25.0, -5.0], N), np.tile([25.0, 5.0], N)
+    sq = dev(U.T.copy())
+    J0, it0, _ = ops.actor_opt(sysd, obj, x, x, sq, S=32, max_iter=0)
+    assert np.array_equal(sq.cpu().numpy(), np.clip(U, lo, hi).T) and int(it0.max()) == 0
+    for k in (0, 13, 31):
+        Jo = oracle.actor_cost(ct, s, np.clip(U[k], lo, hi), [1.0, -2.0, 0.3], [1.0, -2.0, 0.3])
+        assert abs(J0[k].item() - Jo) <= 1e-9 * abs(Jo)
+    best = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    Jmin = torch.zeros(1, dtype=torch.float64, device="cuda")
+    J1, it1, _ = ops.actor_opt(sysd, obj, x, x, sq, S=32, max_iter=300, best_out=best, Jmin_out=Jmin)
+    assert bool((J1 <= J0 + 1e-12).all()) and best[0].item() == int(np.argmin(J1.cpu().numpy())) and Jmin[0].item() == J1.min().item()
+    # strictly convex objective: all 32 starts end at the same minimum
+    assert float(J1.max() - J1.min()) <= 1e-6 * float(J1.min())
+    # empty batch: a no-op
+    e0 = torch.zeros((n, 0), dtype=torch.float64, device="cuda")
+    ops.actor_opt(sysd, obj, e0, e0, torch.zeros((N * m, 0), dtype=torch.float64, device="cuda"), max_iter=5)

@@ -589,6 +589,33 @@ def test_errors_are_loud(rb):
         ops.rk45_step(sysd, sol, y, f, t, h, status, action)
 
 
+def test_empty_batch_is_a_no_op(rb):
+    """E = 0 (an empty shard): every entry point returns success without touching a pointer."""
+    _, _C, ops = rb
+    name = "3wrobotNI"
+    p = PRESET[name]
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    sol = _C.make_solver(1.0, 0.005)
+    obj = _C.make_objective(3, 2, mode="RQL", Nactor=6, pred_step_size=0.01, R1=p["R1_diag"], buffer_size=10)
+    z = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt, device="cuda")       # noqa: E731
+    i32 = torch.int32
+    y, a = z(3, 0), z(2, 0)
+    ops.rhs(sysd, y, a)
+    ops.state_dyn(sysd, y, a)
+    ops.rk45_step(sysd, sol, y, z(3, 0), z(0), z(0), z(0, dt=i32), a)
+    ops.rk45_advance(sysd, sol, obj, y, z(3, 0), z(0), z(0), z(0, dt=i32), a, z(0), 0.01, 4, state_sys=z(3, 0), accum=z(0),
+                     sample_flag=z(0, dt=i32))
+    J, am, jm = ops.actor_cost(sysd, obj, y, y, z(12, 8), False, 8, w_critic=z(5))
+    assert J.shape == (0, 8) and am.numel() == 0
+    ops.stage_obj(obj, 3, 2, y, a)
+    ops.critic(obj, 3, 2, y, a, z(5))
+    ops.critic_cost(obj, 3, 2, z(10, 3, 0), z(10, 2, 0), z(5, 0, 1), z(5, 0))
+    ops.critic_fit(obj, 3, 2, z(10, 3, 0), z(10, 2, 0), z(5, 0), 0.0, 1e3, z(5, 0), w_init=z(5))
+    ops.ctrl_sample(z(0), z(0), 0.01)
+    ops.push_buffers(3, 2, z(10, 3, 0), z(10, 2, 0), y, a)
+    ops.nominal_ni(sysd, y, 0.5, a)
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_host_staged_loop_equals_resident_loop(rb, graph):
     """engine.HostStagedLoop (lane state owned by pinned host memory, several environment blocks on their own
