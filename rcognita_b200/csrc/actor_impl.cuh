@@ -238,6 +238,7 @@ __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T>
         constexpr int CH = 4;
         const int na = O.Nactor;
         T a[CH][M], an[CH][M];
+        int bad = 0;
 #pragma unroll
         for (int i = 0; i < CH; ++i)
 #pragma unroll
@@ -250,11 +251,17 @@ __device__ __forceinline__ T actor_cost_lane(const SysDev<T> &S, const ObjDev<T>
                     an[i][j] = (k0 + CH + i < na) ? __ldg(cp + ((int64_t)(k0 + CH + i) * M + j) * ld) : T(0);
 #pragma unroll
             for (int i = 0; i < CH; ++i)
-                if (k0 + i < na) ev.stage(k0 + i, k0 + i + 1 == na, a[i]);
+                if (k0 + i < na) {
+                    if constexpr (LEAN) bad |= nonfinite_bits(a[i][0]) | nonfinite_bits(a[i][M - 1]);
+                    ev.stage(k0 + i, k0 + i + 1 == na, a[i]);
+                }
 #pragma unroll
             for (int i = 0; i < CH; ++i)
 #pragma unroll
                 for (int j = 0; j < M; ++j) a[i][j] = an[i][j];
+        }
+        if constexpr (LEAN) {
+            if (bad) ev.J = (T)CUDART_NAN;
         }
     }
     return ev.J;
@@ -602,7 +609,7 @@ static void launch_actor_mc(const ActorLaunch<T> &L)
             case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6, true>(L); return;
             case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8, true>(L); return;
             case 10: launch_actor_one<T, SYS, MODE, CS, true, 10, true>(L); return;
-            default: break;
+            default: launch_actor_one<T, SYS, MODE, CS, true, 0, true>(L); return;      // runtime horizon, lean
             }
         }
     }
