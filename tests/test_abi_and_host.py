@@ -34,12 +34,12 @@ def test_header_symbols_are_exported(lib_path):
 
 
 def test_struct_layouts_match_header():
-    """ctypes mirrors of rcg_system_t / rcg_objective_t / rcg_solver_t must have the C sizes."""
+    """ctypes mirrors of rcg_system_t / rcg_objective_t / rcg_solver_t / rcg_log_t must have the C sizes."""
     from rcognita_b200 import _C
     src = r'''
     #include <stdio.h>
     #include "rcg.h"
-    int main(void) { printf("%zu %zu %zu\n", sizeof(rcg_system_t), sizeof(rcg_objective_t), sizeof(rcg_solver_t)); return 0; }
+    int main(void) { printf("%zu %zu %zu %zu\n", sizeof(rcg_system_t), sizeof(rcg_objective_t), sizeof(rcg_solver_t), sizeof(rcg_log_t)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -48,7 +48,8 @@ def test_struct_layouts_match_header():
         exe = os.path.join(td, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(_C.RcgSystem), ctypes.sizeof(_C.RcgObjective), ctypes.sizeof(_C.RcgSolver)]
+    assert sizes == [ctypes.sizeof(_C.RcgSystem), ctypes.sizeof(_C.RcgObjective), ctypes.sizeof(_C.RcgSolver),
+                     ctypes.sizeof(_C.RcgLog)]
 
 
 def test_dim_helpers_and_descriptors():
