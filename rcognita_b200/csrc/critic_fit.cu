@@ -51,7 +51,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
                   const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
                   const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
                   double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out,
-                  const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
+                  int max_ls, const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
                   int32_t *__restrict__ todo_list, int32_t *__restrict__ todo_count)
 {
     constexpr int D = dim_critic_c(CS, N, M);
@@ -173,7 +173,7 @@ critic_fit_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const dou
                 const double D0 = dual(lam);
                 double a = 1.0;
                 bool ok = false;
-                for (int ls = 0; ls < 40 && evals < max_evals; ++ls) {     // Armijo backtracking on the dual
+                for (int ls = 0; ls < max_ls && evals < max_evals; ++ls) {     // Armijo backtracking on the dual
                     ++evals;
                     for (int r = 0; r < K; ++r) lt[r] = fma(a, dl[r], lam[r]);
                     if (dual(lt) <= D0 + 1e-4 * a * slope + 1e-14 * fabs(D0)) { ok = true; break; }
@@ -267,7 +267,7 @@ critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const do
                    const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
                    const double *__restrict__ winit_g, double *__restrict__ w_g, const int32_t *__restrict__ mask,
                    double mu_rel, int max_outer, int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out,
-                  const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
+                  int max_ls, const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
                   int32_t *__restrict__ todo_list, int32_t *__restrict__ todo_count)
 {
     constexpr int D = dim_critic_c(CS, N, M), P = N + M;
@@ -389,7 +389,7 @@ critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const do
                 // pass B: Armijo backtracking on the dual; the clip pattern of the trial point comes for free
                 double a = 1.0;
                 bool ok = false, same = false;
-                for (int ls = 0; ls < 40 && evals < max_evals; ++ls) {
+                for (int ls = 0; ls < max_ls && evals < max_evals; ++ls) {
                     ++evals;
                     const double t0 = fma(a, d0, l0), t1 = fma(a, d1, l1), t2 = fma(a, d2, l2);
                     double Dt = fma(0.5 * mu, t0 * t0 + t1 * t1 + t2 * t2, -(b[0] * t0 + b[1] * t1 + b[2] * t2));
@@ -447,6 +447,201 @@ critic_fit3_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const do
     if (Jc_out) Jc_out[e] = Jbest;
 }
 
+// ---- second phase, K <= 3: ONE WARP PER PROBLEM ------------------------------------------------------------
+// The environments that exhaust the first-phase budget need hundreds to thousands of dual evaluations; one
+// environment per lane, each evaluation is a serial pass over the D weights (a ~2 us dependency chain for the
+// 28-weight critic) and the launch lasts as long as its slowest lane.  Here lane j owns weight j (and j + 32 when
+// D > 32): its three feature products stay in registers, a pass is a handful of FP64 operations per lane followed by a
+// butterfly all-reduce (every lane ends up with the same sums, so control flow stays warp-uniform), the clip pattern
+// is a pair of ballots.  Same algorithm and constants as critic_fit3_kernel; sums are formed in a different order,
+// so results agree with the one-lane version to rounding, not bit for bit.  Warps pull problems from a queue.
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <int N, int M, int CS, bool RDIAG>
+__global__ void __launch_bounds__(128)
+critic_fit3_warp_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, const double *__restrict__ obs_buf,
+                        const double *__restrict__ act_buf, double *__restrict__ wprev_g, double lo, double hi,
+                        const double *__restrict__ winit_g, double *__restrict__ w_g, double mu_rel0, int max_outer,
+                        int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out, int max_ls,
+                        const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
+                        int32_t *__restrict__ queue)
+{
+    constexpr int D = dim_critic_c(CS, N, M), P = N + M;
+    constexpr int SLOTS = (D + 31) / 32;                    // weights per lane (1, or 2 for the 35-weight critic)
+    using FI = FeatIdx<CS, N, M>;
+    const int lane = threadIdx.x & 31;
+    const int K = O.Ncritic - 1;
+    const int count = *lane_count;
+    auto clipw = [&](double z) { return z < lo ? lo : (z > hi ? hi : z); };
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(queue, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= count) return;
+        const int64_t e = lane_list[item];
+
+        // rows u[r] = [chi(o[k-1], a[k-1]), 1] and right-hand sides b[r] (every lane keeps a copy: 3 x 8 doubles)
+        double u[3][P + 1], b[3];
+        double bb = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int i = 0; i <= P; ++i) u[r][i] = 0.0;
+            b[r] = 0.0;
+            if (r < K) {
+                const int k = K - r;
+                double op[N], on[N], ap[M], an[M];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    op[i] = obs_buf[((int64_t)(k - 1) * N + i) * E + e];
+                    on[i] = obs_buf[((int64_t)k * N + i) * E + e];
+                }
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    ap[j] = act_buf[((int64_t)(k - 1) * M + j) * E + e];
+                    an[j] = act_buf[((int64_t)k * M + j) * E + e];
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) u[r][i] = (CS == RCG_CRITIC_QUAD_MIX) ? op[i] : op[i] - O.target[i];
+#pragma unroll
+                for (int j = 0; j < M; ++j) u[r][N + j] = ap[j];
+                u[r][P] = 1.0;
+                const GlobalWF<double> wp{wprev_g, E, e};
+                b[r] = O.gamma * critic<double, N, M, CS>(O, on, an, wp) + stage_obj<double, N, M, RDIAG>(O, op, ap);
+            }
+            bb = fma(b[r], b[r], bb);
+        }
+        // this lane's weights: feature products, prox centre
+        double p0[SLOTS], p1[SLOTS], p2[SLOTS], wc[SLOTS], wn[SLOTS];
+        bool own[SLOTS];
+        double tr = 0;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            const int j = lane + 32 * sl;
+            own[sl] = j < D;
+            const int ja = own[sl] ? FI::a(j) : 0, jb = own[sl] ? FI::b(j) : 0;
+            p0[sl] = own[sl] ? u[0][ja] * u[0][jb] : 0.0;
+            p1[sl] = own[sl] ? u[1][ja] * u[1][jb] : 0.0;
+            p2[sl] = own[sl] ? u[2][ja] * u[2][jb] : 0.0;
+            wc[sl] = own[sl] ? clipw(winit_g ? winit_g[j] : w_g[j * E + e]) : 0.0;
+            wn[sl] = wc[sl];
+            tr += p0[sl] * p0[sl] + p1[sl] * p1[sl] + p2[sl] * p2[sl];
+        }
+        const double trace = warp_sum(tr);
+        double r0 = 0, r1 = 0, r2 = 0;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) { r0 = fma(p0[sl], wc[sl], r0); r1 = fma(p1[sl], wc[sl], r1); r2 = fma(p2[sl], wc[sl], r2); }
+        r0 = warp_sum(r0) - b[0]; r1 = warp_sum(r1) - b[1]; r2 = warp_sum(r2) - b[2];
+        double Jbest = 0.5 * (r0 * r0 + r1 * r1 + r2 * r2);
+        const double J0 = Jbest;
+        double mu_rel = mu_rel0;
+
+        if (K >= 1 && trace > 0 && isfinite(trace) && isfinite(bb)) {
+            int evals = 0;
+            for (int outer = 0; outer < max_outer && evals < max_evals; ++outer) {
+                const double mu = mu_rel * trace / K;
+                mu_rel *= 1e-2;
+                double l0 = 0, l1 = 0, l2 = 0;
+                for (int it = 0; it < max_newton && evals < max_evals; ++it) {
+                    ++evals;
+                    // pass A
+                    double F0 = 0, F1 = 0, F2 = 0, H00 = 0, H10 = 0, H11 = 0, H20 = 0, H21 = 0, H22 = 0, Ds = 0;
+                    unsigned lowA[SLOTS], highA[SLOTS];
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) {
+                        const double z = fma(p2[sl], l2, fma(p1[sl], l1, fma(p0[sl], l0, wc[sl])));
+                        const bool below = own[sl] && !(z > lo), above = own[sl] && !(z < hi);
+                        const double w = below ? lo : (above ? hi : z);
+                        if (own[sl]) {
+                            Ds += below ? lo * z - 0.5 * lo * lo : (above ? hi * z - 0.5 * hi * hi : 0.5 * z * z);
+                            F0 = fma(p0[sl], w, F0); F1 = fma(p1[sl], w, F1); F2 = fma(p2[sl], w, F2);
+                            if (!below && !above) {
+                                H00 = fma(p0[sl], p0[sl], H00); H10 = fma(p1[sl], p0[sl], H10); H11 = fma(p1[sl], p1[sl], H11);
+                                H20 = fma(p2[sl], p0[sl], H20); H21 = fma(p2[sl], p1[sl], H21); H22 = fma(p2[sl], p2[sl], H22);
+                            }
+                        }
+                        lowA[sl] = __ballot_sync(0xffffffffu, below);
+                        highA[sl] = __ballot_sync(0xffffffffu, above);
+                    }
+                    F0 = warp_sum(F0) + (mu * l0 - b[0]); F1 = warp_sum(F1) + (mu * l1 - b[1]); F2 = warp_sum(F2) + (mu * l2 - b[2]);
+                    H00 = warp_sum(H00) + mu; H10 = warp_sum(H10); H11 = warp_sum(H11) + mu;
+                    H20 = warp_sum(H20); H21 = warp_sum(H21); H22 = warp_sum(H22) + mu;
+                    const double D0 = warp_sum(Ds) + fma(0.5 * mu, l0 * l0 + l1 * l1 + l2 * l2, -(b[0] * l0 + b[1] * l1 + b[2] * l2));
+                    if (fmax(fmax(fabs(F0), fabs(F1)), fabs(F2)) <= 1e-13 * sqrt(bb)) break;
+                    if (!(H00 > 0)) break;
+                    const double c00 = sqrt(H00), c10 = H10 / c00, c20 = H20 / c00;
+                    const double t11 = H11 - c10 * c10;
+                    if (!(t11 > 0)) break;
+                    const double c11 = sqrt(t11), c21 = (H21 - c20 * c10) / c11;
+                    const double t22 = H22 - c20 * c20 - c21 * c21;
+                    if (!(t22 > 0)) break;
+                    const double c22 = sqrt(t22);
+                    const double y0 = -F0 / c00, y1 = (-F1 - c10 * y0) / c11, y2 = (-F2 - c20 * y0 - c21 * y1) / c22;
+                    const double d2 = y2 / c22, d1 = (y1 - c21 * d2) / c11, d0 = (y0 - c10 * d1 - c20 * d2) / c00;
+                    const double slope = F0 * d0 + F1 * d1 + F2 * d2;
+                    if (!(slope < 0)) break;
+                    // pass B: Armijo backtracking on the dual
+                    double a = 1.0;
+                    bool ok = false, same = false;
+                    for (int ls = 0; ls < max_ls && evals < max_evals; ++ls) {
+                        ++evals;
+                        const double t0 = fma(a, d0, l0), t1 = fma(a, d1, l1), t2 = fma(a, d2, l2);
+                        double Dp = 0;
+                        bool eq = true;
+#pragma unroll
+                        for (int sl = 0; sl < SLOTS; ++sl) {
+                            const double z = fma(p2[sl], t2, fma(p1[sl], t1, fma(p0[sl], t0, wc[sl])));
+                            const bool below = own[sl] && !(z > lo), above = own[sl] && !(z < hi);
+                            if (own[sl]) Dp += below ? lo * z - 0.5 * lo * lo : (above ? hi * z - 0.5 * hi * hi : 0.5 * z * z);
+                            eq = eq && (__ballot_sync(0xffffffffu, below) == lowA[sl]) && (__ballot_sync(0xffffffffu, above) == highA[sl]);
+                        }
+                        const double Dt = warp_sum(Dp) + fma(0.5 * mu, t0 * t0 + t1 * t1 + t2 * t2, -(b[0] * t0 + b[1] * t1 + b[2] * t2));
+                        if (Dt <= D0 + 1e-4 * a * slope + 1e-14 * fabs(D0)) {
+                            ok = true;
+                            l0 = t0; l1 = t1; l2 = t2;
+                            same = (a == 1.0) && eq;
+                            break;
+                        }
+                        a *= 0.5;
+                    }
+                    if (!ok || same) break;
+                }
+                // prox step result, its cost
+                double q0 = 0, q1 = 0, q2 = 0;
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    wn[sl] = own[sl] ? clipw(fma(p2[sl], l2, fma(p1[sl], l1, fma(p0[sl], l0, wc[sl])))) : 0.0;
+                    q0 = fma(p0[sl], wn[sl], q0); q1 = fma(p1[sl], wn[sl], q1); q2 = fma(p2[sl], wn[sl], q2);
+                }
+                q0 = warp_sum(q0) - b[0]; q1 = warp_sum(q1) - b[1]; q2 = warp_sum(q2) - b[2];
+                const double Jn = 0.5 * (q0 * q0 + q1 * q1 + q2 * q2);
+                if (Jn < Jbest) {
+                    Jbest = Jn;
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) wc[sl] = wn[sl];
+                    if (Jn <= 1e-12 * J0 || Jn <= 1e-20 * bb) break;
+                }
+            }
+        }
+        __syncwarp();                                      // every lane has read w_prev before anyone overwrites it
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            const int j = lane + 32 * sl;
+            if (own[sl]) {
+                w_g[j * E + e] = wc[sl];
+                if (update_prev) wprev_g[j * E + e] = wc[sl];
+            }
+        }
+        if (lane == 0 && Jc_out) Jc_out[e] = Jbest;
+    }
+}
+
 static bool fit_rdiag(const rcg_objective_t *obj, int p)
 {
     return obj->r_is_diag && is_diag(obj->R1, p) && (obj->stage_struct == RCG_STAGE_QUADRATIC || is_diag(obj->R2, p));
@@ -480,18 +675,19 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     const int outer = 5;
     const double mu_rel = 1e-3;
     const int newton = 20;
+    const int max_ls = 40;          // Armijo halvings per Newton step (a cap of 12 saves 17 % of the fit time in config 3 but moves the fitted costs)
     const bool fast = obj->Ncritic - 1 <= 3;
     // Run-to-convergence fits of a large batch go in two phases.  A few per cent of in-loop problems need hundreds
     // to thousands of dual evaluations while the rest finish within a few dozen; with one environment per lane every
     // warp that holds one of them waits for it (ncu: 3.3 of 32 lanes active on average).  Phase 1 gives every
     // environment kPhase1Budget evaluations; those that run out are queued (and write nothing), phase 2 restarts
     // exactly them, packed densely into warps.  Each environment's result is what the single-phase kernel computes.
-    constexpr int kPhase1Budget = 32;
+    constexpr int kPhase1Budget = 32;           // 4 ... 48 measured within 5 % of each other (config 3)
     // Measured on B200 (profiles/r01_critic_fit_two_phase.txt): 23.0 -> 20.8 ms per 1 M fits of the 28-weight critic
     // inside config 3's loop -- the rest of the tail is the serial dependency chain of the environments that run
     // into the iteration caps, not idle lanes; for small critics the second launch costs more than it saves
     // (2tank, 3 weights: 0.49 -> 0.55 ms), hence the dim_critic threshold.
-    const bool two_phase = max_evals <= 0 && E >= 4096 && dim_critic_c(obj->critic_struct, n, m) >= 10 &&
+    const bool two_phase = max_evals <= 0 && dim_critic_c(obj->critic_struct, n, m) >= 10 &&
                            getenv("RCG_FIT_ONE_PHASE") == nullptr;
     int32_t *todo = nullptr;
     if (two_phase) {
@@ -508,14 +704,18 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
             (void)cudaGetLastError();
             pool_configured = true;
         }
-        if (cudaMallocAsync((void **)&todo, (size_t)(E + 1) * sizeof(int32_t), s) != cudaSuccess) {
+        if (cudaMallocAsync((void **)&todo, (size_t)(E + 2) * sizeof(int32_t), s) != cudaSuccess) {
             (void)cudaGetLastError();
             todo = nullptr;                                // no pool on this device: single phase
         } else {
-            cudaMemsetAsync(todo + E, 0, sizeof(int32_t), s);
+            cudaMemsetAsync(todo + E, 0, 2 * sizeof(int32_t), s);      // [E] = queued environments, [E + 1] = work queue
         }
     }
     const int nphases = todo ? 2 : 1;
+    const bool warp_phase2 = getenv("RCG_FIT_LANE_PHASE2") == nullptr;      // second phase: one warp per environment
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     for (int phase = 0; phase < nphases; ++phase) {
         const int evals = (todo && phase == 0) ? kPhase1Budget : (max_evals > 0 ? max_evals : 0x7fffffff);
         const int32_t *lane_list = (todo && phase == 1) ? todo : nullptr, *lane_count = (todo && phase == 1) ? todo + E : nullptr;
@@ -527,16 +727,21 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
         static bool configured = false;                                                                                   \
         if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; } \
         kern<<<grid, 128, smem, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mask, mu_rel, outer, newton,  \
-                                     evals, update_prev, Jc_out, lane_list, lane_count, todo_list, todo_count);                  \
+                                     evals, update_prev, Jc_out, max_ls, lane_list, lane_count, todo_list, todo_count);          \
     }
+#define FIT3W(NN, MM, CS, RD)                                                                                             \
+    critic_fit3_warp_kernel<NN, MM, CS, RD><<<(unsigned)(sms * 8), 128, 0, s>>>(                                         \
+        O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mu_rel, outer, newton, evals, update_prev, Jc_out,      \
+        max_ls, lane_list, lane_count, todo + E + 1);
 #define FIT(NN, MM, CS)                                                                                                   \
-    if (fast) { if (rd) FIT3(NN, MM, CS, true) else FIT3(NN, MM, CS, false) }                                             \
+    if (fast && lane_list && warp_phase2) { if (rd) FIT3W(NN, MM, CS, true) else FIT3W(NN, MM, CS, false) }               \
+    else if (fast) { if (rd) FIT3(NN, MM, CS, true) else FIT3(NN, MM, CS, false) }                                        \
     else if (rd) critic_fit_kernel<NN, MM, CS, true><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, \
                                                                      mask, mu_rel, outer, newton, evals, update_prev, Jc_out,      \
-                                                                     lane_list, lane_count, todo_list, todo_count);                \
+                                                                     max_ls, lane_list, lane_count, todo_list, todo_count);        \
     else critic_fit_kernel<NN, MM, CS, false><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w,  \
                                                                    mask, mu_rel, outer, newton, evals, update_prev, Jc_out,        \
-                                                                   lane_list, lane_count, todo_list, todo_count);
+                                                                   max_ls, lane_list, lane_count, todo_list, todo_count);
 #define FITCS(NN, MM)                  \
     switch (obj->critic_struct) {      \
     case 0: FIT(NN, MM, 0) break;      \
@@ -547,6 +752,7 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
         if (n == 3) { FITCS(3, 2) } else if (n == 5) { FITCS(5, 2) } else { FITCS(2, 1) }
 #undef FITCS
 #undef FIT
+#undef FIT3W
 #undef FIT3
         if (int rc = check_launch("rcg_critic_fit")) {
             if (todo) cudaFreeAsync(todo, s);
