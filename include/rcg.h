@@ -271,8 +271,9 @@ int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E,
  * and, on the committed goldens, <= the reference's.  Lanes with mask == 0 are left untouched.
  * update_prev != 0 additionally stores the result in w_prev [dimc][E] (controllers.py:1471).
  * max_evals > 0 bounds the dual evaluations spent per environment (the best iterate so far is returned when the
- * budget runs out; a few per cent of in-loop problems need hundreds of evaluations and, one environment per
- * lane, hold their whole warp back); max_evals <= 0: run to convergence.  Jc_out[E] (may be NULL) receives
+ * budget runs out); max_evals <= 0: run to convergence -- for critics with >= 10 weights in two launches: a budgeted
+ * pass with one environment per lane, then the unfinished environments again with one warp each (scratch from the
+ * stream-ordered allocator of `stream`).  Jc_out[E] (may be NULL) receives
  * _critic_cost at the returned weights. */
 int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, const double *obs_buf,
                    const double *act_buf, double *w_prev, double w_min, double w_max, const double *w_init,
