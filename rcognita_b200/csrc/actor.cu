@@ -10,7 +10,7 @@ namespace rcg {
 // 2-D tensor map of a per-environment candidate array [rows = Nactor*m][cols = E*C] (row-major, cols
 // contiguous), box = 32 columns x all rows.  cuTensorMapEncodeTiled is resolved through the runtime so
 // that the library does not link against libcuda directly.
-static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, int64_t cols, int rows)
+static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, int64_t cols, int rows, int box_rows)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -29,7 +29,7 @@ static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, 
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)cols * elem};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)rows};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     const cuuint32_t estride[2] = {1u, 1u};
     const CUresult r = encode(tm, elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                               const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -96,6 +96,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     // TMA-staged kernel: per-environment candidates, diagonal R, a specialised horizon, and a candidate
     // count whose lane mapping is a contiguous box (C a multiple of 32, or a power of two below 32)
     L.use_tma = false;
+    L.use_tma_rt = false;
     {
         const int na = obj->Nactor;
         const bool na_ok = na == 3 || na == 5 || na == 6 || na == 8 || na == 10;
@@ -103,8 +104,13 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
         const int64_t cols = E * (int64_t)C;
         if (cand_per_env && L.rdiag && na_ok && c_ok && cols % (16 / (int)sizeof(T)) == 0 && cols < (int64_t)1 << 31 &&
             ((uintptr_t)cand % 16) == 0 && getenv("RCG_ACTOR_NO_TMA") == nullptr) {
-            if (int rc = make_cand_tensor_map(&L.tmap, cand, sizeof(T), cols, na * m)) return rc;
+            if (int rc = make_cand_tensor_map(&L.tmap, cand, sizeof(T), cols, na * m, na * m)) return rc;
             L.use_tma = true;
+        } else if (cand_per_env && L.rdiag && !na_ok && c_ok && cols % (16 / (int)sizeof(T)) == 0 && cols < (int64_t)1 << 31 &&
+                   ((uintptr_t)cand % 16) == 0 && getenv("RCG_ACTOR_NO_TMA") == nullptr) {
+            // runtime horizon: boxes of kRtChunk stages; rows past Nactor*m of the last box are zero-filled
+            if (int rc = make_cand_tensor_map(&L.tmap, cand, sizeof(T), cols, na * m, kRtChunk * m)) return rc;
+            L.use_tma_rt = true;
         }
     }
     L.stream = (cudaStream_t)stream;

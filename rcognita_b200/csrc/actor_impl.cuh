@@ -549,6 +549,161 @@ actor_cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     }
 }
 
+// ---- TMA-staged variant for RUNTIME horizons (any Nactor without a compile-time specialisation) ---------------
+// Same staging idea, but a box holds kRtChunk stages of 32 candidates (kRtChunk * m component rows x 32 columns,
+// 2 KB in fp64): the lanes evaluate their candidate chunk by chunk while the next chunks of the same candidates -- and
+// then the next 32 candidates -- are in flight.  Rows beyond Nactor * m of the last chunk are out of bounds for the
+// tensor map and arrive as zeros (never evaluated).  Lean objective only when LEAN (see ActorEval).
+constexpr int kRtChunk = 4;
+constexpr int kRtStages = 6;
+template <typename T, int M>
+__host__ __device__ constexpr int tma_rt_smem_bytes() { return kActorWarps * kRtStages * (kRtChunk * M * 32 * (int)sizeof(T) + 8); }
+
+template <typename T, int SYS, int MODE, int CS, bool LEAN>
+__global__ void __launch_bounds__(kActorThreads, 2)
+actor_cost_tma_rt_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SysDev<T> S,
+                         const __grid_constant__ ObjDev<T> O, const __grid_constant__ ActorArgs A,
+                         const T *__restrict__ state_sys_g, const T *__restrict__ obs_g, const T *__restrict__ cand_g,
+                         const T *__restrict__ w_g, const int32_t *__restrict__ mask_g, T *__restrict__ J_g,
+                         int32_t *__restrict__ argmin_g, T *__restrict__ Jmin_g, T *__restrict__ action_g,
+                         T *__restrict__ accum_g, T sampling_time)
+{
+    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    constexpr int ROWS = kRtChunk * M, BOX = ROWS * 32, STAGES = kRtStages;
+    constexpr int DIMC = (MODE == RCG_MODE_MPC) ? 1 : dim_critic_c(CS, N, M);
+    constexpr int kNone = 0x7fffffff;
+    extern __shared__ __align__(128) unsigned char actor_smem[];
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *ring = reinterpret_cast<T *>(actor_smem) + (size_t)wi * STAGES * BOX;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(actor_smem + (size_t)kActorWarps * STAGES * BOX * sizeof(T)) + wi * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t E = A.E;
+    const int C = A.C, seg = A.seg, na = O.Nactor;
+    const int nchunks = (na + kRtChunk - 1) / kRtChunk;
+    const int slot = lane >> A.seg_shift, cl = lane & (seg - 1);
+    const int epw = 32 >> A.seg_shift;
+    const int cpl = (C + seg - 1) >> A.seg_shift;                       // 32-candidate boxes per environment group
+    const int64_t ld = E * (int64_t)C;
+    const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + wi;
+    const int64_t nwarps = (int64_t)gridDim.x * kActorWarps;
+    const int64_t ngroups = (A.num_groups > warp0) ? (A.num_groups - warp0 + nwarps - 1) / nwarps : 0;
+
+    auto env_active = [&](int64_t gi, int sl) -> int {
+        if (gi >= ngroups) return 0;
+        const int64_t e = (warp0 + gi * nwarps) * epw + sl;
+        return (e < E && (mask_g == nullptr || mask_g[e] != 0)) ? 1 : 0;
+    };
+    // producer (lane 0): boxes in the order (group, 32-candidate box, chunk)
+    int64_t p_gi = 0;
+    int p_ci = 0, p_k = 0, p_act = 0;
+    if (lane == 0) p_act = (epw == 1) ? env_active(0, 0) : (ngroups > 0);
+    auto issue = [&](int stage) {
+        if (p_gi < ngroups) {
+            if (p_act) {
+                const int64_t x = (warp0 + p_gi * nwarps) * (int64_t)epw * C + (int64_t)p_ci * 32;
+                mbar_arrive_expect_tx(&bars[stage], (uint32_t)(BOX * sizeof(T)));
+                tma_load_box(ring + (size_t)stage * BOX, &tmap, (int)x, p_k * ROWS, &bars[stage]);
+            } else {
+                mbar_arrive(&bars[stage]);
+            }
+            if (++p_k == nchunks) {
+                p_k = 0;
+                if (++p_ci == cpl) {
+                    p_ci = 0;
+                    ++p_gi;
+                    p_act = (epw == 1) ? env_active(p_gi, 0) : (p_gi < ngroups);
+                }
+            }
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) issue(s);
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t gi = 0; gi < ngroups; ++gi) {
+        const int64_t e = (warp0 + gi * nwarps) * epw + slot;
+        const bool active = env_active(gi, slot) != 0;
+        T bestJ = T(0);
+        int bestI = kNone;
+        T x0[N], ob[N], w[DIMC];
+        T s0 = T(0), c0 = T(1);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { x0[i] = state_sys_g[i * E + e]; ob[i] = obs_g[i * E + e]; }
+            if constexpr (MODE != RCG_MODE_MPC) {
+#pragma unroll
+                for (int i = 0; i < DIMC; ++i) w[i] = A.w_per_env ? w_g[i * E + e] : w_g[i];
+            }
+            if constexpr (SYS != RCG_SYS_2TANK) sincos_t(x0[2], &s0, &c0);
+        }
+        for (int ci = 0; ci < cpl; ++ci) {
+            const int c = cl + ci * seg;
+            const bool valid = active && c < C;
+            ActorEval<T, SYS, MODE, CS, true, LEAN> ev(S, O, x0, ob, s0, c0, w);
+            int bad = 0;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                mbar_wait(&bars[stage], phase);                    // this chunk has landed
+                T a[kRtChunk][M];
+                {
+                    const T *src = ring + (size_t)stage * BOX + lane;
+#pragma unroll
+                    for (int i = 0; i < kRtChunk; ++i)
+#pragma unroll
+                        for (int j = 0; j < M; ++j) a[i][j] = src[(i * M + j) * 32];
+                }
+                __syncwarp();
+                if (lane == 0) issue(stage);                       // refill the slot
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < kRtChunk; ++i) {
+                        const int k = kc * kRtChunk + i;
+                        if (k < na) {
+                            if constexpr (LEAN) bad |= nonfinite_bits(a[i][0]) | nonfinite_bits(a[i][M - 1]);
+                            ev.stage(k, k + 1 == na, a[i]);
+                        }
+                    }
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (valid) {
+                const T J = (LEAN && bad) ? (T)CUDART_NAN : ev.J;
+                if (J_g) J_g[e * (int64_t)C + c] = J;
+                if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
+            }
+        }
+        for (int off = seg >> 1; off > 0; off >>= 1) {
+            const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
+            const int oI = __shfl_xor_sync(0xffffffffu, bestI, off);
+            if (oI != kNone && (bestI == kNone || argmin_better(oJ, oI, bestJ, bestI))) { bestJ = oJ; bestI = oI; }
+        }
+        if (active && cl == 0 && bestI != kNone) {
+            if (argmin_g) argmin_g[e] = bestI;
+            if (Jmin_g) Jmin_g[e] = bestJ;
+            if (action_g || accum_g) {
+                T act[M];
+                const T *cb = cand_g + e * (int64_t)C + bestI;
+#pragma unroll
+                for (int j = 0; j < M; ++j) act[j] = cb[j * ld];
+                if (action_g) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) action_g[j * E + e] = act[j];
+                }
+                if (accum_g) accum_g[e] += stage_obj<T, N, M, true, true>(O, ob, act) * sampling_time;
+            }
+        }
+    }
+}
+
 template <typename T>
 struct ActorLaunch {
     SysDev<T> S;
@@ -567,6 +722,7 @@ struct ActorLaunch {
     int sms;
     int64_t blocks_needed;
     bool use_tma;              // per-env candidates staged by TMA (tmap valid)
+    bool use_tma_rt;           // ... runtime-horizon variant (tmap box = kRtChunk stages)
     CUtensorMap tmap;
     cudaStream_t stream;
 };
@@ -585,6 +741,22 @@ static void launch_actor_one(const ActorLaunch<T> &L)
                 configured = true;
             }
             const int64_t pg = (int64_t)L.sms * tma_min_ctas<T, LL>();
+            const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
+            kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
+                                                         L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
+            return;
+        }
+    }
+    if constexpr (RDIAG && NA == 0) {
+        if (L.use_tma_rt) {
+            auto kern = actor_cost_tma_rt_kernel<T, SYS, MODE, CS, LEAN>;
+            const size_t smem = (size_t)tma_rt_smem_bytes<T, SysDim<SYS>::m>();
+            static bool configured = false;                   // per instantiation
+            if (!configured) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured = true;
+            }
+            const int64_t pg = (int64_t)L.sms * 2;
             const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
             kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
                                                          L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);

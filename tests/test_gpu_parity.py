@@ -217,6 +217,11 @@ def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
     ("3wrobotNI", "MPC", "quad-nomix", 5, 2502, 8), ("3wrobot", "RQL", "quadratic", 10, 1500, 64),
     ("2tank", "SQL", "quad-nomix", 8, 6000, 32), ("2tank", "MPC", "quad-nomix", 3, 7001, 2),
     ("3wrobotNI", "SQL", "quad-lin", 6, 1000, 1024),
+    # horizons without a compile-time specialisation: the runtime-horizon TMA kernel (boxes of 4 stages; the last box
+    # of Nactor = 7, 13, 50, 1 reaches past the array and is zero-filled by the tensor map)
+    ("3wrobotNI", "MPC", "quad-nomix", 7, 3001, 256), ("3wrobot", "RQL", "quadratic", 20, 700, 64),
+    ("2tank", "SQL", "quad-nomix", 1, 5000, 32), ("3wrobotNI", "SQL", "quad-lin", 50, 300, 16),
+    ("3wrobot", "MPC", "quad-nomix", 13, 1203, 8), ("2tank", "RQL", "quad-mix", 12, 900, 96),
 ])
 def test_actor_tma_kernel_matches_direct_kernel(rb, name, mode, cs, N, E, C_):
     """The TMA-staged kernel (per-env candidates, compile-time horizon, C a multiple of 32 or a power of two
