@@ -322,6 +322,37 @@ class ClosedLoopEngine:
                 k += 1
         return k
 
+    # -- checkpoint / resume: everything a continuation depends on, as host tensors
+    _CKPT_EXTRA = ("obs_buf", "act_buf", "w", "w_prev", "critic_clock", "critic_flag", "Jc", "nfits", "sqn")
+
+    def state_dict(self):
+        """Snapshot of the run (lane state, counters, critic buffers / weights, optimiser sequences, trajectory ring):
+        ``load_state_dict`` on an engine built with the same arguments continues bit-identically."""
+        if not self._first_done:
+            self._first_step()
+        torch.cuda.synchronize(self.device)
+        sd = {"blob": self._blob.cpu(), "intervals": self.intervals, "E": self.E, "system": int(self.sysd.sys_id)}
+        for name in self._CKPT_EXTRA:
+            v = getattr(self, name, None)
+            if isinstance(v, torch.Tensor):
+                sd[name] = v.cpu()
+        if self.log is not None:
+            sd["log_rows"], sd["log_count"] = self.log.rows.cpu(), self.log.count.cpu()
+        return sd
+
+    def load_state_dict(self, sd):
+        if sd["E"] != self.E or sd["system"] != int(self.sysd.sys_id) or sd["blob"].numel() != self._blob.numel():
+            raise ValueError("checkpoint was taken from an engine with a different system / batch / layout")
+        self._blob.copy_(sd["blob"])
+        for name in self._CKPT_EXTRA:
+            if name in sd:
+                getattr(self, name).copy_(sd[name])
+        if self.log is not None and "log_rows" in sd:
+            self.log.rows.copy_(sd["log_rows"])
+            self.log.count.copy_(sd["log_count"])
+        self.intervals = int(sd["intervals"])
+        self._first_done = True
+
     def trajectory(self, e=0):
         """Logged rows of environment ``e`` in the reference's column order (rcognita/loggers.py:41-94), oldest
         kept row first: NI t,x,y,alpha,stage_obj,accum_obj,v,omega; 3wrobot t,x,y,alpha,v,omega,stage_obj,accum_obj,F,M;

@@ -594,6 +594,39 @@ def test_errors_are_loud(rb):
         ops.rk45_step(sysd, sol, y, f, t, h, status, action)
 
 
+@pytest.mark.parametrize("name,mode,kw", [
+    ("3wrobotNI", "MPC", dict(actor="candidates")), ("3wrobotNI", "MPC", dict(actor="opt", opt_start="argmin", log_every=2, log_capacity=16)),
+    ("2tank", "SQL", dict(critic_fit=True)),
+])
+def test_checkpoint_resume_is_bit_identical(rb, name, mode, kw):
+    """state_dict() after 7 intervals, 9 more; a fresh engine that loads the snapshot and runs the same 9 intervals ends
+    in exactly the same state (lane state, counters, critic weights, trajectory ring)."""
+    from rcognita_b200.engine import ClosedLoopEngine
+    p = PRESET[name]
+    n, m = DIMS[name]
+    E, N = 257, 6
+    x0 = random_states(name, E, 31)
+    cand = random_cands(name, (64,), N, 32)
+    args = dict(pars=p["pars"], ctrl_bnds=p["bnds"], mode=mode, Nactor=N, dt=p["dt"], pred_step_size=p["dt"] * p["psm"], t1=1e6,
+                R1=p["R1_diag"], observation_target=p["target"], **kw)
+    a = ClosedLoopEngine(name, x0, cand, **args)
+    for _ in range(7):
+        a.run_interval()
+    sd = a.state_dict()
+    for _ in range(9):
+        a.run_interval()
+    b = ClosedLoopEngine(name, x0, cand, **args)
+    b.load_state_dict(sd)
+    for _ in range(9):
+        b.run_interval()
+    assert torch.equal(a._blob, b._blob) and a.intervals == b.intervals == 16
+    if kw.get("critic_fit"):
+        assert torch.equal(a.w, b.w) and torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.nfits, b.nfits)
+    if a.log is not None:
+        assert torch.equal(a.log.count, b.log.count)
+        assert np.array_equal(a.trajectory(5), b.trajectory(5))
+
+
 def test_empty_batch_is_a_no_op(rb):
     """E = 0 (an empty shard): every entry point returns success without touching a pointer."""
     _, _C, ops = rb
