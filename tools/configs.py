@@ -162,6 +162,36 @@ def run_config2_actors(a):
         del eng
 
 
+def run_env_steps(a):
+    """Closed-loop env-steps/s of 3wrobot_NI (dt = 0.01) at scale with cheap controllers in the loop: the nominal parking
+    controller, MPC over a small shared candidate table, and MPC with the batched optimiser -- the env-step side of the
+    north-star target (the headline bench is dominated by its 256 candidate evaluations per environment and sample)."""
+    E = (a.envs + 1023) // 1024 * 1024
+    bn = [[-25.0, 25.0], [-5.0, 5.0]]
+    x0 = torch.as_tensor(synthetic_states("3wrobotNI", 0, E, seed=0), device="cuda")
+    cand16 = synthetic_candidates(bn, 6, 16, seed=1)
+    for tag, cand, kw in (("nominal", None, dict(actor="nominal", ctrl_gain=0.5)),
+                          ("mpc_16_shared_candidates", cand16, dict(actor="candidates")),
+                          ("mpc_optimizer_pg1e-4", None, dict(actor="opt", opt_start="init", opt_pg_tol=1e-4, opt_f_tol=1e-8))):
+        eng = ClosedLoopEngine("3wrobotNI", x0, cand, ctrl_bnds=bn, mode="MPC", Nactor=6, dt=0.01, t1=1e6, R1=[1, 10, 1, 0, 0], **kw)
+        for _ in range(5):
+            eng.run_interval()
+        torch.cuda.synchronize()
+        s0 = int(eng.nsteps.sum().item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.intervals):
+            eng.run_interval()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        steps = int(eng.nsteps.sum().item()) - s0
+        print(json.dumps(dict(config="closed-loop env-steps", controller=tag, E=E, intervals=a.intervals,
+                              ms_per_interval=ms / a.intervals, env_steps_per_s=steps / ms * 1e3,
+                              failed=int((eng.status == _C.FAILED).sum().item()))), flush=True)
+        del eng
+
+
 def pct(x):
     x = np.asarray(x, dtype=np.float64)
     return {"p50": float(np.percentile(x, 50)), "p99": float(np.percentile(x, 99)), "max": float(x.max())}
@@ -208,14 +238,18 @@ def run_fp32_report(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["config2", "config3", "config4", "fp32"])
+    ap.add_argument("what", choices=["config2", "config3", "config4", "fp32", "envsteps"])
+    ap.add_argument("--intervals", type=int, default=200)
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--cands", type=int, default=256)
     ap.add_argument("--t1", type=float, default=0.0)
     ap.add_argument("--opt-sweep", action="store_true", help="config2: sweep the minimiser's stopping rule")
     ap.add_argument("--fit-evals", type=int, default=0, help="work bound of the critic fit per environment (0 = to convergence)")
     a = ap.parse_args()
-    if a.what == "config2":
+    if a.what == "envsteps":
+        a.envs = a.envs or 1 << 20
+        run_env_steps(a)
+    elif a.what == "config2":
         a.envs, a.t1 = a.envs or 65536, a.t1 or 2.0
         run_config2_actors(a)
     elif a.what == "config3":
