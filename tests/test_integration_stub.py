@@ -59,3 +59,21 @@ def test_documented_binding_runs_and_matches_the_oracle():
             Jr, ar = oracle.actor_cost_table(c, s, table, obs[e], xs[e], ctrl.w_critic)
             assert np.max(np.abs(J[e] - Jr) / np.abs(Jr)) <= 1e-9
             assert am[e] == int(np.argmin(J[e]))
+
+
+@pytest.mark.gpu
+def test_readme_quick_tour_runs_as_printed():
+    """The README's quick-tour block, executed as printed (only the batch and the episode length are shrunk)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    md = open(os.path.join(ROOT, "README.md")).read()
+    src = next(b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "ClosedLoopEngine" in b)
+    assert "size=(65536, 3)" in src and "t1=10.0" in src
+    src = src.replace("size=(65536, 3)", "size=(600, 3)").replace("t1=10.0", "t1=0.3")
+    ns = {}
+    exec(src, ns)
+    res, rows, ckpt = ns["res"], ns["rows"], ns["ckpt"]
+    assert res["y"].shape == (600, 3) and np.all(res["status"] == 1) and np.all(res["t"] >= 0.3)
+    assert rows.shape[1] == 8 and rows.shape[0] == int(res["nsteps"][7]) // 4 and rows[-1, 0] <= res["t"][7]
+    assert ckpt["blob"].numel() > 0 and ckpt["E"] == 600
