@@ -654,8 +654,8 @@ def test_empty_batch_is_a_no_op(rb):
     ops.nominal_ni(sysd, y, 0.5, a)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_host_staged_loop_equals_resident_loop(rb, graph):
+@pytest.mark.parametrize("graph,actor", [(False, "candidates"), (True, "candidates"), (True, "opt")])
+def test_host_staged_loop_equals_resident_loop(rb, graph, actor):
     """engine.HostStagedLoop (lane state owned by pinned host memory, several environment blocks on their own
     streams, optionally replayed as one CUDA graph per step) takes exactly the same steps as the device-resident
     ClosedLoopEngine: identical state, clocks, counters and picks on every lane after every control interval."""
@@ -664,7 +664,7 @@ def test_host_staged_loop_equals_resident_loop(rb, graph):
     p = PRESET[name]
     x0 = random_states(name, E, 71)
     cand = random_cands(name, (E, C_), N, 72)
-    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.4, R1=p["R1_diag"])
+    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.4, R1=p["R1_diag"], actor=actor)
     ref = ClosedLoopEngine(name, x0, cand, **kw)
     loop = HostStagedLoop(name, x0, cand, nchunks=3, **kw)
     if graph:
