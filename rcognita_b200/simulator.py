@@ -131,13 +131,32 @@ class Simulator:
         state = self.state_full
         return self.t, state, self.sys_out(state), state
 
-    def reset(self, literal=False):
+    def reset(self, literal=False, mask=None):
         """Documented intent of ``Simulator.reset`` (multi-episode runs): restore state_full_init, t0,
         f(t0, y0) and h_abs = first_step.  ``literal=True`` reproduces what the reference's code
         actually does (simulator.py:197-201): only the clock and the status are rewound, the state,
-        FSAL derivative and step size carry over."""
+        FSAL derivative and step size carry over.
+        ``mask`` ([E] bool / int, numpy or tensor): re-initialise only those environments (a batch whose episodes end at
+        different times restarts the finished lanes and leaves the others untouched); the restarted lanes get
+        f = fun(t0, y0) with the system's current action of that lane, like a freshly constructed RK45."""
+        if mask is None:
+            if literal:
+                self._t.fill_(self.t0)
+                self._status.fill_(_C.RUNNING)
+            else:
+                self._construct_solver()
+            return
+        sel = torch.as_tensor(mask, device=self._y.device).reshape(-1) != 0
+        if sel.numel() != self.E:
+            raise ValueError(f"mask must have {self.E} entries")
+        self._t.masked_fill_(sel, self.t0)
+        self._status.masked_fill_(sel, _C.RUNNING)
         if literal:
-            self._t.fill_(self.t0)
-            self._status.fill_(_C.RUNNING)
-        else:
-            self._construct_solver()
+            return
+        self._y.copy_(torch.where(sel[None, :], self._y0, self._y))
+        self._h.masked_fill_(sel, self.first_step)
+        self._nfev.masked_fill_(sel, 1)
+        act = self.sys._action_soa.clone()                 # rcg_rhs clips in place: only the restarted lanes may be touched
+        f0 = ops.rhs(self.sys._sysd, self._y, act)
+        self._f.copy_(torch.where(sel[None, :], f0, self._f))
+        self.sys._action_soa.copy_(torch.where(sel[None, :], act, self.sys._action_soa))

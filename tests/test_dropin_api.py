@@ -347,3 +347,45 @@ def test_engine_with_critic_fit_equals_class_loop(rb, name, mode, cs, N, t1):
     assert np.array_equal(sim._y.t().cpu().numpy(), got["y"])
     assert rel_err(ctrl._accum.cpu().numpy(), got["accum"]) <= 1e-12       # fused vs separate accumulation kernels
     assert np.array_equal(ctrl._w_critic.t().cpu().numpy(), got["w_critic"])
+
+
+@gpu
+def test_simulator_masked_reset(rb):
+    """Simulator.reset(mask=...): the selected environments restart exactly like a freshly constructed simulator
+    (state, t0, first_step, f(t0, y0) with the lane's current action), the others are left untouched bit for bit."""
+    import oracle
+    from rcognita_b200 import simulator, systems
+    bn = np.array([[-25, 25], [-5, 5]], dtype=float)
+    rng = np.random.default_rng(4)
+    E = 40
+    x0 = np.stack([rng.uniform(-5, 5, E), rng.uniform(-5, 5, E), rng.uniform(-3, 3, E)], 1)
+
+    def make():
+        sy = systems.Sys3WRobotNI(sys_type="diff_eqn", dim_state=3, dim_input=2, dim_output=3, dim_disturb=2, pars=[],
+                                  ctrl_bnds=bn, is_dyn_ctrl=0, is_disturb=0, pars_disturb=[])
+        sim = simulator.Simulator("diff_eqn", sy.closed_loop_rhs, sy.out, x0, disturb_init=[], action_init=np.zeros(2), t0=0,
+                                  t1=1.0, dt=0.01, max_step=0.005, first_step=1e-6, atol=1e-5, rtol=1e-3, is_disturb=0, is_dyn_ctrl=0)
+        return sy, sim
+    sy, sim = make()
+    act = rng.uniform(bn[:, 0] * 1.4, bn[:, 1] * 1.4, size=(E, 2))        # some outside the bounds
+    for _ in range(7):
+        sim.sim_step()
+        sy.receive_action(act)
+    before = [t.clone() for t in (sim._y, sim._f, sim._t, sim._h, sim._status, sim._nfev)]
+    mask = np.zeros(E, dtype=bool)
+    mask[[1, 5, 6, 33]] = True
+    sim.reset(mask=mask)
+    keep = torch.as_tensor(~mask, device="cuda")
+    for a, b in zip(before, (sim._y, sim._f, sim._t, sim._h, sim._status, sim._nfev)):
+        assert torch.equal(a[..., keep], b[..., keep])
+    m = torch.as_tensor(mask, device="cuda")
+    assert torch.equal(sim._y[:, m].t().cpu(), torch.as_tensor(x0[mask]))
+    assert bool((sim._t[m] == 0).all()) and bool((sim._h[m] == 1e-6).all()) and bool((sim._nfev[m] == 1).all())
+    s = oracle.make_sys("3wrobotNI", [], bn)
+    for e in np.flatnonzero(mask):
+        f = oracle.closed_loop_rhs(s, x0[e], act[e].copy())
+        f = f[0] if isinstance(f, tuple) else f
+        assert np.max(np.abs(sim._f[:, e].cpu().numpy() - np.asarray(f))) <= 1e-12 * max(1.0, np.max(np.abs(f)))
+    for _ in range(3):
+        sim.sim_step()                                                   # restarted and running lanes step on together
+    assert bool((sim._status == 0).all())
