@@ -10,7 +10,6 @@ Shard boundaries are multiples of ``BLOCK`` environments so that block-keyed syn
 """
 from __future__ import annotations
 
-import numpy as np
 
 BLOCK = 1024        # shard granularity (environments)
 

@@ -13,7 +13,6 @@ as CUDA tensors (views of the solver state, invalidated by the next ``sim_step``
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from . import _C, ops
