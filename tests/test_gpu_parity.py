@@ -580,6 +580,34 @@ def test_fp32_twin_tolerance(rb):
         assert am[e] == ar or abs(Jr[am[e]] - Jr[ar]) <= 2e-5 * abs(Jr[ar])
 
 
+@pytest.mark.parametrize("name,mode,N,C_", [("3wrobotNI", "MPC", 6, 64), ("3wrobotNI", "MPC", 7, 64), ("3wrobot", "RQL", 20, 32),
+                                           ("2tank", "SQL", 13, 96)])
+def test_fp32_twin_per_env_candidates(rb, name, mode, N, C_):
+    """_f32 twins of the TMA-staged kernels (specialised and runtime horizons, lean and general objectives) with
+    per-environment candidates: costs within 5e-5 relative of the fp64 kernels on the same inputs."""
+    _, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E = 517
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], critic_struct="quad-nomix",
+                            R1=p["R1_diag"], observation_target=p["target"])
+    obs = soa(random_states(name, E, 61))
+    g = torch.Generator(device="cuda").manual_seed(62)
+    b = torch.tensor(p["bnds"], device="cuda", dtype=torch.float64)
+    cand = torch.empty((N * m, E * C_), device="cuda", dtype=torch.float64)
+    for k in range(N * m):
+        j = k % m
+        cand[k] = b[j, 0] + (b[j, 1] - b[j, 0]) * torch.rand((E * C_,), device="cuda", dtype=torch.float64, generator=g)
+    w = dev(np.random.default_rng(63).uniform(0.5, 2, size=n + m))
+    J64, am64, _ = ops.actor_cost(sysd, obj, obs, obs, cand, True, C_, w_critic=w)
+    f32 = torch.float32
+    J32, am32, _ = ops.actor_cost(sysd, obj, obs.to(f32), obs.to(f32), cand.to(f32), True, C_, w_critic=w.to(f32))
+    rel = ((J32.double() - J64).abs() / J64.abs().clamp_min(1e-12)).max().item()
+    assert rel <= 5e-5, rel
+    assert (am32 == am64).double().mean().item() >= 0.98
+
+
 def test_errors_are_loud(rb):
     rcognita_b200, _C, ops = rb
     p = PRESET["3wrobotNI"]
