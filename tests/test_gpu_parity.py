@@ -285,6 +285,30 @@ def test_actor_tma_kernel_matches_direct_kernel(rb, name, mode, cs, N, E, C_):
         assert rel_err(J[e], Jr) <= COST_RTOL
 
 
+@pytest.mark.parametrize("pred_step", [0.01, 0.02, 0.06, 0.2])
+@pytest.mark.parametrize("per_env", [False, True])
+def test_actor_cost_heading_rotation_paths(rb, pred_step, per_env):
+    """The predictor advances (sin, cos) of the heading by rotation: truncated polynomials for |h * omega| <= 1/8 (the
+    presets), the full small-angle polynomials up to pi/4 (pred_step 0.06: most candidates), a full sincos beyond
+    (0.2).  All three paths must give the reference's cost to 1e-9, in the TMA-staged and the direct kernel."""
+    _, _C, ops = rb
+    name, N, C_, E = "3wrobotNI", 6, 64, 300
+    p = PRESET[name]
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    kw = dict(mode="MPC", Nactor=N, pred_step_size=pred_step, R1=p["R1_diag"])
+    obj = _C.make_objective(3, 2, **kw)
+    s = oracle.make_sys(name, p["pars"], p["bnds"]); c = oracle.make_ctrl(3, 2, **kw)
+    obs = random_states(name, E, 81)
+    cand = random_cands(name, (E, C_) if per_env else (C_,), N, 82)
+    cd = dev(cand.transpose(2, 0, 1).reshape(2 * N, E * C_).copy()) if per_env else dev(cand.T.copy())
+    J, am, _ = ops.actor_cost(sysd, obj, soa(obs), soa(obs), cd, per_env, C_)
+    J, am = J.cpu().numpy(), am.cpu().numpy()
+    for e in range(0, E, 7):
+        Jr, ar = oracle.actor_cost_table(c, s, cand[e] if per_env else cand, obs[e], obs[e])
+        assert rel_err(J[e], Jr) <= COST_RTOL, (e, pred_step)
+        assert am[e] == ar or abs(Jr[am[e]] - Jr[ar]) <= 1e-12 * abs(Jr[ar])
+
+
 def test_argmin_ties_and_nan(rb):
     """np.argmin semantics: first minimum wins; NaN counts as minimal (first NaN wins)."""
     _, _C, ops = rb
