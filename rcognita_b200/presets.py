@@ -1,7 +1,7 @@
 """The presets' argument set and headless main loop (presets/main_3wrobot_NI.py, main_3wrobot.py, main_2tank.py)
 on top of the B200 engine.  Flag names, types and defaults are the reference's, including
 the ``type=bool`` quirk (any non-empty string is True; pass '' for False).  New flags select the batch:
-``--num_envs``, ``--num_candidates``, ``--seed``, ``--state_spread``.
+``--num_envs``, ``--num_candidates``, ``--seed``, ``--state_spread``, ``--candidate_table``.
 
 Differences: ``--is_visualization`` has no effect beyond a notice (the matplotlib animators are outside the hot
 path; the loop run is the headless one, presets/main_3wrobot_NI.py:411-462); ``--ctrl_mode nominal`` runs the
@@ -106,6 +106,8 @@ def make_parser(system: str) -> argparse.ArgumentParser:
     p.add_argument('--num_envs', type=int, default=1, help='environments stepped in parallel (1 = the reference\'s shapes)')
     p.add_argument('--num_candidates', type=int, default=256, help='candidate action sequences of the arg-min actor')
     p.add_argument('--seed', type=int, default=1, help='seed of the candidate table (and of the initial-state spread)')
+    p.add_argument('--candidate_table', type=str, default='random', choices=['random', 'structured'],
+                   help='candidate action sequences: uniform random, or constant sequences on a log-spaced grid + random fill')
     p.add_argument('--actor', type=str, default='candidates', choices=['candidates', 'opt'],
                    help='stand-in for the SLSQP actor: arg-min over candidates, or the batched bounded minimiser')
     p.add_argument('--opt_start', type=str, default='argmin', choices=['argmin', 'init'],
@@ -152,6 +154,7 @@ def build(system: str, args):
                                       critic_period=critic_period, critic_struct=args.critic_struct,
                                       stage_obj_struct=args.stage_obj_struct, stage_obj_pars=[R1, R2][:1 if args.stage_obj_struct == 'quadratic' else 2],
                                       observation_target=S["target"], num_candidates=args.num_candidates, seed=args.seed,
+                                      candidates='structured' if args.candidate_table == 'structured' else None,
                                       actor=args.actor, opt_start=args.opt_start, opt_iters=args.opt_iters)
     my_sim = simulator.Simulator(sys_type="diff_eqn", closed_loop_rhs=my_sys.closed_loop_rhs, sys_out=my_sys.out,
                                  state_init=x0, disturb_init=[], action_init=np.zeros(m), t0=0, t1=args.t1, dt=args.dt,

@@ -111,6 +111,23 @@ def test_product_never_touches_the_oracle():
     assert "oracle" not in out
 
 
+def test_structured_candidates_table():
+    from rcognita_b200.controllers import structured_candidates
+    for bnds, N, C in (([[-25, 25], [-5, 5]], 6, 256), ([[0, 1]], 8, 64), ([[-300, 300], [-100, 100]], 10, 100), ([[-25, 25], [-5, 5]], 3, 16)):
+        b = np.array(bnds, dtype=float)
+        m = b.shape[0]
+        tab = structured_candidates(bnds, N, C, seed=3)
+        assert tab.shape == (C, N * m)
+        assert np.all(tab >= np.tile(b[:, 0], N)) and np.all(tab <= np.tile(b[:, 1], N))
+        const = tab[np.all(tab.reshape(C, N, m) == tab.reshape(C, N, m)[:, :1, :], axis=(1, 2))]
+        assert len(const) >= min(C, 9)                                  # the grid part: constant sequences
+        mid = 0.5 * (b[:, 0] + b[:, 1])
+        assert any(np.allclose(r[:m], mid) for r in const)              # holding the mid-point is a candidate
+        if C >= 3 ** m:
+            assert any(np.allclose(r[:m], b[:, 1]) for r in const) and any(np.allclose(r[:m], b[:, 0]) for r in const)
+        assert np.array_equal(tab, structured_candidates(bnds, N, C, seed=3))
+
+
 def test_shard_range_partition():
     from rcognita_b200 import shard
     for E in (1024, 65536, 1048576, 5 * 1024):
