@@ -222,8 +222,9 @@ class ClosedLoopEngine:
     def _first_step(self):
         ops.rk45_step(self.sysd, self.sol, self.y, self.f, self.t, self.h_abs, self.status, self.action, nfev=self.nfev)
         self.nsteps += 1
-        flag = (self.t - self.ctrl_clock >= self.sampling_time).to(torch.int32)
-        self.sample_flag.copy_(flag)
+        # compute_action's clock test (controllers.py:1440-1442): sets sample_flag and moves ctrl_clock where it fires
+        ops.ctrl_sample(self.t, self.ctrl_clock, self.sampling_time, mask_out=self.sample_flag)
+        flag = self.sample_flag
         self.action.copy_(self.action_init[:, None].expand(self.m, self.E))
         hold = torch.empty((self.E,), dtype=self.dtype, device=self.device)
         if self.dtype == torch.float64:
@@ -232,7 +233,6 @@ class ClosedLoopEngine:
             hold = ops.stage_obj(self.obj, self.n, self.m, self.y.double(), self.action.double()).to(self.dtype)
         self.accum += hold * self.sampling_time * (1 - flag).to(self.dtype)
         if bool(flag.any()):
-            self.ctrl_clock.copy_(torch.where(flag.bool(), self.t, self.ctrl_clock))
             self.nsamples += self.sample_flag
             self._actor()                                   # state_sys is still y0 here
         self.state_sys.copy_(self.y)

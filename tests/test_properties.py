@@ -72,13 +72,15 @@ torch = pytest.importorskip("torch")
 
 
 @pytest.mark.gpu
-@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(name=st.sampled_from(SYSTEMS), mode=st.sampled_from(["MPC", "RQL", "SQL"]), N=st.sampled_from([1, 3, 6, 7, 10, 13]),
        E=st.integers(1, 700), C=st.sampled_from([1, 2, 8, 32, 33, 96, 256]), per_env=st.booleans(), seed=st.integers(0, 2**31 - 1))
 def test_actor_cost_lane_permutation_and_split_invariance(name, mode, N, E, C, per_env, seed):
-    """rcg_actor_cost on a batch, on a random permutation of its environments, and on its two halves: identical costs,
-    arg-min and J_min per environment, bit for bit -- whatever kernel variant (TMA / direct / runtime horizon) each call
-    happens to select."""
+    """rcg_actor_cost on a batch, on a random permutation of its environments, and on its two halves: the same costs,
+    arg-min and J_min per environment.  A permutation keeps the launch geometry, so it must be bit-identical; halving the
+    batch can select another kernel variant (the TMA-staged kernels need an even number of candidate columns), and two
+    variants are separate compilations whose FMA contraction may differ: costs then agree to 1e-12 and the arg-min up to
+    such ties."""
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device is visible")
     from rcognita_b200 import _C, ops
@@ -108,4 +110,7 @@ def test_actor_cost_lane_permutation_and_split_invariance(name, mode, N, E, C, p
     if E >= 2:
         h = E // 2
         a, b2 = run(np.arange(h)), run(np.arange(h, E))
-        assert np.array_equal(np.concatenate([a[0], b2[0]]), full[0]) and np.array_equal(np.concatenate([a[1], b2[1]]), full[1])
+        J2, am2 = np.concatenate([a[0], b2[0]]), np.concatenate([a[1], b2[1]])
+        assert np.max(np.abs(J2 - full[0]) / np.maximum(np.abs(full[0]), 1e-300)) <= 1e-12
+        for e in np.flatnonzero(am2 != full[1]):
+            assert abs(full[0][e, am2[e]] - full[0][e, full[1][e]]) <= 1e-12 * abs(full[0][e, full[1][e]])
