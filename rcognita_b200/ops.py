@@ -180,6 +180,9 @@ def _opt_workspace(sysd, obj, E, S, device, workspace=None):
     return workspace, need
 
 
+opt_workspace = _opt_workspace          # public name: (tensor, bytes) of the scratch rcg_actor_opt / rcg_actor_grad need
+
+
 def actor_grad(sysd, obj, state_sys, obs, sqn, S=1, w_critic=None, w_per_env=False, workspace=None):
     """``_actor_cost`` and its exact gradient for E x S action sequences: ``sqn`` ``[N*m, E*S]`` ->
     ``(J [E*S], grad [N*m, E*S])`` (adjoint of the Euler rollout; the reference's SLSQP uses forward differences)."""
