@@ -120,3 +120,24 @@ def test_committed_fixtures_are_what_the_live_reference_produces(mg):
     for c in nom_cases[:10]:
         nom = mg.controllers.CtrlNominal3WRobotNI(ctrl_gain=c["gain"], ctrl_bnds=bn, t0=0, sampling_time=0.01)
         assert mg.L(nom.compute_action(1.0, np.array(c["obs"]))) == c["action"]
+
+
+@pytest.mark.parametrize("name,mode,N,t1,seed", [("3wrobotNI", "MPC", 5, 0.6, 5), ("2tank", "MPC", 4, 4.0, 6), ("3wrobot", "MPC", 3, 0.3, 7)])
+def test_oracle_closed_loop_equals_live_reference_loop_on_fresh_inputs(mg, name, mode, N, t1, seed):
+    """The reference's own loop (Simulator + CtrlOptPred, `_actor_optimizer` replaced by its `_actor_cost` on a candidate
+    table + np.argmin -- SURVEY App. A.4) from a FRESH random start and table against orc_closed_loop: same number of
+    solver steps and controller samples, final state and accumulated objective to 1e-9."""
+    n, m = DIMS[name]
+    P = PRESET[name]
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-3, 3, size=n)
+    g = mg.closed_loop(name, mode, N, t1, C=24, seed=seed, x0=x0)
+    rows = np.array(g["rows"])
+    s = oracle.make_sys(name, P["pars"], P["bnds"])
+    ct = oracle.make_ctrl(n, m, mode=mode, Nactor=N, pred_step_size=P["dt"] * P["psm"], R1=P["R1_diag"],
+                          observation_target=P["target"])
+    ref = oracle.closed_loop(ct, s, x0[None, :], np.array(g["cand"]), g["action_init"], P["dt"], 0.0, t1, P["dt"] / 2)
+    assert int(ref["nsteps"][0]) == rows.shape[0] and int(ref["nsamples"][0]) == len(g["picks"])
+    assert abs(ref["t"][0] - rows[-1, 0]) <= 1e-12 * t1
+    assert np.max(np.abs(ref["y"][0] - rows[-1, 1:1 + n]) / np.maximum(np.abs(rows[-1, 1:1 + n]), 1e-2)) <= 1e-9
+    assert abs(ref["accum"][0] - rows[-1, 1 + n + m]) <= 1e-9 * abs(rows[-1, 1 + n + m])
