@@ -141,3 +141,43 @@ def test_oracle_closed_loop_equals_live_reference_loop_on_fresh_inputs(mg, name,
     assert abs(ref["t"][0] - rows[-1, 0]) <= 1e-12 * t1
     assert np.max(np.abs(ref["y"][0] - rows[-1, 1:1 + n]) / np.maximum(np.abs(rows[-1, 1:1 + n]), 1e-2)) <= 1e-9
     assert abs(ref["accum"][0] - rows[-1, 1 + n + m]) <= 1e-9 * abs(rows[-1, 1 + n + m])
+
+
+@pytest.mark.parametrize("name,mode,cs,N,scale,seed", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 4.0, 11), ("3wrobotNI", "RQL", "quadratic", 5, 0.3, 12),
+    ("3wrobot", "MPC", "quad-nomix", 5, 2.0, 13), ("3wrobot", "SQL", "quad-nomix", 6, 0.5, 14),
+    ("2tank", "SQL", "quad-lin", 8, 1.0, 15), ("2tank", "MPC", "quad-nomix", 10, 0.2, 16)])
+def test_restated_minimiser_reaches_live_slsqp_minimum_on_fresh_problems(mg, name, mode, cs, N, scale, seed):
+    """The reference's `_actor_optimizer` (SLSQP) run live on a FRESH problem, against the oracle's restatement of the
+    batched minimiser from the same start point: minimum reached or beaten (SLSQP's own tolerance as slack), feasible."""
+    n, m = DIMS[name]
+    P = PRESET[name]
+    rng = np.random.default_rng(seed)
+    tgt = np.array(P["target"]) if len(P["target"]) else 0.0
+    x_sys = rng.uniform(-1, 1, size=n) * scale + tgt
+    ob = x_sys + rng.normal(size=n) * 0.005 * scale
+    my_sys = mg.make_sys(name)
+    ctrl = mg.make_ctrl(name, my_sys, mode, N, critic_struct=cs, state_sys=x_sys)
+    w = rng.uniform(0, 2, size=ctrl.dim_critic)
+    ctrl.w_critic = w
+    rec = {}
+    orig = mg.controllers.minimize
+
+    def wrapped(fun, x0, **kw):
+        rec["res"] = orig(fun, x0, **kw)
+        return rec["res"]
+    mg.controllers.minimize = wrapped
+    try:
+        ctrl._actor_optimizer(ob)
+    finally:
+        mg.controllers.minimize = orig
+    J_ref = float(ctrl._actor_cost(np.asarray(rec["res"].x, dtype=float), ob))
+    s = oracle.make_sys(name, P["pars"], P["bnds"])
+    ct = oracle.make_ctrl(n, m, mode=mode, Nactor=N, pred_step_size=float(ctrl.pred_step_size), critic_struct=cs,
+                          R1=np.diag(np.array(P["R1_diag"], dtype=float)), observation_target=P["target"])
+    x, J, iters, nfev = oracle.actor_opt(ct, s, np.asarray(ctrl.action_sqn_init, dtype=float), ob, x_sys, w, max_iter=300,
+                                         pg_tol=1e-7, f_tol=1e-12)
+    b = np.array(P["bnds"], dtype=float)
+    assert np.all(x >= np.tile(b[:, 0], N)) and np.all(x <= np.tile(b[:, 1], N))
+    assert abs(J - float(ctrl._actor_cost(x, ob))) <= 1e-9 * max(abs(J), 1e-9)
+    assert J <= J_ref + 1e-7 * max(abs(J_ref), 1.0), (J, J_ref, iters, rec["res"].nfev)
