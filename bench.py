@@ -335,6 +335,23 @@ def run_b200(args):
                             "rcg_actor_opt (exact adjoint gradient, projected L-BFGS from action_sqn_init, one bounded "
                             "minimisation of _actor_cost per environment and control interval)"}
         del eng2
+        if not args.no_cpu_baseline:
+            # the checker's restatement of the same minimiser on the host cores (bounded sample), like cpu_baseline
+            import oracle
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)          # all host cores, like the cpu_baseline leg below
+            ns = min(E, 32768)
+            so = oracle.make_sys(SYSTEM, [], BNDS)
+            co = oracle.make_ctrl(3, 2, mode="MPC", Nactor=N, pred_step_size=DT, R1=R1_DIAG)
+            xs = np.ascontiguousarray(np.asarray(x0[:ns], dtype=np.float64))
+            sq0 = np.tile(np.asarray(ACTION_INIT, dtype=np.float64), N)
+            oracle.actor_opt_batch(co, so, sq0, xs[:1024], pg_tol=1e-4, f_tol=1e-8)            # thread pool warm-up
+            tc = time.time()
+            oracle.actor_opt_batch(co, so, sq0, xs, pg_tol=1e-4, f_tol=1e-8)
+            tc = time.time() - tc
+            actor_opt["cpu_port"] = {"solves_per_s": ns / tc, "cores": oracle.num_threads(), "kind": "port",
+                                     "sample": f"{ns} minimisations from action_sqn_init at the initial states "
+                                               "(oracle/rcg_oracle_opt.c, C + OpenMP)"}
 
     if rank != 0:
         if world > 1:

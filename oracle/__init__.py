@@ -106,6 +106,9 @@ def lib():
         L.orc_actor_opt.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                     ip, ip]
         L.orc_actor_opt.restype = C.c_double
+        L.orc_actor_opt_batch.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, dp, dp, C.c_int, C.c_double,
+                                          C.c_double, C.c_int, dp]
+        L.orc_actor_opt_batch.restype = C.c_longlong
         L.orc_nominal_ni.argtypes = [C.c_double, C.POINTER(SysT), dp, dp]
         L.orc_nominal_ni.restype = None
         L.orc_argmin.argtypes = [dp, C.c_int]
@@ -288,6 +291,18 @@ def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_
     J = lib().orc_actor_opt(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp,
                             int(max_iter), float(pg_tol), float(f_tol), C.byref(it), C.byref(nf))
     return a, J, it.value, nf.value
+
+
+def actor_opt_batch(c, s, x_init, states, w_critic=None, max_iter=300, pg_tol=1e-7, f_tol=1e-12, nthreads=0):
+    """orc_actor_opt for every row of ``states`` [E, n] (observation = state_sys), OpenMP over the problems.
+    Returns (J [E], gradient evaluations)."""
+    xi, xip = _d(np.asarray(x_init, dtype=np.float64).reshape(-1))
+    st, stp = _d(np.atleast_2d(states))
+    w, wp = (None, _null()) if w_critic is None else _d(w_critic)
+    J = np.zeros(st.shape[0])
+    g = lib().orc_actor_opt_batch(C.byref(c), C.byref(s), st.shape[0], xip, stp, wp, int(max_iter), float(pg_tol), float(f_tol),
+                                  int(nthreads), J.ctypes.data_as(C.POINTER(C.c_double)))
+    return J, int(g)
 
 
 def nominal_ni(ctrl_gain, s, observation):

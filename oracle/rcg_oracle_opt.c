@@ -15,6 +15,9 @@
  */
 #include <math.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "rcg_oracle.h"
 
@@ -271,6 +274,31 @@ double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const d
     if (iters_out) *iters_out = iters;
     if (nfev_out) *nfev_out = nfev;
     return J;
+}
+
+/* Batch driver of orc_actor_opt for the CPU baseline of bench.py's actor_optimizer block: E independent problems
+ * (observation = state_sys = row e of `states` [E, n], the same start point x_init [Nactor*m] and weights for all),
+ * OpenMP over the problems.  J_out [E]; returns the total number of gradient evaluations. */
+long long orc_actor_opt_batch(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *x_init, const double *states,
+                              const double *w_critic, int max_iter, double pg_tol, double f_tol, int nthreads,
+                              double *J_out)
+{
+    const int n = s->n, L = c->Nactor * s->m;
+    long long grads = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : grads)
+    for (int e = 0; e < E; ++e) {
+        double x[ORC_OPT_LMAX];
+        int it = 0, nf = 0;
+        memcpy(x, x_init, sizeof(double) * (size_t)L);
+        J_out[e] = orc_actor_opt(c, s, x, states + (long)e * n, states + (long)e * n, w_critic, max_iter, pg_tol, f_tol, &it, &nf);
+        grads += it + 1;
+    }
+    return grads;
 }
 
 /* ------------------------------------------------- CtrlNominal3WRobotNI (nominal parking controller) */
