@@ -12,7 +12,7 @@ from golden_util import DIMS, PRESET
 SYSTEMS = ["3wrobotNI", "3wrobot", "2tank"]
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(nb=st.integers(1, 4096), world=st.integers(1, 64))
 def test_shard_range_partitions_the_batch(nb, world):
     from rcognita_b200 import shard
@@ -26,7 +26,7 @@ def test_shard_range_partitions_the_batch(nb, world):
     assert max(sizes) - min(sizes) <= shard.BLOCK and sizes == sorted(sizes, reverse=True)
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(st.lists(st.one_of(st.floats(-1e6, 1e6), st.just(float("nan")), st.just(float("inf")), st.just(-0.0), st.just(0.0)),
                 min_size=1, max_size=70))
 def test_oracle_argmin_is_numpy_argmin(vals):
@@ -34,7 +34,7 @@ def test_oracle_argmin_is_numpy_argmin(vals):
     assert oracle.argmin(J) == int(np.argmin(J))
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(name=st.sampled_from(SYSTEMS), mode=st.sampled_from(["MPC", "RQL", "SQL"]),
        cs=st.sampled_from(["quad-lin", "quadratic", "quad-nomix", "quad-mix"]), N=st.integers(1, 9),
        gamma=st.sampled_from([1.0, 0.9]), seed=st.integers(0, 2**31 - 1))
