@@ -106,6 +106,9 @@ def lib():
         L.orc_actor_opt.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                     ip, ip]
         L.orc_actor_opt.restype = C.c_double
+        L.orc_actor_opt_hybrid.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_int, C.c_double,
+                                           C.c_double, ip, ip]
+        L.orc_actor_opt_hybrid.restype = C.c_double
         L.orc_actor_opt_batch.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, dp, dp, C.c_int, C.c_double,
                                           C.c_double, C.c_int, dp]
         L.orc_actor_opt_batch.restype = C.c_longlong
@@ -291,6 +294,20 @@ def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_
     J = lib().orc_actor_opt(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp,
                             int(max_iter), float(pg_tol), float(f_tol), C.byref(it), C.byref(nf))
     return a, J, it.value, nf.value
+
+
+def actor_opt_hybrid(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_sweeps=25, max_iter=300,
+                     pg_tol=1e-7, f_tol=1e-12):
+    """Control-limited Gauss-Newton (iLQR) sweeps, then the L-BFGS iteration from there (rcg_oracle_opt.c): groundwork
+    for the next optimiser kernel.  Returns (x, J, sweeps, lbfgs_iters)."""
+    a = np.array(action_sqn_init, dtype=np.float64).reshape(-1).copy()
+    o, op = _d(observation)
+    x, xp = _d(state_sys)
+    w, wp = (None, _null()) if w_critic is None else _d(w_critic)
+    sw, it = C.c_int(0), C.c_int(0)
+    J = lib().orc_actor_opt_hybrid(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp, int(max_sweeps),
+                                   int(max_iter), float(pg_tol), float(f_tol), C.byref(sw), C.byref(it))
+    return a, J, sw.value, it.value
 
 
 def actor_opt_batch(c, s, x_init, states, w_critic=None, max_iter=300, pg_tol=1e-7, f_tol=1e-12, nthreads=0):

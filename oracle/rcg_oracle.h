@@ -131,6 +131,9 @@ double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *act
 double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
                      const double *state_sys, const double *w_critic, int max_iter, double pg_tol, double f_tol,
                      int *iters_out, int *nfev_out);
+double orc_actor_opt_hybrid(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
+                            const double *state_sys, const double *w_critic, int max_sweeps, int max_iter, double pg_tol,
+                            double f_tol, int *sweeps_out, int *iters_out);
 long long orc_actor_opt_batch(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *x_init, const double *states,
                               const double *w_critic, int max_iter, double pg_tol, double f_tol, int nthreads,
                               double *J_out);

@@ -340,3 +340,302 @@ void orc_nominal_ni(double ctrl_gain, const orc_sys_t *s, const double *obs, dou
     if (s->has_bnds)
         for (int k = 0; k < 2; ++k) action[k] = clipd(action[k], s->lo[k], s->hi[k]);
 }
+
+/* ------------------------------------------------- control-limited Gauss-Newton (iLQR) sweeps + L-BFGS hand-over
+ *
+ * Groundwork for the successor of the projected L-BFGS kernel (numpy prototype:
+ * tools/ilqr_prototype.py).  Every stage term of _actor_cost is exactly quadratic in z = [obs - shift, action]
+ * (stage_obj 'quadratic': z^T R1 z scaled by gamma**k; the four critic structures: a quadratic form in chi, or in the
+ * raw observation for quad-mix, plus a linear part for quad-lin), so a reverse Riccati pass over the horizon with the
+ * linearised Euler step gives a Newton-like step with O(n^2) state; the box on the actions is handled per stage by a
+ * clamped Newton step (m <= 2: the 3^m active sets are enumerated), Q_aa is regularised (Levenberg-Marquardt), the
+ * forward pass backtracks on the TRUE cost (orc_actor_cost).  At most max_sweeps sweeps; a start that is already
+ * stationary (projected-gradient test) costs none; four failed forward passes in a row -- the indefinite critics --
+ * hand over to orc_actor_opt, which also polishes the result.  'biquadratic' stage costs are not quadratic: L-BFGS only. */
+static void stage_quad(const orc_ctrl_t *c, int n, int m, int use_critic, double gk, const double *w, double *H, double *g0,
+                       double *shift)
+{
+    const int p = n + m;
+    memset(H, 0, sizeof(double) * ORC_MAX_P * ORC_MAX_P);
+    memset(g0, 0, sizeof(double) * ORC_MAX_P);
+    for (int i = 0; i < n; ++i) shift[i] = c->has_target ? c->target[i] : 0.0;
+    if (!use_critic) {
+        for (int i = 0; i < p; ++i)
+            for (int j = 0; j < p; ++j) H[i * ORC_MAX_P + j] = gk * (c->R1[i * p + j] + c->R1[j * p + i]);
+        return;
+    }
+    int k = 0;
+    switch (c->critic_struct) {
+    case ORC_CRITIC_QUAD_LIN:
+    case ORC_CRITIC_QUADRATIC:
+        for (int i = 0; i < p; ++i)
+            for (int j = i; j < p; ++j) { H[i * ORC_MAX_P + j] += w[k]; H[j * ORC_MAX_P + i] += w[k]; ++k; }
+        if (c->critic_struct == ORC_CRITIC_QUAD_LIN)
+            for (int i = 0; i < p; ++i) g0[i] = w[k++];
+        break;
+    case ORC_CRITIC_QUAD_NOMIX:
+        for (int i = 0; i < p; ++i) H[i * ORC_MAX_P + i] = 2.0 * w[k++];
+        break;
+    default:                                    /* quad-mix: raw observation */
+        for (int i = 0; i < n; ++i) shift[i] = 0.0;
+        for (int i = 0; i < n; ++i) H[i * ORC_MAX_P + i] = 2.0 * w[k++];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < m; ++j) { H[i * ORC_MAX_P + n + j] += w[k]; H[(n + j) * ORC_MAX_P + i] += w[k]; ++k; }
+        for (int j = 0; j < m; ++j) H[(n + j) * ORC_MAX_P + n + j] = 2.0 * w[k++];
+        break;
+    }
+}
+
+/* (d f / d x, d f / d a) of _state_dyn (systems.py:308-323, :370-382, :412-419), row-major [n][n], [n][m]. */
+static void dyn_jac(const orc_sys_t *s, const double *x, const double *a, double *fx, double *fa)
+{
+    const int n = s->n, m = s->m;
+    memset(fx, 0, sizeof(double) * (size_t)(n * n));
+    memset(fa, 0, sizeof(double) * (size_t)(n * m));
+    if (s->sys_id == ORC_SYS_3WROBOT_NI) {
+        double sn, cs;
+        orc_sincos(x[2], &sn, &cs);
+        fx[0 * n + 2] = -a[0] * sn; fx[1 * n + 2] = a[0] * cs;
+        fa[0 * m + 0] = cs; fa[1 * m + 0] = sn; fa[2 * m + 1] = 1.0;
+    } else if (s->sys_id == ORC_SYS_3WROBOT) {
+        double sn, cs;
+        orc_sincos(x[2], &sn, &cs);
+        fx[0 * n + 2] = -x[3] * sn; fx[1 * n + 2] = x[3] * cs;
+        fx[0 * n + 3] = cs; fx[1 * n + 3] = sn; fx[2 * n + 4] = 1.0;
+        fa[3 * m + 0] = 1.0 / s->pars[0]; fa[4 * m + 1] = 1.0 / s->pars[1];
+    } else {
+        const double t1 = s->pars[0], t2 = s->pars[1], K1 = s->pars[2], K2 = s->pars[3], K3 = s->pars[4];
+        fx[0] = -1.0 / t1; fx[1 * n + 0] = K2 / t2; fx[1 * n + 1] = (-1.0 + 2.0 * K3 * x[1]) / t2;
+        fa[0] = K1 / t1;
+    }
+}
+
+/* argmin 1/2 d^T Q d + q^T d, lo <= d <= hi, m <= 2, Q positive definite: best feasible KKT point over the 3^m
+ * active sets.  free[j] = 1 where the minimiser is interior. */
+static void box_newton(int m, const double *Q, const double *q, const double *lo, const double *hi, double *d, int *fr)
+{
+    double bestv = INFINITY;
+    int found = 0;
+    const int npat = (m == 1) ? 3 : 9;
+    for (int pat = 0; pat < npat; ++pat) {
+        int st[2] = {pat % 3, pat / 3};
+        double t[2] = {0.0, 0.0};
+        for (int j = 0; j < m; ++j) t[j] = (st[j] == 1) ? lo[j] : (st[j] == 2) ? hi[j] : 0.0;
+        if (m == 1) {
+            if (st[0] == 0) t[0] = -q[0] / Q[0];
+        } else if (st[0] == 0 && st[1] == 0) {
+            const double det = Q[0] * Q[3] - Q[1] * Q[2];
+            t[0] = (-q[0] * Q[3] + q[1] * Q[1]) / det;
+            t[1] = (-q[1] * Q[0] + q[0] * Q[2]) / det;
+        } else if (st[0] == 0) {
+            t[0] = -(q[0] + Q[1] * t[1]) / Q[0];
+        } else if (st[1] == 0) {
+            t[1] = -(q[1] + Q[2] * t[0]) / Q[3];
+        }
+        int feas = 1;
+        for (int j = 0; j < m; ++j) feas = feas && isfinite(t[j]) && t[j] >= lo[j] - 1e-12 && t[j] <= hi[j] + 1e-12;
+        if (!feas) continue;
+        double v = 0.0;
+        for (int i = 0; i < m; ++i) {
+            v += q[i] * t[i];
+            for (int j = 0; j < m; ++j) v += 0.5 * t[i] * Q[i * m + j] * t[j];
+        }
+        if (v < bestv) {
+            bestv = v;
+            found = 1;
+            for (int j = 0; j < m; ++j) { d[j] = t[j]; fr[j] = (st[j] == 0); }
+        }
+    }
+    if (!found)
+        for (int j = 0; j < m; ++j) { d[j] = clipd(-q[j] / fmax(Q[j * m + j], 1e-12), lo[j], hi[j]); fr[j] = 0; }
+}
+
+double orc_actor_opt_hybrid(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
+                            const double *state_sys, const double *w_critic, int max_sweeps, int max_iter, double pg_tol,
+                            double f_tol, int *sweeps_out, int *iters_out)
+{
+    const int n = s->n, m = s->m, N = c->Nactor, L = N * m, P = ORC_MAX_P;
+    const double h = c->pred_step_size;
+    double lo[ORC_MAX_M], hi[ORC_MAX_M];
+    int sweeps = 0, iters = 0, nf = 0;
+    for (int j = 0; j < m; ++j) {
+        lo[j] = s->has_bnds ? s->lo[j] : -INFINITY;
+        hi[j] = s->has_bnds ? s->hi[j] : INFINITY;
+    }
+    for (int i = 0; i < L; ++i) x[i] = clipd(x[i], lo[i % m], hi[i % m]);
+    if (c->stage_struct == ORC_STAGE_QUADRATIC && max_sweeps > 0) {
+        static _Thread_local double X[ORC_MAX_NACTOR][ORC_MAX_N], kff[ORC_MAX_NACTOR][ORC_MAX_M],
+            Kfb[ORC_MAX_NACTOR][ORC_MAX_M][ORC_MAX_N], Un[ORC_OPT_LMAX], g[ORC_OPT_LMAX];
+        double H[ORC_MAX_P * ORC_MAX_P], g0[ORC_MAX_P], shift[ORC_MAX_N];
+        double J = orc_actor_grad(c, s, x, observation, state_sys, w_critic, g);
+        double pg = 0.0;
+        for (int i = 0; i < L; ++i) pg = fmax(pg, fabs(clipd(x[i] - g[i], lo[i % m], hi[i % m]) - x[i]));
+        double mu = 1e-6;
+        int stalls = 0;
+        while (pg > pg_tol && sweeps < max_sweeps) {
+            ++sweeps;
+            for (int i = 0; i < n; ++i) X[0][i] = state_sys[i];
+            for (int k = 1; k < N; ++k) {
+                double dd[ORC_MAX_N];
+                orc_state_dyn(s, X[k - 1], x + (k - 1) * m, dd);
+                for (int i = 0; i < n; ++i) X[k][i] = X[k - 1][i] + h * dd[i];
+            }
+            int ok = 0;
+            while (!ok) {                                  /* reverse pass; raise mu until every Q_aa is positive definite */
+                double Vx[ORC_MAX_N] = {0}, Vxx[ORC_MAX_N * ORC_MAX_N] = {0};
+                ok = 1;
+                for (int k = N - 1; k >= 0 && ok; --k) {
+                    const int use_critic = (c->mode == ORC_MODE_SQL) || (c->mode == ORC_MODE_RQL && k == N - 1);
+                    stage_quad(c, n, m, use_critic, pow(c->gamma, (double)k), w_critic, H, g0, shift);
+                    const double *ob = (k == 0) ? observation : X[k];
+                    const double *a = x + k * m;
+                    double z[ORC_MAX_P], gz[ORC_MAX_P];
+                    for (int i = 0; i < n; ++i) z[i] = ob[i] - shift[i];
+                    for (int j = 0; j < m; ++j) z[n + j] = a[j];
+                    for (int i = 0; i < n + m; ++i) {
+                        double acc = g0[i];
+                        for (int j = 0; j < n + m; ++j) acc += H[i * P + j] * z[j];
+                        gz[i] = acc;
+                    }
+                    double Qx[ORC_MAX_N], Qa[ORC_MAX_M], Qxx[ORC_MAX_N * ORC_MAX_N], Qax[ORC_MAX_M * ORC_MAX_N], Qaa[4];
+                    for (int i = 0; i < n; ++i) {
+                        Qx[i] = (k > 0) ? gz[i] : 0.0;
+                        for (int j = 0; j < n; ++j) Qxx[i * n + j] = (k > 0) ? H[i * P + j] : 0.0;
+                    }
+                    for (int j = 0; j < m; ++j) {
+                        Qa[j] = gz[n + j];
+                        for (int i = 0; i < n; ++i) Qax[j * n + i] = (k > 0) ? H[(n + j) * P + i] : 0.0;
+                        for (int l = 0; l < m; ++l) Qaa[j * m + l] = H[(n + j) * P + n + l];
+                    }
+                    if (k < N - 1) {
+                        double fx[ORC_MAX_N * ORC_MAX_N], fa[ORC_MAX_N * ORC_MAX_M], A[ORC_MAX_N * ORC_MAX_N], B[ORC_MAX_N * ORC_MAX_M];
+                        double VA[ORC_MAX_N * ORC_MAX_N], VB[ORC_MAX_N * ORC_MAX_M];
+                        dyn_jac(s, X[k], a, fx, fa);
+                        for (int i = 0; i < n; ++i)
+                            for (int j = 0; j < n; ++j) A[i * n + j] = (i == j ? 1.0 : 0.0) + h * fx[i * n + j];
+                        for (int i = 0; i < n; ++i)
+                            for (int j = 0; j < m; ++j) B[i * m + j] = h * fa[i * m + j];
+                        for (int i = 0; i < n; ++i) {
+                            for (int j = 0; j < n; ++j) {
+                                double acc = 0.0;
+                                for (int l = 0; l < n; ++l) acc += Vxx[i * n + l] * A[l * n + j];
+                                VA[i * n + j] = acc;
+                            }
+                            for (int j = 0; j < m; ++j) {
+                                double acc = 0.0;
+                                for (int l = 0; l < n; ++l) acc += Vxx[i * n + l] * B[l * m + j];
+                                VB[i * m + j] = acc;
+                            }
+                        }
+                        for (int i = 0; i < n; ++i) {
+                            for (int l = 0; l < n; ++l) Qx[i] += A[l * n + i] * Vx[l];
+                            for (int j = 0; j < n; ++j)
+                                for (int l = 0; l < n; ++l) Qxx[i * n + j] += A[l * n + i] * VA[l * n + j];
+                        }
+                        for (int j = 0; j < m; ++j) {
+                            for (int l = 0; l < n; ++l) Qa[j] += B[l * m + j] * Vx[l];
+                            for (int i = 0; i < n; ++i)
+                                for (int l = 0; l < n; ++l) Qax[j * n + i] += B[l * m + j] * VA[l * n + i];
+                            for (int q = 0; q < m; ++q)
+                                for (int l = 0; l < n; ++l) Qaa[j * m + q] += B[l * m + j] * VB[l * m + q];
+                        }
+                    }
+                    double Qr[4];
+                    for (int j = 0; j < m * m; ++j) Qr[j] = Qaa[j];
+                    for (int j = 0; j < m; ++j) Qr[j * m + j] += mu;
+                    const int pd = (m == 1) ? (Qr[0] > 0.0)
+                                            : (Qr[0] > 0.0 && Qr[0] * Qr[3] - 0.25 * (Qr[1] + Qr[2]) * (Qr[1] + Qr[2]) > 0.0);
+                    if (!pd) { ok = 0; break; }
+                    double dlo[ORC_MAX_M], dhi[ORC_MAX_M], d[ORC_MAX_M];
+                    int fr[ORC_MAX_M];
+                    for (int j = 0; j < m; ++j) { dlo[j] = lo[j] - a[j]; dhi[j] = hi[j] - a[j]; }
+                    box_newton(m, Qr, Qa, dlo, dhi, d, fr);
+                    double K[ORC_MAX_M * ORC_MAX_N] = {0};
+                    if (m == 1) {
+                        if (fr[0]) for (int i = 0; i < n; ++i) K[i] = -Qax[i] / Qr[0];
+                    } else if (fr[0] && fr[1]) {
+                        const double det = Qr[0] * Qr[3] - Qr[1] * Qr[2];
+                        for (int i = 0; i < n; ++i) {
+                            K[0 * n + i] = -(Qr[3] * Qax[0 * n + i] - Qr[1] * Qax[1 * n + i]) / det;
+                            K[1 * n + i] = -(Qr[0] * Qax[1 * n + i] - Qr[2] * Qax[0 * n + i]) / det;
+                        }
+                    } else if (fr[0]) {
+                        for (int i = 0; i < n; ++i) K[0 * n + i] = -Qax[0 * n + i] / Qr[0];
+                    } else if (fr[1]) {
+                        for (int i = 0; i < n; ++i) K[1 * n + i] = -Qax[1 * n + i] / Qr[3];
+                    }
+                    for (int j = 0; j < m; ++j) {
+                        kff[k][j] = d[j];
+                        for (int i = 0; i < n; ++i) Kfb[k][j][i] = K[j * n + i];
+                    }
+                    /* V_x = Q_x + K^T Q_aa d + K^T Q_a + Q_ax^T d;  V_xx = Q_xx + K^T Q_aa K + K^T Q_ax + Q_ax^T K */
+                    double Qd[ORC_MAX_M] = {0}, QK[ORC_MAX_M * ORC_MAX_N] = {0};
+                    for (int j = 0; j < m; ++j)
+                        for (int q = 0; q < m; ++q) {
+                            Qd[j] += Qaa[j * m + q] * d[q];
+                            for (int i = 0; i < n; ++i) QK[j * n + i] += Qaa[j * m + q] * K[q * n + i];
+                        }
+                    for (int i = 0; i < n; ++i) {
+                        double v = Qx[i];
+                        for (int j = 0; j < m; ++j) v += K[j * n + i] * (Qd[j] + Qa[j]) + Qax[j * n + i] * d[j];
+                        Vx[i] = v;
+                    }
+                    for (int i = 0; i < n; ++i)
+                        for (int l = 0; l < n; ++l) {
+                            double v = Qxx[i * n + l];
+                            for (int j = 0; j < m; ++j) v += K[j * n + i] * (QK[j * n + l] + Qax[j * n + l]) + Qax[j * n + i] * K[j * n + l];
+                            Vxx[i * n + l] = v;
+                        }
+                    for (int i = 0; i < n; ++i)
+                        for (int l = i + 1; l < n; ++l) {
+                            const double v = 0.5 * (Vxx[i * n + l] + Vxx[l * n + i]);
+                            Vxx[i * n + l] = v; Vxx[l * n + i] = v;
+                        }
+                }
+                if (!ok) {
+                    mu = fmax(mu * 10.0, 1e-6);
+                    if (mu > 1e12) break;
+                }
+            }
+            if (!ok) break;
+            /* forward pass with backtracking on the true cost */
+            double alpha = 1.0, Jn = J;
+            int improved = 0;
+            for (int bt = 0; bt < 12 && !improved; ++bt) {
+                double xs[ORC_MAX_N], dd[ORC_MAX_N];
+                for (int i = 0; i < n; ++i) xs[i] = state_sys[i];
+                for (int k = 0; k < N; ++k) {
+                    for (int j = 0; j < m; ++j) {
+                        double v = x[k * m + j] + alpha * kff[k][j];
+                        for (int i = 0; i < n; ++i) v += Kfb[k][j][i] * (xs[i] - X[k][i]);
+                        Un[k * m + j] = clipd(v, lo[j], hi[j]);
+                    }
+                    if (k < N - 1) {
+                        orc_state_dyn(s, xs, Un + k * m, dd);
+                        for (int i = 0; i < n; ++i) xs[i] = xs[i] + h * dd[i];
+                    }
+                }
+                Jn = orc_actor_cost(c, s, Un, observation, state_sys, w_critic);
+                if (Jn < J) improved = 1; else alpha *= 0.5;
+            }
+            if (!improved) {
+                mu *= 10.0;
+                if (mu > 1e12 || ++stalls >= 4) break;
+                continue;
+            }
+            stalls = 0;
+            const double dJ = J - Jn;
+            memcpy(x, Un, sizeof(double) * (size_t)L);
+            J = Jn;
+            mu = fmax(mu / 10.0, 1e-9);
+            if (dJ <= 1e-9 * fmax(fabs(J), 1.0)) break;
+            orc_actor_grad(c, s, x, observation, state_sys, w_critic, g);
+            pg = 0.0;
+            for (int i = 0; i < L; ++i) pg = fmax(pg, fabs(clipd(x[i] - g[i], lo[i % m], hi[i % m]) - x[i]));
+        }
+    }
+    const double J = orc_actor_opt(c, s, x, observation, state_sys, w_critic, max_iter, pg_tol, f_tol, &iters, &nf);
+    if (sweeps_out) *sweeps_out = sweeps;
+    if (iters_out) *iters_out = iters;
+    return J;
+}

@@ -285,3 +285,25 @@ def test_actor_opt_oracle_reaches_the_reference_slsqp_minimum():
         assert J <= c["J_init"] + 1e-12 * abs(c["J_init"])
         assert J <= c["J_ref"] + 1e-7 * max(abs(c["J_ref"]), 1.0), (c["system"], c["mode"], c["critic_struct"], c["N"], J, c["J_ref"])
         assert J == oracle.actor_cost(ct, s, x, c["obs"], c["state_sys"], w)
+
+
+def test_actor_opt_hybrid_reaches_the_slsqp_minimum_with_bounded_iterations():
+    """Gauss-Newton (iLQR) sweeps + L-BFGS hand-over (groundwork for the next optimiser kernel): at or
+    below the live reference's SLSQP cost on every golden problem, inside the box, and the slowest problem needs an
+    order of magnitude fewer dependent iterations than L-BFGS alone (which runs up to its 300-iteration cap)."""
+    worst, total_lbfgs = 0, 0
+    for c in load("actor_opt.json"):
+        s, ct, w = _opt_case(c)
+        x, J, sweeps, iters = oracle.actor_opt_hybrid(ct, s, c["x_init"], c["obs"], c["state_sys"], w, max_sweeps=25,
+                                                      max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+        _, _, it_alone, _ = oracle.actor_opt(ct, s, c["x_init"], c["obs"], c["state_sys"], w, max_iter=300, pg_tol=1e-7,
+                                             f_tol=1e-12)
+        b = np.array(PRESET[c["system"]]["bnds"], dtype=float)
+        lo, hi = np.tile(b[:, 0], c["N"]), np.tile(b[:, 1], c["N"])
+        assert np.all(x >= lo) and np.all(x <= hi)
+        assert J <= c["J_ref"] + 1e-7 * max(abs(c["J_ref"]), 1.0), (c["system"], c["mode"], c["critic_struct"], c["N"], J, c["J_ref"])
+        assert J == oracle.actor_cost(ct, s, x, c["obs"], c["state_sys"], w)
+        assert sweeps <= 25
+        worst = max(worst, sweeps + iters)
+        total_lbfgs = max(total_lbfgs, it_alone)
+    assert worst <= 40 and total_lbfgs >= 5 * worst, (worst, total_lbfgs)
