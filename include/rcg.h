@@ -233,6 +233,21 @@ int rcg_actor_grad(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t 
                    const double *obs, const double *sqn, const double *w_critic, int32_t w_per_env, double *workspace,
                    int64_t workspace_bytes, double *J_out, double *grad_out, void *stream);
 
+/* Gauss-Newton (iLQR) pre-pass of rcg_actor_opt for long horizons and stiff predictors (Sys3WRobot): every stage term of
+ * _actor_cost (controllers.py:1273-1328) is quadratic in [observation - shift, action], so a reverse Riccati pass with the
+ * linearised Euler predictor gives a Newton-like step from O(n^2) state per problem; control limits by a clamped Newton
+ * step per stage, Levenberg-Marquardt regularisation, backtracking on the cost.  At most max_sweeps sweeps per problem; a
+ * start that passes the projected-gradient test (pg_tol) is left untouched; four failed forward passes in a row stop.
+ * The cost never increases.  sqn, mask, w_critic as for rcg_actor_opt (sqn is clipped to the box); 'biquadratic' stage
+ * costs are not quadratic: sqn is left untouched and sweeps_out = 0.  Call rcg_actor_opt afterwards: it
+ * finishes from the returned point (on the reference's 72 recorded problems the slowest one needs 33 dependent iterations
+ * instead of 300).  workspace: rcg_actor_ilqr_workspace_bytes() bytes.  sweeps_out[E*S] or NULL. */
+int64_t rcg_actor_ilqr_workspace_bytes(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S);
+int rcg_actor_ilqr(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S, const double *state_sys,
+                   const double *obs, double *sqn, const double *w_critic, int32_t w_per_env, const int32_t *mask,
+                   int32_t max_sweeps, double pg_tol, double *workspace, int64_t workspace_bytes, int32_t *sweeps_out,
+                   void *stream);
+
 /* Start points from an arg-min: sqn_out[i][e] = candidate idx[e] of environment e (cand laid out as for
  * rcg_actor_cost; L = Nactor*m rows), for the lanes with mask != 0 and 0 <= idx[e] < C. */
 int rcg_gather_sqn(int32_t L, int64_t E, int32_t C, const double *cand, int32_t cand_per_env, const int32_t *idx,

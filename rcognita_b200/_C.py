@@ -80,6 +80,9 @@ def _load():
     L.rcg_actor_opt.argtypes = ([sysp, objp, i64, i32, vp, vp, vp, vp, i32, vp, i32, dbl, dbl, vp, i64]
                                 + [vp] * 7 + [dbl, vp])
     L.rcg_actor_grad.argtypes = [sysp, objp, i64, i32, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp]
+    L.rcg_actor_ilqr_workspace_bytes.argtypes = [sysp, objp, i64, i32]
+    L.rcg_actor_ilqr_workspace_bytes.restype = C.c_int64
+    L.rcg_actor_ilqr.argtypes = [sysp, objp, i64, i32, vp, vp, vp, vp, i32, vp, i32, dbl, vp, i64, vp, vp]
     L.rcg_gather_sqn.argtypes = [i32, i64, i32, vp, i32, vp, vp, vp, vp]
     L.rcg_nominal_ni.argtypes = [sysp, i64, vp, dbl, vp, vp, objp, vp, dbl, vp]
     L.rcg_stage_obj.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, dbl, vp]
@@ -97,7 +100,7 @@ EXPORTS = [
     "rcg_version", "rcg_last_error_string", "rcg_device_count", "rcg_dim_state", "rcg_dim_input", "rcg_dim_critic",
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
     "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_rk45_advance_logged", "rcg_log_rows", "rcg_actor_cost", "rcg_actor_cost_f32",
-    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
+    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_actor_ilqr_workspace_bytes", "rcg_actor_ilqr", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 
 

@@ -36,7 +36,8 @@ class ClosedLoopEngine:
     enumerate-and-argmin over the candidate set; ``"opt"`` = the batched bounded minimiser ``rcg_actor_opt``
     (exact adjoint gradients, projected quasi-Newton; at most ``opt_iters`` iterations per sample) started from the
     arg-min candidate (``opt_start="argmin"``) or, like the reference, from ``action_sqn_init`` every time
-    (``opt_start="init"``; the candidate set is then unused and may be ``None``); ``"nominal"`` = the reference's
+    (``opt_start="init"``; the candidate set is then unused and may be ``None``), optionally after at most
+    ``opt_presweeps`` control-limited Gauss-Newton (iLQR) sweeps (``rcg_actor_ilqr``; 0 = off); ``"nominal"`` = the reference's
     ``CtrlNominal3WRobotNI`` with ``ctrl_gain`` (Sys3WRobotNI only; ``action_init`` defaults to zeros like the
     reference's ``action_curr``, candidates unused).
 
@@ -50,7 +51,8 @@ class ClosedLoopEngine:
                  R2=None, stage_obj_struct="quadratic", observation_target=(), critic_struct="quad-nomix",
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
                  buffer_size=10, critic_period=None, critic_fit_evals=0, actor="candidates", opt_start="argmin",
-                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, ctrl_gain=0.5, log_every=0, log_capacity=0):
+                 opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, opt_presweeps=0, ctrl_gain=0.5, log_every=0,
+                 log_capacity=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -89,6 +91,8 @@ class ClosedLoopEngine:
                 raise ValueError("trajectory logging needs log_capacity >= 1 and fp64")
             self.actor, self.opt_start = actor, opt_start
             self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
+            self.opt_presweeps = int(opt_presweeps)
+            self.ilqr_ws = None
             if actor == "opt" and dtype != torch.float64:
                 raise ValueError("the actor optimiser runs in fp64")
             if candidates is None:
@@ -183,6 +187,10 @@ class ClosedLoopEngine:
             self.sqn = torch.zeros((L, E), dtype=dt, device=dev)
             self.sqn_init = self.action_init.repeat(self.obj.Nactor)[:, None].expand(L, E).contiguous()   # rep_mat (:973-978)
             self.opt_ws, _ = ops._opt_workspace(self.sysd, self.obj, E, 1, dev)
+            if self.opt_presweeps > 0:
+                self.ilqr_ws = torch.empty((max(ops.ilqr_workspace_bytes(self.sysd, self.obj, E, 1) // 8, 1),),
+                                           dtype=torch.float64, device=dev)
+                self.ilqr_sweeps = torch.zeros((E,), dtype=torch.int32, device=dev)
 
     def reset(self):
         """Documented intent of ``Simulator.reset`` + ``CtrlOptPred.reset``: restore y0, t0,
@@ -280,6 +288,10 @@ class ClosedLoopEngine:
                 ops.gather_sqn(self.cand, self.cand_per_env, self.C, self.argmin, self.sqn, mask=self.sample_flag)
             else:
                 self.sqn.copy_(self.sqn_init)              # my_action_sqn_init (:1383), the same for every sample
+            if self.opt_presweeps > 0:                     # Gauss-Newton (iLQR) sweeps first: rcg_actor_ilqr
+                ops.actor_ilqr(self.sysd, self.obj, self.state_sys, self.y, self.sqn, S=1, w_critic=self.w,
+                               w_per_env=self.w_per_env, mask=self.sample_flag, max_sweeps=self.opt_presweeps,
+                               pg_tol=self.opt_pg_tol, workspace=self.ilqr_ws, sweeps_out=self.ilqr_sweeps)
             ops.actor_opt(self.sysd, self.obj, self.state_sys, self.y, self.sqn, S=1, w_critic=self.w,
                           w_per_env=self.w_per_env, mask=self.sample_flag, max_iter=self.opt_iters,
                           pg_tol=self.opt_pg_tol, f_tol=self.opt_f_tol, workspace=self.opt_ws, Jmin_out=self.Jmin,

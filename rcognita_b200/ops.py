@@ -233,6 +233,38 @@ def actor_opt(sysd, obj, state_sys, obs, sqn, S=1, w_critic=None, w_per_env=Fals
     return J_out, iters_out, nfev_out
 
 
+def ilqr_workspace_bytes(sysd, obj, E, S=1):
+    need = int(_C.lib.rcg_actor_ilqr_workspace_bytes(C.byref(sysd), C.byref(obj), int(E), int(S)))
+    if need < 0:
+        raise ValueError("rcg_actor_ilqr_workspace_bytes: bad arguments")
+    return need
+
+
+def actor_ilqr(sysd, obj, state_sys, obs, sqn, S=1, w_critic=None, w_per_env=False, mask=None, max_sweeps=25, pg_tol=1e-7,
+               workspace=None, sweeps_out=None):
+    """Gauss-Newton (iLQR) pre-pass of :func:`actor_opt`: at most ``max_sweeps`` control-limited Riccati sweeps per
+    problem on ``sqn`` ``[N*m, E*S]`` in place (the cost never increases).  Returns ``sweeps [E*S]``."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    E = obs.shape[1]
+    L = obj.Nactor * m
+    dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
+    wshape = None if w_critic is None else ((dimc, E) if w_per_env else (dimc,))
+    need = int(_C.lib.rcg_actor_ilqr_workspace_bytes(C.byref(sysd), C.byref(obj), E, int(S)))
+    if need < 0:
+        raise ValueError("rcg_actor_ilqr_workspace_bytes: bad arguments")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((max(need // 8, 1),), dtype=_F64, device=obs.device)
+    if sweeps_out is None:
+        sweeps_out = torch.zeros((E * S,), dtype=_I32, device=obs.device)
+    _C.check(_C.lib.rcg_actor_ilqr(C.byref(sysd), C.byref(obj), E, int(S), _ptr(state_sys, _F64, (n, E), "state_sys"),
+                                   _ptr(obs, _F64, (n, E), "obs"), _ptr(sqn, _F64, (L, E * S), "sqn"),
+                                   _ptr(w_critic, _F64, wshape, "w_critic", optional=True), int(bool(w_per_env)),
+                                   _ptr(mask, _I32, (E,), "mask", optional=True), int(max_sweeps), float(pg_tol),
+                                   _ptr(workspace), need, _ptr(sweeps_out, _I32, (E * S,), "sweeps_out"), _stream()),
+             "rcg_actor_ilqr")
+    return sweeps_out
+
+
 def gather_sqn(cand, cand_per_env, C_, idx, out, mask=None):
     """Start points of the optimiser from an arg-min: ``out[:, e]`` = candidate ``idx[e]`` of environment e."""
     L, E = out.shape
