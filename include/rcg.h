@@ -235,12 +235,13 @@ int rcg_actor_grad(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t 
 
 /* Gauss-Newton (iLQR) pre-pass of rcg_actor_opt for long horizons and stiff predictors (Sys3WRobot): every stage term of
  * _actor_cost (controllers.py:1273-1328) is quadratic in [observation - shift, action], so a reverse Riccati pass with the
- * linearised Euler predictor gives a Newton-like step from O(n^2) state per problem; control limits by a clamped Newton
+ * linearised Euler predictor (plus, for Sys3WRobot, the second-order term of its heading/speed coupling) gives a Newton-like
+ * step from O(n^2) state per problem; control limits by a clamped Newton
  * step per stage, Levenberg-Marquardt regularisation, backtracking on the cost.  At most max_sweeps sweeps per problem; a
  * start that passes the projected-gradient test (pg_tol) is left untouched; four failed forward passes in a row stop.
  * The cost never increases.  sqn, mask, w_critic as for rcg_actor_opt (sqn is clipped to the box); 'biquadratic' stage
  * costs are not quadratic: sqn is left untouched and sweeps_out = 0.  Call rcg_actor_opt afterwards: it
- * finishes from the returned point (on the reference's 72 recorded problems the slowest one needs 33 dependent iterations
+ * finishes from the returned point (on the reference's 72 recorded problems the slowest one needs 38 dependent iterations
  * instead of 300).  workspace: rcg_actor_ilqr_workspace_bytes() bytes.  sweeps_out[E*S] or NULL. */
 int64_t rcg_actor_ilqr_workspace_bytes(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S);
 int rcg_actor_ilqr(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t S, const double *state_sys,

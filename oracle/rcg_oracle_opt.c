@@ -347,7 +347,8 @@ void orc_nominal_ni(double ctrl_gain, const orc_sys_t *s, const double *obs, dou
  * tools/ilqr_prototype.py).  Every stage term of _actor_cost is exactly quadratic in z = [obs - shift, action]
  * (stage_obj 'quadratic': z^T R1 z scaled by gamma**k; the four critic structures: a quadratic form in chi, or in the
  * raw observation for quad-mix, plus a linear part for quad-lin), so a reverse Riccati pass over the horizon with the
- * linearised Euler step gives a Newton-like step with O(n^2) state; the box on the actions is handled per stage by a
+ * linearised Euler step (plus, for Sys3WRobot, the second-order term of its heading/speed coupling) gives a Newton-like step
+ * with O(n^2) state; the box on the actions is handled per stage by a
  * clamped Newton step (m <= 2: the 3^m active sets are enumerated), Q_aa is regularised (Levenberg-Marquardt), the
  * forward pass backtracks on the TRUE cost (orc_actor_cost).  At most max_sweeps sweeps; a start that is already
  * stationary (projected-gradient test) costs none; four failed forward passes in a row -- the indefinite critics --
@@ -531,6 +532,14 @@ double orc_actor_opt_hybrid(const orc_ctrl_t *c, const orc_sys_t *s, double *x, 
                             for (int l = 0; l < n; ++l) Qx[i] += A[l * n + i] * Vx[l];
                             for (int j = 0; j < n; ++j)
                                 for (int l = 0; l < n; ++l) Qxx[i * n + j] += A[l * n + i] * VA[l * n + j];
+                        }
+                        if (s->sys_id == ORC_SYS_3WROBOT) {          /* second-order term of the heading/speed coupling (DDP) */
+                            double sn, cs;
+                            orc_sincos(X[k][2], &sn, &cs);
+                            Qxx[2 * n + 2] += h * (Vx[0] * (-X[k][3] * cs) + Vx[1] * (-X[k][3] * sn));
+                            const double cc = h * (Vx[0] * (-sn) + Vx[1] * cs);
+                            Qxx[2 * n + 3] += cc;
+                            Qxx[3 * n + 2] += cc;
                         }
                         for (int j = 0; j < m; ++j) {
                             for (int l = 0; l < n; ++l) Qa[j] += B[l * m + j] * Vx[l];

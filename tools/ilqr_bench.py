@@ -49,7 +49,7 @@ def run(name, N, pred, R1, E, spread, center, presweeps, reps=3):
 
 if __name__ == "__main__":
     E = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-    for pre in (0, 25):
+    for pre in (0, 25, 50):
         run("3wrobot", 10, 0.1, np.diag([10.0, 10.0, 1.0, 0, 0, 0, 0]), E, [0.5, 0.5, 0.2, 0.3, 0.3], [5.0, 5.0, 2.4, 0, 0], pre)
     for pre in (0, 25):
         run("3wrobotNI", 6, 0.01, PRESET["3wrobotNI"]["R1_diag"], E, [2.0, 2.0, 1.0], [0.0, 0.0, 0.0], pre)
