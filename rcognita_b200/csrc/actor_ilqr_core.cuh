@@ -129,17 +129,25 @@ constexpr int kIlqrMaxStalls = 4;
 // per-problem workspace in doubles: rollout [NA][n], feed-forward [NA][m], gains [NA][m][n], trial sequence [NA][m]
 __host__ __device__ inline int64_t ilqr_ws_per_problem(int na, int n, int m) { return (int64_t)na * (n + 2 * m + m * n); }
 
-// U[i * us] = component i of the action sequence (in/out); ws[i * wss] = workspace double i of this problem.
-// Returns the number of accepted-or-attempted sweeps.
-template <int SYS>
-__host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const ObjDev<double> &O, int mode, int cs_id,
-                                              const double *x0, const double *ob0, const double *w, double *U, int64_t us,
-                                              double *ws, int64_t wss, int max_sweeps, double pg_tol)
+// Feeder concept (the source of problems; the loop below is PERSISTENT: a lane that finishes its problem asks for the
+// next one, so the lanes of a warp stay busy although sweep counts differ between problems):
+//   bool next(double *x0, double *ob0, double *w, double *&U, int64_t &us)  -- fetch the next problem of this lane: state,
+//        observation, critic weights, U[i * us] = component i of its action sequence (in/out); false = no more work;
+//   bool all_idle(bool idle)   -- true when every lane that shares this lane's control flow is out of work (warp vote);
+//   void done(int sweeps)      -- the current problem is finished.
+// ws[i * wss] = workspace double i of this lane (ilqr_ws_per_problem doubles).  The caller guarantees a 'quadratic' stage
+// cost and max_sweeps >= 1.
+template <int SYS, class Feeder>
+__host__ __device__ inline void ilqr_run(const SysDev<double> &Sd, const ObjDev<double> &O, int mode, int cs_id, Feeder &feed,
+                                         double *ws, int64_t wss, int max_sweeps, double pg_tol)
 {
     constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m, P = N + M;
+    constexpr int DIMW = P * (P + 1) / 2 + P;
     const int NA = O.Nactor;
     const double h = O.pred_step_size;
-    if (O.stage_struct != RCG_STAGE_QUADRATIC || max_sweeps <= 0) return 0;
+    double x0[N], ob0[N], w[DIMW];
+    double *U = nullptr;
+    int64_t us = 0;
 
     double lo[M], hi[M];
     for (int j = 0; j < M; ++j) {
@@ -153,7 +161,12 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
         for (int j = 0; j < P; ++j) { Hs[i * P + j] = O.R1[i * P + j] + O.R1[j * P + i]; Hc[i * P + j] = 0.0; }
     }
     for (int i = 0; i < N; ++i) { shs[i] = O.target[i]; shc[i] = O.target[i]; }
-    if (mode != RCG_MODE_MPC) {
+    auto critic_form = [&]() {                                 // per problem: the weights may differ between environments
+        if (mode == RCG_MODE_MPC) return;
+        for (int i = 0; i < P; ++i) {
+            gc[i] = 0.0;
+            for (int j = 0; j < P; ++j) Hc[i * P + j] = 0.0;
+        }
         int k = 0;
         if (cs_id == RCG_CRITIC_QUAD_LIN || cs_id == RCG_CRITIC_QUADRATIC) {
             for (int i = 0; i < P; ++i)
@@ -169,7 +182,7 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
                 for (int j = 0; j < M; ++j) { Hc[i * P + N + j] += w[k]; Hc[(N + j) * P + i] += w[k]; ++k; }
             for (int j = 0; j < M; ++j) Hc[(N + j) * P + N + j] = 2.0 * w[k++];
         }
-    }
+    };
     auto is_critic = [&](int k) { return mode == RCG_MODE_SQL || (mode == RCG_MODE_RQL && k == NA - 1); };
     // gradient (gz) and value of stage k at (ob, a)
     auto stage = [&](int k, const double *ob, const double *a, double *gz) -> double {
@@ -199,8 +212,6 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
     auto Kfb = [&](int k, int j, int i) -> double & { return ws[((int64_t)NA * (N + M) + (k * M + j) * N + i) * wss]; };
     auto Un = [&](int i) -> double & { return ws[((int64_t)NA * (N + M + M * N) + i) * wss]; };
 
-    for (int i = 0; i < NA * M; ++i) Ux(i) = ilqr_clip(Ux(i), lo[i % M], hi[i % M]);
-
     // rollout of the current sequence: keeps the predictor states, returns the cost
     auto rollout = [&]() -> double {
         double st[N], dd[N], a[M], Jc = 0.0;
@@ -217,10 +228,28 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
         return Jc;
     };
 
-    double J = rollout();
-    double mu = 1e-6;
+    double J = 0.0, mu = 1e-6;
     int sweeps = 0, stalls = 0;
-    while (sweeps < max_sweeps) {
+    bool need = true, idle = false;
+    for (;;) {
+        if (need) {
+            need = false;
+            if (!feed.next(x0, ob0, w, U, us)) {
+                idle = true;
+            } else {
+                critic_form();
+                for (int i = 0; i < NA * M; ++i) Ux(i) = ilqr_clip(Ux(i), lo[i % M], hi[i % M]);
+                J = rollout();
+                mu = 1e-6;
+                sweeps = 0;
+                stalls = 0;
+            }
+        }
+        if (feed.all_idle(idle)) break;
+        if (idle) continue;
+        // ---- one pass = one sweep of the current problem ----
+        bool fin = !(sweeps < max_sweeps);
+        if (!fin) {
         // ---- reverse pass: gains and feed-forward steps; raise mu until every Q_aa is positive definite ----
         bool ok = false;
         double pg = 0.0;
@@ -361,7 +390,9 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
                 if (mu > 1e12) break;
             }
         }
-        if (!ok || !(pg > pg_tol)) break;
+        if (!ok || !(pg > pg_tol)) fin = true;
+        }
+        if (!fin) {
         ++sweeps;
         // ---- forward pass with backtracking on the cost ----
         double alpha = 1.0, Jn = J;
@@ -388,18 +419,66 @@ __host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const Ob
         }
         if (!improved) {
             mu *= 10.0;
-            if (mu > 1e12 || ++stalls >= kIlqrMaxStalls) break;
-            continue;
+            if (mu > 1e12 || ++stalls >= kIlqrMaxStalls) fin = true;
+        } else {
+            stalls = 0;
+            const double dJ = J - Jn;
+            for (int i = 0; i < NA * M; ++i) Ux(i) = Un(i);
+            J = rollout();                                         // refresh the stored rollout for the next reverse pass
+            mu = (mu / 10.0 > 1e-9) ? mu / 10.0 : 1e-9;
+            const double scale = (fabs(J) > 1.0) ? fabs(J) : 1.0;
+            if (dJ <= 1e-9 * scale) fin = true;
         }
-        stalls = 0;
-        const double dJ = J - Jn;
-        for (int i = 0; i < NA * M; ++i) Ux(i) = Un(i);
-        J = rollout();                                             // refresh the stored rollout for the next reverse pass
-        mu = (mu / 10.0 > 1e-9) ? mu / 10.0 : 1e-9;
-        const double scale = (fabs(J) > 1.0) ? fabs(J) : 1.0;
-        if (dJ <= 1e-9 * scale) break;
+        }
+        if (fin) {
+            feed.done(sweeps);
+            need = true;
+        }
     }
-    return sweeps;
+}
+
+// One problem on the calling thread (host checks; E x S = 1).  Returns the number of sweeps.
+struct IlqrSingleFeeder {
+    const double *x0, *ob0, *w;
+    double *U;
+    int64_t us;
+    int n, dimw, sweeps;
+    bool taken;
+    __host__ __device__ bool next(double *x, double *ob, double *ww, double *&Uo, int64_t &uso)
+    {
+        if (taken) return false;
+        taken = true;
+        for (int i = 0; i < n; ++i) { x[i] = x0[i]; ob[i] = ob0[i]; }
+        for (int i = 0; i < dimw; ++i) ww[i] = w[i];
+        Uo = U;
+        uso = us;
+        return true;
+    }
+    __host__ __device__ bool all_idle(bool idle) const { return idle; }
+    __host__ __device__ void done(int s) { sweeps = s; }
+};
+
+__host__ __device__ inline int ilqr_dim_critic(int mode, int cs, int n, int m)
+{
+    const int p = n + m;
+    if (mode == RCG_MODE_MPC) return 0;
+    switch (cs) {
+    case RCG_CRITIC_QUAD_LIN:   return p * (p + 1) / 2 + p;
+    case RCG_CRITIC_QUADRATIC:  return p * (p + 1) / 2;
+    case RCG_CRITIC_QUAD_NOMIX: return p;
+    default:                    return n + n * m + m;
+    }
+}
+
+template <int SYS>
+__host__ __device__ inline int ilqr_presweeps(const SysDev<double> &Sd, const ObjDev<double> &O, int mode, int cs_id,
+                                              const double *x0, const double *ob0, const double *w, double *U, int64_t us,
+                                              double *ws, int64_t wss, int max_sweeps, double pg_tol)
+{
+    if (O.stage_struct != RCG_STAGE_QUADRATIC || max_sweeps <= 0) return 0;
+    IlqrSingleFeeder f{x0, ob0, w, U, us, SysDim<SYS>::n, ilqr_dim_critic(mode, cs_id, SysDim<SYS>::n, SysDim<SYS>::m), 0, false};
+    ilqr_run<SYS>(Sd, O, mode, cs_id, f, ws, wss, max_sweeps, pg_tol);
+    return f.sweeps;
 }
 
 }  // namespace rcg
