@@ -95,3 +95,44 @@ def test_core_leaves_stationary_starts_and_non_quadratic_costs_alone(host):
     assert sw == 0 and np.array_equal(U, np.array(c["x_init"], dtype=np.float64))
     U, sw = _run(host, rs, ro, c, w, max_sweeps=0)
     assert sw == 0 and np.array_equal(U, np.array(c["x_init"], dtype=np.float64))
+
+
+def test_core_on_random_problems_of_every_system_mode_and_critic(host):
+    """240 seeded random problems (3 systems x MPC/RQL/SQL x 4 critic structures, random states, starts, positive or
+    indefinite weights): the sweeps never leave the box and never raise the cost; sweep count and cost agree with the
+    checker's restatement (libm vs the checker's own sincos can flip a line-search decision: >= 97 % identical)."""
+    rng = np.random.default_rng(11)
+    structs = ["quad-lin", "quadratic", "quad-nomix", "quad-mix"]
+    total = same = 0
+    for name in ("3wrobotNI", "3wrobot", "2tank"):
+        n, m = DIMS[name]
+        P = PRESET[name]
+        b = np.array(P["bnds"], dtype=float)
+        for mode in ("MPC", "RQL", "SQL"):
+            for cs in structs if mode != "MPC" else structs[:1]:
+                for rep in range(8 if mode != "MPC" else 16):
+                    N = int(rng.integers(1, 9))
+                    R1 = np.diag(rng.uniform(0.0, 10.0, size=n + m) * (rng.uniform(size=n + m) < 0.8))
+                    kw = dict(mode=mode, Nactor=N, pred_step_size=float(rng.choice([0.01, 0.05, 0.1])),
+                              gamma=float(rng.choice([1.0, 0.95])), critic_struct=cs, R1=R1)
+                    tgt = list(P["target"]) if name == "2tank" else []
+                    s = oracle.make_sys(name, P["pars"], P["bnds"])
+                    ct = oracle.make_ctrl(n, m, observation_target=tgt, **kw)
+                    rs = _C.make_system(name, P["pars"], P["bnds"])
+                    ro = _C.make_objective(n, m, observation_target=tgt or (), **kw)
+                    dimc = _C.dim_critic(cs, n, m)
+                    w = rng.uniform(0.0, 20.0, size=dimc) if cs in ("quadratic", "quad-nomix") else rng.normal(size=dimc) * 5.0
+                    x0 = rng.normal(size=n) * (3.0 if name != "2tank" else 0.5)
+                    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+                    start = rng.uniform(lo, hi) * rng.choice([0.0, 0.3, 1.0])
+                    c = dict(x_init=list(start), state_sys=list(x0), obs=list(x0))
+                    wl = w if mode != "MPC" else None
+                    U, sw = _run(host, rs, ro, c, wl)
+                    J0 = oracle.actor_cost(ct, s, np.clip(start, lo, hi), x0, x0, wl)
+                    J1 = oracle.actor_cost(ct, s, U, x0, x0, wl)
+                    assert np.all(U >= lo) and np.all(U <= hi)
+                    assert J1 <= J0 + 1e-9 * max(abs(J0), 1.0), (name, mode, cs, N, J0, J1)
+                    xo, Jo, swo, _ = oracle.actor_opt_hybrid(ct, s, start, x0, x0, wl, max_sweeps=25, max_iter=0, pg_tol=1e-7)
+                    total += 1
+                    same += int(sw == swo and abs(J1 - Jo) <= 1e-9 * max(abs(Jo), 1.0))
+    assert total == 240 and same >= 0.97 * total, (same, total)
