@@ -1,5 +1,5 @@
 """rcg_actor_opt alone vs rcg_actor_ilqr + rcg_actor_opt on one batch of actor problems (device-resident, CUDA events).
-Usage: python tools/ilqr_bench.py [E]   -> one line per configuration."""
+Usage: python tools/ilqr_bench.py [E [f_tol]]   -> one line per configuration."""
 import sys
 import os
 import numpy as np
@@ -11,7 +11,7 @@ from rcognita_b200 import _C, ops          # noqa: E402
 from golden_util import DIMS, PRESET       # noqa: E402
 
 
-def run(name, N, pred, R1, E, spread, center, presweeps, reps=3):
+def run(name, N, pred, R1, E, spread, center, presweeps, reps=3, f_tol=1e-12):
     n, m = DIMS[name]
     P = PRESET[name]
     sysd = _C.make_system(name, P["pars"], P["bnds"])
@@ -35,20 +35,26 @@ def run(name, N, pred, R1, E, spread, center, presweeps, reps=3):
         if presweeps:
             ops.actor_ilqr(sysd, obj, st, st, sqn, max_sweeps=presweeps, pg_tol=1e-7, workspace=ws_i, sweeps_out=sw)
         e1.record()
-        ops.actor_opt(sysd, obj, st, st, sqn, max_iter=300, pg_tol=1e-7, f_tol=1e-12, workspace=ws_o, J_out=J, iters_out=it,
+        ops.actor_opt(sysd, obj, st, st, sqn, max_iter=300, pg_tol=1e-7, f_tol=f_tol, workspace=ws_o, J_out=J, iters_out=it,
                       nfev_out=nf)
         e2.record()
         torch.cuda.synchronize()
         if r:
             best.append((e0.elapsed_time(e2), e0.elapsed_time(e1)))
     tot, pre = min(best)
-    print(f"{name} N={N} E={E} presweeps={presweeps}: {tot:.2f} ms ({pre:.2f} ms sweeps) = {E / tot * 1e3:.3e} solves/s; "
+    print(f"{name} N={N} E={E} presweeps={presweeps} f_tol={f_tol:g}: {tot:.2f} ms ({pre:.2f} ms sweeps) = {E / tot * 1e3:.3e} solves/s; "
           f"mean J {J.mean().item():.6f}; sweeps mean {sw.float().mean().item():.1f} max {sw.max().item()}; "
           f"iters mean {it.float().mean().item():.1f} max {it.max().item()}; nfev mean {nf.float().mean().item():.1f}", flush=True)
 
 
 if __name__ == "__main__":
     E = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+    f_tol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-12
+    if f_tol != 1e-12:                     # tolerance study: Sys3WRobot only
+        for pre in (0, 50):
+            run("3wrobot", 10, 0.1, np.diag([10.0, 10.0, 1.0, 0, 0, 0, 0]), E, [0.5, 0.5, 0.2, 0.3, 0.3], [5.0, 5.0, 2.4, 0, 0], pre,
+                f_tol=f_tol)
+        sys.exit(0)
     for pre in (0, 25, 50):
         run("3wrobot", 10, 0.1, np.diag([10.0, 10.0, 1.0, 0, 0, 0, 0]), E, [0.5, 0.5, 0.2, 0.3, 0.3], [5.0, 5.0, 2.4, 0, 0], pre)
     for pre in (0, 25):
