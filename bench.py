@@ -50,9 +50,17 @@ def parse_args():
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="environments in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=16, help="environment blocks (streams) of the host-staged loop")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="environment blocks (streams) of the host-staged loop")
+    ap.add_argument("--blocks", type=int, default=2, help="environment blocks (streams) of the device-resident pipelined loop")
+    ap.add_argument("--no-extra", action="store_true", help="skip the env-steps and config-3 strong-scaling blocks")
+    ap.add_argument("--envsteps-envs", type=int, default=1 << 20, help="environments per GPU of the env-steps block")
+    ap.add_argument("--envsteps-intervals", type=int, default=100)
+    ap.add_argument("--config3-envs", type=int, default=1 << 20, help="TOTAL environments of the config-3 strong-scaling block")
+    ap.add_argument("--config3-t1", type=float, default=2.0)
+    ap.add_argument("--no-reference-python", action="store_true", help="skip timing the unmodified reference from baseline/_ref")
+    ap.add_argument("--reference-python-budget", type=float, default=6.0, help="seconds of wall budget per reference loop")
     ap.add_argument("--no-opt", action="store_true", help="skip the extra block that times the closed loop with the batched actor optimiser")
-    ap.add_argument("--no-graph", action="store_true", help="drive the host-staged loop from Python instead of a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="drive the host-staged loop from Python instead of one CUDA graph per block")
     return ap.parse_args()
 
 
@@ -159,22 +167,51 @@ def cpu_closed_loop(args, sample_envs, steps, warmup, budget_s=None):
     return tot_evals / el, tot_steps / el, 1e3 * el / done, threads, done
 
 
+def bench_t1(args):
+    """Episode length of both arms: long enough that no environment finishes inside the bench."""
+    return max(10.0, (2 * (args.steps + max(args.warmup, 3)) + 32) * 3 * DT) + 120.0      # + the clock-sampling continuation
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line -- the same keys and values for both arms."""
+    E, C, N = args.envs, args.cands, args.nactor
+    return {"workload": workload_name(args), "envs_total": E * world, "candidates": C, "Nactor": N, "t1": bench_t1(args),
+            "l2": f"per-launch candidate stream {E * C * N * 2 * 8 / 1e9:.2f} GB > 126 MB L2 (no flush needed)"
+                  if not args.shared_cands else "shared table: cache-resident by design",
+            "sharding": f"{world} x contiguous env blocks, no per-step communication"}
+
+
+def reference_python_baseline(args, cores):
+    """The UNMODIFIED reference (baseline/_ref, numpy/scipy) on the host cores: preset-faithful SLSQP loop and the
+    candidate/arg-min loop, a fixed wall budget each (bench_reference.py)."""
+    if args.no_reference_python:
+        return None
+    try:
+        import bench_reference
+        return bench_reference.measure(cores, budget_s=args.reference_python_budget, nactor=args.nactor, ncand=args.cands)
+    except Exception as exc:                               # never let the optional block take the bench line down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for the path (oracle port -- the reference is
-    pure Python and cannot travel to the GPU box) on all host threads, same config/metric."""
+    """--impl reference: the reference's CPU algorithm for the path on all host threads, same config / metric: the
+    oracle port (C + OpenMP; ~200x faster per core than the numpy/scipy original, so the ratio against it is the
+    conservative one), with the unmodified Python reference from baseline/_ref timed beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     sample = cpu_sample_envs(args, host_threads())
     evals_s, steps_s, ms, threads, done = cpu_closed_loop(args, sample, args.steps, args.warmup)
+    cpu = {"value": evals_s, "unit": "evals/s", "cores": threads, "kind": "port", "env_steps_per_s": steps_s,
+           "sample": f"{sample} of {args.envs} envs x {args.cands} candidates, one control interval per step "
+                     f"(oracle/rcg_oracle.c, OpenMP)",
+           "reference_python": reference_python_baseline(args, threads)}
     line = {
         "impl": "reference", "metric": METRIC, "value": evals_s, "unit": "evals/s", "env_steps_per_s": steps_s,
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "t1": 10.0},
-        "cpu_baseline": {"value": evals_s, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} of {args.envs} envs x {args.cands} candidates, one control interval per step "
-                                   f"(oracle/rcg_oracle.c, OpenMP)"},
+        "config": bench_config(args, max(world, args.gpus)), "cpu_baseline": cpu,
         "e2e": {"value": evals_s, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -203,6 +240,86 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+FP64_PEAK_TFLOPS = 36.9          # DFMA issue peak measured with tools/peaks.cu on this pool (profiles/r01_peaks.jsonl)
+NI_STEP_FLOP = 272               # algorithmic flop per accepted 3wrobot_NI RK45 step
+ACTOR_DRAM_BYTES_PER_EVAL = None  # filled from profiles/actor_cost_traffic.json (ncu dram__bytes per launch / evals)
+
+
+def extra_env_steps(args, rank, world, dev, barrier, allreduce_max, allreduce_sum):
+    """Closed-loop env-steps/s of 3wrobot_NI at 1,048,576 environments PER GPU with cheap controllers in the loop (the
+    env-step half of BASELINE.json's metric): the reference's nominal parking controller and MPC over 16 shared
+    candidates.  rk45_advance is FP64-pipe-bound: fraction of the measured DFMA peak at SURVEY section 8d's 272 flop/step."""
+    import torch
+    from rcognita_b200 import shard
+    from rcognita_b200.engine import ClosedLoopEngine
+    from bench_workload import synthetic_candidates, synthetic_states
+    E = args.envsteps_envs
+    lo, hi = shard.shard_range(E * world, rank, world)
+    x0 = torch.as_tensor(synthetic_states(SYSTEM, lo, hi, seed=0), device=dev)
+    out = {"envs_per_gpu": E, "intervals": args.envsteps_intervals, "scaling": "weak"}
+    for tag, cand, kw in (("nominal", None, dict(actor="nominal", ctrl_gain=0.5)),
+                          ("mpc_16_shared_candidates", synthetic_candidates(BNDS, args.nactor, 16, seed=1), dict(actor="candidates"))):
+        eng = ClosedLoopEngine(SYSTEM, x0, cand, ctrl_bnds=BNDS, mode="MPC", Nactor=args.nactor, dt=DT, t1=1e6, R1=R1_DIAG,
+                               device=dev, **kw)
+        for _ in range(5):
+            eng.run_interval()
+        barrier()
+        s0 = int(eng.nsteps.sum().item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.envsteps_intervals):
+            eng.run_interval()
+        e1.record()
+        barrier()
+        ms = allreduce_max(e0.elapsed_time(e1))
+        steps = allreduce_sum(int(eng.nsteps.sum().item()) - s0)
+        sps = steps / (ms * 1e-3)
+        out[tag] = {"env_steps_per_s": sps, "ms_per_interval": ms / args.envsteps_intervals,
+                    "fp64_roofline": {"bound": "fp64 pipe", "flop_per_step": NI_STEP_FLOP, "achieved_tflops": sps * NI_STEP_FLOP / 1e12,
+                                      "peak_tflops": FP64_PEAK_TFLOPS * world, "frac": sps * NI_STEP_FLOP / 1e12 / (FP64_PEAK_TFLOPS * world),
+                                      "note": "a transcendental counts as ONE flop in SURVEY 8d; fp64 sincos/pow expand to ~45 "
+                                              "instructions, so the pipe utilisation is ~3x this fraction (ncu: profiles/)"}}
+        del eng
+    return out
+
+
+def extra_config3_strong(args, rank, world, dev, barrier, allreduce_max, allreduce_sum):
+    """BASELINE config 3, STRONG scaling: 1,048,576 Sys3WRobot environments in total sharded over the ranks, RQL with the
+    'quadratic' critic refitted at every sample, Nactor = 10, 256 shared candidates, whole episodes of t1 = 2.
+    No per-step communication; per-environment returns gathered over NCCL at the end."""
+    import torch
+    from rcognita_b200 import shard
+    from rcognita_b200.engine import ClosedLoopEngine
+    from bench_workload import synthetic_candidates, synthetic_states
+    Eg = args.config3_envs
+    lo, hi = shard.shard_range(Eg, rank, world)
+    bn = [[-300, 300], [-100, 100]]
+    x0 = synthetic_states("3wrobot", lo, hi, seed=0)
+    cand = synthetic_candidates(bn, 10, 256, seed=1)
+    eng = ClosedLoopEngine("3wrobot", x0, cand, pars=[10, 1], ctrl_bnds=bn, mode="RQL", Nactor=10, dt=0.01, pred_step_size=0.02,
+                           t1=args.config3_t1, R1=[1, 10, 1, 0, 0, 0, 0], critic_struct="quadratic", critic_fit=True, Ncritic=4,
+                           buffer_size=10, device=dev)
+    for _ in range(3):
+        eng.run_interval()
+    barrier()
+    s0, n0 = int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k = eng.run()
+    e1.record()
+    barrier()
+    ms = allreduce_max(e0.elapsed_time(e1))
+    steps = allreduce_sum(int(eng.nsteps.sum().item()) - s0)
+    samples = allreduce_sum(int(eng.nsamples.sum().item()) - n0)
+    cnt = torch.tensor([0], dtype=torch.int64, device=dev)
+    returns, _ = shard.gather_returns(eng.accum, cnt)
+    return {"scaling": "strong", "envs_total": Eg, "envs_per_gpu": hi - lo, "t1": args.config3_t1, "candidates": 256, "Nactor": 10,
+            "critic": "quadratic (28 weights), refit every sample", "intervals": k, "ms_total": ms, "ms_per_interval": ms / max(k, 1),
+            "env_steps_per_s": steps / (ms * 1e-3), "actor_evals_per_s": samples * 256 / (ms * 1e-3),
+            "critic_fits_per_s": samples / (ms * 1e-3), "mean_return": float(returns.mean().item()),
+            "returns_gathered": int(returns.numel())}
+
+
 def run_b200(args):
     # Everything the libraries print (NCCL's version banner goes to stdout) is sent to stderr: stdout carries
     # exactly one JSON line.
@@ -214,7 +331,7 @@ def run_b200(args):
 
     import rcognita_b200
     from rcognita_b200 import shard
-    from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop
+    from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop, PipelinedLoop
     from bench_workload import make_workload
 
     rank = int(os.environ.get("RANK", "0"))
@@ -232,82 +349,118 @@ def run_b200(args):
     E, C, N = args.envs, args.cands, args.nactor
     lo, hi = shard.shard_range(E * world, rank, world)
     x0, cand = make_workload(args, lo, hi)
-    t1 = max(10.0, (2 * (K + W) + 32) * 3 * DT)             # long enough that no lane finishes mid-bench
-    eng = ClosedLoopEngine(SYSTEM, x0, cand, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
-                           action_init=ACTION_INIT, device=dev)
+    t1 = bench_t1(args)
+    kw = dict(ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG, action_init=ACTION_INIT)
+    cand = torch.as_tensor(cand, device=dev)                  # one upload, sliced by both loops
+    loop = PipelinedLoop(SYSTEM, x0, cand, nchunks=args.blocks, device=dev, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allreduce_max(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allreduce_sum(x):
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
     # ---- device-resident closed loop: warm-up, then exactly K timed steps
     for _ in range(W):
-        eng.run_interval()
+        loop.step()
+    loop.synchronize()
     barrier()
-    steps0, samples0 = int(eng.nsteps.sum().item()), int(eng.nsamples.sum().item())
+    steps0, samples0 = int(loop.field("nsteps").sum().item()), int(loop.field("nsamples").sum().item())
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     time.sleep(0.3 if rank == 0 else 0.0)
     barrier()
     rcognita_b200.reset_launch_count()
-    eng.actor_events = []
+    loop.actor_events = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
     for _ in range(K):
-        eng.run_interval()
+        loop.step()
+    loop.synchronize()
     ev1.record()
     barrier()
     t_wall1 = time.time()
     launches = rcognita_b200.launch_count()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_total = ev0.elapsed_time(ev1)
-    actor_ms = [a.elapsed_time(b) for a, b in eng.actor_events]
-    eng.actor_events = None
-    d_steps = int(eng.nsteps.sum().item()) - steps0
-    d_evals = (int(eng.nsamples.sum().item()) - samples0) * C
+    actor_ms = [a.elapsed_time(b) for a, b in loop.actor_events]
+    loop.actor_events = None
+    d_steps = int(loop.field("nsteps").sum().item()) - steps0
+    d_evals = (int(loop.field("nsamples").sum().item()) - samples0) * C
+    clocks = None
+    if sampler:
+        # nvidia-smi cannot sample faster than ~10 Hz: a timed region shorter than half a second yields fewer than five
+        # samples, which is not a measurement.  In that case the SAME loop simply keeps running (untimed) until the
+        # sampler has seen it for 1.5 s, and the clocks line says which region it describes.
+        if t_wall1 - t_wall0 < 0.6:
+            t_c0 = time.time()
+            while time.time() - t_c0 < 1.5:
+                for _ in range(64):
+                    loop.step()
+                loop.synchronize()
+                torch.cuda.synchronize()
+            clocks = sampler.stop(t_c0, time.time())
+            clocks["region"] = (f"untimed continuation of the same loop for 1.5 s (the timed region of {K} steps lasted "
+                                f"{1e3 * (t_wall1 - t_wall0):.1f} ms: too short for 5 nvidia-smi samples)")
+        else:
+            clocks = sampler.stop(t_wall0, t_wall1)
+            clocks["region"] = "timed region"
+        if clocks.get("samples", 0) < 5:
+            clocks["reasons"] = list(clocks.get("reasons", [])) + ["fewer than 5 samples: not a measurement"]
 
-    red = torch.tensor([ms_total, float(np.mean(actor_ms))], dtype=torch.float64, device=dev)
+    ms_total = allreduce_max(ms_total)
+    actor_ms_avg = allreduce_max(float(np.mean(actor_ms)))
+    actor_ms_per_step = allreduce_max(float(np.sum(actor_ms)) / K)
     cnt = torch.tensor([d_steps, d_evals, launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
     # end-of-run collectives (the only ones on the path): gather per-env returns, sum the counters
-    returns, cnt = shard.gather_returns(eng.accum, cnt)
-    ms_total, actor_ms_avg = float(red[0].item()), float(red[1].item())
+    returns, cnt = shard.gather_returns(loop.field("accum"), cnt)
     tot_steps, tot_evals, tot_launches = (int(v) for v in cnt.tolist())
     value = tot_evals / (ms_total * 1e-3)
     steps_per_s = tot_steps / (ms_total * 1e-3)
+    evals_per_actor_launch = d_evals / max(1, K * loop.nchunks)
+    del loop
 
-    # ---- end to end: lane state owned by the HOST (pinned), copied in and out every step
+    # ---- end to end: the caller owns state and time in pinned HOST memory, copied in and out every step
     e2e = None
     if not args.no_e2e:
-        loop = HostStagedLoop(SYSTEM, x0, cand, nchunks=args.e2e_chunks, device=dev, ctrl_bnds=BNDS, mode="MPC", Nactor=N,
-                              dt=DT, t1=t1, R1=R1_DIAG, action_init=ACTION_INIT)
-        del cand
-        if not args.no_graph:
-            loop.capture()
-        for _ in range(3):
-            loop.step()
+        hloop = HostStagedLoop(SYSTEM, x0, cand, nchunks=args.e2e_chunks, device=dev, graph=not args.no_graph, **kw)
+        hloop.run(3)
         barrier()
-        s0 = int(loop.host_field("nsamples").sum().item())
+        s0 = int(hloop.field("nsamples").sum().item())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(K):
-            h2d, d2h = loop.step()
+        h2d, d2h = hloop.run(K)
         e1.record()
         barrier()
-        ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        ev_e2e = torch.tensor([(int(loop.host_field("nsamples").sum().item()) - s0) * C], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ev_e2e, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(ev_e2e.item()) / (float(ms_e2e.item()) * 1e-3), "unit": "evals/s",
-               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-               "ms_per_step": float(ms_e2e.item()) / K,
-               "api": f"HostStagedLoop.step: pinned host lane state in and out every step, {args.e2e_chunks} env blocks on "
-                      "separate streams (copies overlap kernels)" + ("" if args.no_graph else ", one CUDA-graph replay per step")
-                      + "; candidate sets resident on the device"}
-        del loop
+        ms_e2e = allreduce_max(e0.elapsed_time(e1))
+        ev_e2e = allreduce_sum((int(hloop.field("nsamples").sum().item()) - s0) * C)
+        e2e = {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "evals/s",
+               "h2d_bytes_per_step": int(h2d // K) * world, "d2h_bytes_per_step": int(d2h // K) * world,
+               "ms_per_step": ms_e2e / K,
+               "host_inputs": "state y[3][E] and solver time t[E] per environment (what Simulator.get_sim_step_data returned)",
+               "host_outputs": "y, t, action[2][E], accum_obj[E], status, sample_flag, argmin",
+               "device_resident": f"solver internals (f, h_abs, state_sys, clocks, counters) and the per-environment candidate "
+                                  f"sets ({E * C * N * 2 * 8 / 1e9:.2f} GB per GPU: controller parameters, uploaded once)",
+               "api": f"HostStagedLoop.run: {hloop.nchunks} environment blocks, each one pinned-host copy in + rk45_advance + "
+                      "actor_cost + one copy out per control interval" + ("" if args.no_graph else " (one CUDA graph per block)")
+                      + "; a block's next interval starts when ITS results are on the host"}
+        del hloop
+    del cand
+
+    extra = None
+    if not args.no_extra:
+        extra = {"env_steps": extra_env_steps(args, rank, world, dev, barrier, allreduce_max, allreduce_sum),
+                 "config3_strong": extra_config3_strong(args, rank, world, dev, barrier, allreduce_max, allreduce_sum)}
 
     # ---- extra (N = 1): the same closed loop with the batched bounded minimiser standing in for the SLSQP
     #      _actor_optimizer instead of enumerate-and-argmin; reported beside the headline, not part of it
@@ -358,7 +511,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (actor_cost_kernel), measured live with CUDA events
+    # ---- roofline of the dominant kernel (actor_cost_tma_kernel), measured live with CUDA events around every launch
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -366,22 +519,34 @@ def run_b200(args):
     except OSError:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    evals_per_launch = E * C                                   # per rank; every env samples in (almost) every interval
-    evals_per_launch = d_evals / max(1, K)
     bytes_per_eval = (N * 2 * 8 + 8) if not args.shared_cands else 8
-    achieved = evals_per_launch * bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "actor_cost_tma_kernel" if not args.shared_cands else "actor_cost_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
-                "kernel_ms_avg": actor_ms_avg, "kernel_share_of_step": actor_ms_avg * K / ms_total,
-                "kernel_evals_per_s": evals_per_launch / (actor_ms_avg * 1e-3)}
+    read_bytes_per_eval = (N * 2 * 8) if not args.shared_cands else 0
+    achieved = evals_per_actor_launch * bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "actor_cost_tma_kernel" if not args.shared_cands else "actor_cost_kernel",
+                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel: read + write)" if peaks else "fallback 6650 GB/s",
+                "bytes_per_eval": bytes_per_eval,
+                "bytes_per_eval_note": f"SURVEY 8d: {read_bytes_per_eval} B candidate read + 8 B cost; this launch folds the cost into "
+                                       "the arg-min and never writes it, so frac_read / frac_dram below are the physical figures",
+                "frac_read": evals_per_actor_launch * read_bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9 / peak_gbs,
+                "evals_per_launch": evals_per_actor_launch, "launches_per_step": args.blocks,
+                "kernel_ms_avg": actor_ms_avg, "kernel_share_of_step": actor_ms_per_step * K / ms_total,
+                "kernel_evals_per_s": evals_per_actor_launch / (actor_ms_avg * 1e-3),
+                "overlap": f"{args.blocks} environment blocks on {args.blocks} streams: each actor launch is timed by events on "
+                           "its own stream while another block's rk45_advance runs beside it (shares can sum to > 1)",
+                # the whole control interval against the same peak: algorithmic bytes of the step / ms_per_step
+                "frac_step": (d_evals / K) * bytes_per_eval / (ms_total / K * 1e-3) / 1e9 / peak_gbs}
     prof = os.path.join(ROOT, "profiles", "actor_cost_traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as fh:
-                roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
-        except (OSError, ValueError):
+                tr = json.load(fh)
+            per_eval = float(tr["dram_bytes_per_launch"]) / float(tr["evals_per_launch"])
+            roofline["traffic"] = per_eval * evals_per_actor_launch
+            roofline["traffic_source"] = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum = {tr['dram_bytes_per_launch']:.4g} B for "
+                                          f"{int(tr['evals_per_launch'])} evals ({per_eval:.1f} B/eval, {tr.get('source', 'profiles/')})")
+            roofline["frac_dram"] = roofline["traffic"] / (actor_ms_avg * 1e-3) / 1e9 / peak_gbs
+        except (OSError, ValueError, KeyError):
             pass
 
     cpu = None
@@ -392,18 +557,15 @@ def run_b200(args):
         ev_s, st_s, ms, threads, done = cpu_closed_loop(args, sample, 400, 3, budget_s=15.0)
         cpu = {"value": ev_s, "unit": "evals/s", "cores": threads, "kind": "port", "env_steps_per_s": st_s,
                "sample": f"{sample} of {E} envs x {C} candidates, {done} control intervals "
-                         f"(oracle/rcg_oracle.c, C + OpenMP, {threads} threads)"}
+                         f"(oracle/rcg_oracle.c, C + OpenMP, {threads} threads)",
+               "reference_python": reference_python_baseline(args, threads)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "env_steps_per_s": steps_per_s, "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "envs_total": E * world, "candidates": C, "Nactor": N, "t1": t1,
-                   "l2": f"per-launch candidate stream {E * C * N * 2 * 8 / 1e9:.2f} GB > 126 MB L2 (no flush needed)"
-                         if not args.shared_cands else "shared table: cache-resident by design",
-                   "sharding": f"{world} x contiguous env blocks, no per-step communication"},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": tot_launches, "roofline": roofline, "cpu_baseline": cpu,
-        "actor_optimizer": actor_opt, "mean_return_so_far": float(returns.mean().item()),
+        "extra": extra, "actor_optimizer": actor_opt, "mean_return_so_far": float(returns.mean().item()),
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

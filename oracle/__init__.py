@@ -63,7 +63,8 @@ class EnvT(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile ``librcg_oracle.so`` (gcc; OpenMP if the toolchain has it)."""
-    srcs = [os.path.join(_HERE, "rcg_oracle.c"), os.path.join(_HERE, "rcg_oracle_opt.c")]
+    srcs = [os.path.join(_HERE, "rcg_oracle.c"), os.path.join(_HERE, "rcg_oracle_opt.c"),
+            os.path.join(_HERE, "rcg_oracle_critic.c")]
     hdr = os.path.join(_HERE, "rcg_oracle.h")
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(f) for f in srcs + [hdr])):
@@ -127,6 +128,12 @@ def lib():
         L.orc_env_interval.argtypes = [C.POINTER(EnvT), C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, C.c_int, dp,
                                        C.c_int, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_longlong)]
         L.orc_env_interval.restype = C.c_longlong
+        L.orc_critic_fit.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp, C.c_int, ip]
+        L.orc_critic_fit.restype = C.c_double
+        L.orc_closed_loop_critic.argtypes = ([C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int]
+                                             + [C.c_double] * 10 + [C.c_int, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp,
+                                                                    dp, dp, dp, C.c_int, ip])
+        L.orc_closed_loop_critic.restype = C.c_longlong
         L.orc_num_threads.restype = C.c_int
         L.orc_has_openmp.restype = C.c_int
         L.orc_sincos.argtypes = [C.c_double, dp, dp]
@@ -385,6 +392,64 @@ def closed_loop(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_
         traj.ctypes.data_as(dp) if traj_cap > 0 else _null(), int(traj_cap), C.byref(rows), C.byref(evals))
     return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfev": nfe,
             "traj": traj[: rows.value], "total_steps": int(total), "total_evals": int(evals.value)}
+
+
+def critic_fit(c, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w_init=None, max_evals=0):
+    """Bounded least-squares stand-in for ``_critic_optimizer`` (rcg_oracle_critic.c: the algorithm of the product's
+    ``rcg_critic_fit`` restated in scalar C).  Buffers ``[buffer_size, n]`` / ``[buffer_size, m]`` (row 0 = oldest).
+    Returns (w, J_c(w), dual passes)."""
+    ob, obp = _d(obs_buf)
+    ab, abp = _d(act_buf)
+    wv, wvp = _d(w_prev)
+    D = dim_critic({v: k for k, v in CRITIC_STRUCTS.items()}[c.critic_struct], n, m)
+    wi = np.ones(D) if w_init is None else np.asarray(w_init, dtype=np.float64)
+    wi, wip = _d(wi)
+    w = np.zeros(D)
+    ev = C.c_int(0)
+    J = lib().orc_critic_fit(C.byref(c), n, m, obp, abp, wvp, float(w_min), float(w_max), wip,
+                             w.ctypes.data_as(C.POINTER(C.c_double)), int(max_evals), C.byref(ev))
+    return w, J, ev.value
+
+
+def closed_loop_critic(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_step, buffer_size, w_bounds,
+                       critic_period=None, first_step=1e-6, rtol=1e-3, atol=1e-5, w_replay=None,
+                       max_steps_per_env=1 << 30, nthreads=0, traj_cap=0):
+    """RQL / SQL closed loop INCLUDING the critic branch of ``compute_action`` (controllers.py:1455-1479) with the
+    enumerate-and-argmin actor: FIFO buffers, critic clock, refit by :func:`critic_fit` -- or, with ``w_replay``
+    ``[F, dimc]``, fit number j LOADS ``w_replay[j]`` (the reference's recorded SLSQP results).  ``traj`` rows of env 0:
+    [t, y(n), action(m), accum, argmin, Jmin, sampled, nfits]."""
+    x0, x0p = _d(np.atleast_2d(state_init))
+    E = x0.shape[0]
+    cd, cp = _d(cand)
+    per_env = int(cd.ndim == 3)
+    ncand = cd.shape[-2]
+    ai, aip = _d(np.atleast_1d(action_init))
+    n, m = s.n, s.m
+    D = lib().orc_dim_critic(c.critic_struct, n, m)
+    if w_replay is None:
+        wr, wrp, nrep = None, _null(), 0
+    else:
+        wr, wrp = _d(np.atleast_2d(w_replay))
+        nrep = wr.shape[0]
+    yf = np.zeros((E, n)); tf = np.zeros(E); acc = np.zeros(E)
+    nst = np.zeros(E, dtype=np.int32); nsa = np.zeros(E, dtype=np.int32); nft = np.zeros(E, dtype=np.int32)
+    wf = np.zeros((E, D)); Jc = np.zeros(E)
+    obf = np.zeros((E, buffer_size, n)); abf = np.zeros((E, buffer_size, m))
+    ncol = 1 + n + m + 5
+    traj = np.zeros((max(traj_cap, 1), ncol))
+    rows = C.c_int(0)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    total = lib().orc_closed_loop_critic(
+        C.byref(c), C.byref(s), E, x0p, ncand, cp, per_env, aip, int(buffer_size), float(w_bounds[0]), float(w_bounds[1]),
+        float(sampling_time), float(sampling_time if critic_period is None else critic_period), float(t0), float(t1),
+        float(max_step), float(first_step), float(rtol), float(atol), int(max_steps_per_env), int(nthreads), wrp, nrep,
+        yf.ctypes.data_as(dp), tf.ctypes.data_as(dp), acc.ctypes.data_as(dp), nst.ctypes.data_as(ip), nsa.ctypes.data_as(ip),
+        nft.ctypes.data_as(ip), wf.ctypes.data_as(dp), Jc.ctypes.data_as(dp), obf.ctypes.data_as(dp), abf.ctypes.data_as(dp),
+        traj.ctypes.data_as(dp) if traj_cap > 0 else _null(), int(traj_cap), C.byref(rows))
+    if total < 0:
+        raise ValueError("buffer_size exceeds the oracle's ORC_MAX_BUF")
+    return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfits": nft, "w_critic": wf, "Jc": Jc,
+            "obs_buf": obf, "act_buf": abf, "traj": traj[: rows.value], "total_steps": int(total)}
 
 
 def sincos(x):

@@ -137,6 +137,29 @@ double orc_actor_opt_hybrid(const orc_ctrl_t *c, const orc_sys_t *s, double *x, 
 long long orc_actor_opt_batch(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *x_init, const double *states,
                               const double *w_critic, int max_iter, double pg_tol, double f_tol, int nthreads,
                               double *J_out);
+/* rcg_oracle_critic.c: the critic side of compute_action for RQL / SQL (ref: controllers.py:1248-1271, :1455-1479). */
+#define ORC_MAX_BUF 32
+typedef struct {
+    double obs_buf[ORC_MAX_BUF * ORC_MAX_N];    /* CtrlOptPred.observation_buffer [buffer_size, n], row 0 = oldest */
+    double act_buf[ORC_MAX_BUF * ORC_MAX_M];    /* CtrlOptPred.action_buffer [buffer_size, m]                      */
+    double w[ORC_MAX_W], w_prev[ORC_MAX_W];     /* w_critic, w_critic_prev                                         */
+    double critic_clock, Jc;
+    int nfits;
+} orc_critic_state_t;
+double orc_critic_fit(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
+                      const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
+                      int max_evals, int *evals_out);
+void   orc_critic_state_init(orc_critic_state_t *k, int dimc, double t0);
+int    orc_env_iterate_critic(orc_env_t *v, orc_critic_state_t *k, const orc_ctrl_t *c, const orc_sys_t *s, int C,
+                              const double *tab, int buffer_size, double w_lo, double w_hi, double sampling_time,
+                              double critic_period, double t1, const double *w_replay, int n_replay);
+long long orc_closed_loop_critic(const orc_ctrl_t *c, const orc_sys_t *s, int E, const double *state_init, int C,
+                                 const double *cand, int cand_per_env, const double *action_init, int buffer_size,
+                                 double w_lo, double w_hi, double sampling_time, double critic_period, double t0, double t1,
+                                 double max_step, double first_step, double rtol, double atol, int max_steps_per_env,
+                                 int nthreads, const double *w_replay, int n_replay, double *y_final, double *t_final,
+                                 double *accum, int *nsteps, int *nsamples, int *nfits, double *w_final, double *Jc_final,
+                                 double *obs_buf_final, double *act_buf_final, double *traj, int traj_cap, int *traj_rows);
 void   orc_nominal_ni(double ctrl_gain, const orc_sys_t *s, const double *obs, double *action);
 int       orc_num_threads(void);
 int       orc_has_openmp(void);

@@ -171,7 +171,7 @@ double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *act
  *                 spans the box and the backtracking finds the scale); d_B = 0
  *           if g.d >= 0: forget the pairs, d_F = -g_F w / |P(x - g) - x|_inf
  *           projected backtracking: x+ = P(x + lambda d), lambda = 1, 1/2, ... until
- *                 J(x+) <= J + 1e-4 g.(x+ - x)                      (monotone: the last iterate is the best)
+ *                 J(x+) <= J + 1e-4 min(g.(x+ - x), 0)              (monotone: the last iterate is the best)
  *           remember s = x+ - x, y = g+ - g
  *   stop also when the cost moved by <= f_tol * max(|J|, 1) twice in a row, when the line search fails, or after
  *   max_iter iterations. */
@@ -252,7 +252,7 @@ double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const d
             }
             Jt = orc_actor_cost(c, s, xt, observation, state_sys, w_critic);
             ++nfev;
-            if (Jt <= J + 1e-4 * gs) { ok = 1; break; }
+            if (Jt <= J + 1e-4 * fmin(gs, 0.0)) { ok = 1; break; }       /* never accept an increase (gs can be >= 0 after the projection) */
             lam *= 0.5;
         }
         if (!ok) break;

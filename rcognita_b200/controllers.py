@@ -79,19 +79,21 @@ def _owner_system(fn, attr):
 
 class CtrlOptPred:
     """rcognita/controllers.py:679-1493.  New keywords (all optional, after the reference's):
-    ``candidates`` ``[C, Nactor*m]`` shared table or ``[E, C, Nactor*m]`` per-environment sets;
-    ``num_candidates`` / ``seed`` used when ``candidates`` is None (uniform random sequences) or ``'structured'``
-    (``structured_candidates``: constant sequences on a log-spaced grid + random fill); ``actor='opt'`` replaces the plain arg-min by
-    the batched bounded minimiser ``rcg_actor_opt`` (exact adjoint gradients, projected quasi-Newton, at most
-    ``opt_iters`` iterations -- the reference's SLSQP has maxiter 300) started from the arg-min candidate
-    (``opt_start='argmin'``) or from ``action_sqn_init`` like the reference (``opt_start='init'``)."""
+    ``actor='opt'`` (the default when no candidate table is given -- the reference's semantics): the batched bounded
+    minimiser ``rcg_actor_opt`` (exact adjoint gradients, projected quasi-Newton, at most ``opt_iters`` iterations -- the
+    reference's SLSQP has maxiter 300) inside the controller's own ``ctrl_bnds`` box, started from ``action_sqn_init``
+    like the reference (``opt_start='init'``, the default without a table) or from the arg-min candidate
+    (``opt_start='argmin'``); ``actor='candidates'`` (the default when ``candidates`` is given): enumerate-and-argmin
+    over ``candidates`` ``[C, Nactor*m]`` (shared table), ``[E, C, Nactor*m]`` (per-environment sets), ``'structured'``
+    (``structured_candidates``: constant sequences on a log-spaced grid + random fill) or ``'random'``
+    (``num_candidates`` uniform random sequences drawn with ``seed``)."""
 
     def __init__(self, dim_input, dim_output, mode='MPC', ctrl_bnds=[], action_init=[], t0=0, sampling_time=0.1,
                  Nactor=1, pred_step_size=0.1, sys_rhs=[], sys_out=[], state_sys=[], prob_noise_pow=1,
                  is_est_model=0, model_est_stage=1, model_est_period=0.1, buffer_size=20, model_order=3,
                  model_est_checks=0, gamma=1, Ncritic=4, critic_period=0.1, critic_struct='quad-nomix',
                  stage_obj_struct='quadratic', stage_obj_pars=[], observation_target=[],
-                 candidates=None, num_candidates=256, seed=1, actor='candidates', opt_start='argmin', opt_iters=300,
+                 candidates=None, num_candidates=256, seed=1, actor=None, opt_start=None, opt_iters=300,
                  opt_pg_tol=1e-7, opt_f_tol=1e-12):
         if is_est_model:
             raise NotImplementedError("is_est_model=1 is outside the B200 hot path (needs sippy; dead code upstream)")
@@ -143,16 +145,28 @@ class CtrlOptPred:
         self._obj = _C.make_objective(n, m, mode=mode, Nactor=Nactor, pred_step_size=pred_step_size, gamma=gamma,
                                       Ncritic=Ncritic, buffer_size=buffer_size, critic_struct=critic_struct,
                                       stage_obj_struct=stage_obj_struct, R1=R1, R2=R2, observation_target=tgt)
+        # Defaults follow the reference: without a candidate table the actor MINIMISES _actor_cost from action_sqn_init
+        # inside the controller's box (what SLSQP does at controllers.py:1383-1398); handing in a table selects
+        # enumerate-and-argmin, the throughput form.
+        if actor is None:
+            actor = 'candidates' if candidates is not None else 'opt'
+        if opt_start is None:
+            opt_start = 'argmin' if candidates is not None else 'init'
         if actor not in ('candidates', 'opt') or opt_start not in ('argmin', 'init'):
             raise ValueError("actor must be 'candidates' or 'opt'; opt_start 'argmin' or 'init'")
+        # The optimiser's box is the CONTROLLER's (Bounds(action_sqn_min, action_sqn_max), :1384), not the System's
+        # clipping range: a descriptor of its own carries it (the predictor uses the unclipped _state_dyn, so only
+        # the box differs).  has_bnds is forced: the reference bounds SLSQP even with all-zero bounds.
+        self._sysd = _C.make_system(self._sys.name, self._sys.pars, ctrl_bnds)
+        self._sysd.has_bnds = 1
         self.actor, self.opt_start = actor, opt_start
         self.opt_iters, self.opt_pg_tol, self.opt_f_tol = int(opt_iters), float(opt_pg_tol), float(opt_f_tol)
         # candidate action sequences of the enumerate-and-argmin actor
         L = Nactor * m
         if isinstance(candidates, str):
-            if candidates != 'structured':
-                raise ValueError("candidates must be an array, None (uniform random) or 'structured'")
-            candidates = structured_candidates(ctrl_bnds, Nactor, int(num_candidates), seed)
+            if candidates not in ('structured', 'random'):
+                raise ValueError("candidates must be an array, None, 'random' or 'structured'")
+            candidates = structured_candidates(ctrl_bnds, Nactor, int(num_candidates), seed) if candidates == 'structured' else None
         if candidates is None:
             candidates = np.random.default_rng(seed).uniform(self.action_sqn_min, self.action_sqn_max,
                                                              size=(int(num_candidates), L))
@@ -203,7 +217,7 @@ class CtrlOptPred:
             L = self.Nactor * m
             self._sqn = torch.zeros((L, E), dtype=_F64, device=dev)
             self._sqn_init = torch.as_tensor(self.action_sqn_init, device=dev)[:, None].expand(L, E).contiguous()
-            self._opt_ws, _ = ops._opt_workspace(self._sys._sysd, self._obj, E, 1, dev)
+            self._opt_ws, _ = ops._opt_workspace(self._sysd, self._obj, E, 1, dev)
             self.opt_iters_used = torch.zeros((E,), dtype=_I32, device=dev)
             self.opt_nfev_used = torch.zeros((E,), dtype=_I32, device=dev)
 
@@ -318,7 +332,7 @@ class CtrlOptPred:
         sq = sq.to(device=self.device, dtype=_F64)
         single = sq.dim() == 1
         tab = (sq[None, :] if single else sq).t().contiguous()                 # [L, C]
-        J, _, _ = ops.actor_cost(self._sys._sysd, self._obj, self._state_sys, obs, tab, False, tab.shape[1],
+        J, _, _ = ops.actor_cost(self._sysd, self._obj, self._state_sys, obs, tab, False, tab.shape[1],
                                  w_critic=self._w_critic if self.mode != 'MPC' else None, w_per_env=True)
         if single:
             J = J[:, 0]
@@ -339,18 +353,18 @@ class CtrlOptPred:
         if self.actor == 'opt':
             # bounded minimisation of _actor_cost (what SLSQP does in the reference), one thread per environment
             if self.opt_start == 'argmin':
-                ops.actor_cost(self._sys._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
+                ops.actor_cost(self._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
                                self.num_candidates, w_critic=w, w_per_env=True, mask=mask, want_J=False,
                                argmin_out=self._argmin, Jmin_out=self._Jmin)
                 ops.gather_sqn(self._cand, self._cand_per_env, self.num_candidates, self._argmin, self._sqn, mask=mask)
             else:
                 self._sqn.copy_(self._sqn_init)                                      # my_action_sqn_init (:1383)
-            ops.actor_opt(self._sys._sysd, self._obj, self._state_sys, obs, self._sqn, S=1, w_critic=w, w_per_env=True,
+            ops.actor_opt(self._sysd, self._obj, self._state_sys, obs, self._sqn, S=1, w_critic=w, w_per_env=True,
                           mask=mask, max_iter=self.opt_iters, pg_tol=self.opt_pg_tol, f_tol=self.opt_f_tol,
                           workspace=self._opt_ws, Jmin_out=self._Jmin, action_out=self._action_curr,
                           iters_out=self.opt_iters_used, nfev_out=self.opt_nfev_used, want_stats=False)
             return self._out(self._action_curr)
-        ops.actor_cost(self._sys._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
+        ops.actor_cost(self._sysd, self._obj, self._state_sys, obs, self._cand, self._cand_per_env,
                        self.num_candidates, w_critic=w, w_per_env=True,
                        mask=mask, want_J=False, argmin_out=self._argmin, Jmin_out=self._Jmin,
                        action_out=self._action_curr)

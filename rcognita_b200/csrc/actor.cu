@@ -93,6 +93,8 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     L.grid = (unsigned)(blocks_needed < max_grid ? blocks_needed : max_grid);
     L.sms = sms;
     L.blocks_needed = blocks_needed;
+    L.ctas_per_sm_cap = 0;
+    if (const char *e = getenv("RCG_ACTOR_CTAS_PER_SM")) L.ctas_per_sm_cap = atoi(e);      // experiment: 0 = default, -1 = non-persistent
     // TMA-staged kernel: per-environment candidates, diagonal R, a specialised horizon, and a candidate
     // count whose lane mapping is a contiguous box (C a multiple of 32, or a power of two below 32)
     L.use_tma = false;

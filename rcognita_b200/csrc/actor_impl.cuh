@@ -721,6 +721,7 @@ struct ActorLaunch {
     unsigned grid;
     int sms;
     int64_t blocks_needed;
+    int ctas_per_sm_cap;
     bool use_tma;              // per-env candidates staged by TMA (tmap valid)
     bool use_tma_rt;           // ... runtime-horizon variant (tmap box = kRtChunk stages)
     CUtensorMap tmap;
@@ -740,7 +741,15 @@ static void launch_actor_one(const ActorLaunch<T> &L)
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 configured = true;
             }
-            const int64_t pg = (int64_t)L.sms * tma_min_ctas<T, LL>();
+            // Grid: at least one resident wave (sms x CTAs per SM); beyond that one CTA per kEnvsPerWarp environments
+            // per warp rather than a persistent grid: short-lived CTAs let the block scheduler slot the concurrently
+            // running rk45_advance launch of another environment block (engine.PipelinedLoop) between them as they
+            // retire -- measured on B200 (profiles/r02_overlap_grid_sweep.txt): 0.333 -> 0.300 ms per control interval.
+            constexpr int kEnvsPerWarp = 4;
+            int64_t pg = (int64_t)L.sms * tma_min_ctas<T, LL>();
+            if (L.blocks_needed / kEnvsPerWarp > pg) pg = L.blocks_needed / kEnvsPerWarp;
+            if (L.ctas_per_sm_cap > 0) pg = (int64_t)L.sms * L.ctas_per_sm_cap;                      // RCG_ACTOR_CTAS_PER_SM: experiments
+            if (L.ctas_per_sm_cap < 0) pg = L.blocks_needed / (-L.ctas_per_sm_cap);
             const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
             kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
                                                          L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);

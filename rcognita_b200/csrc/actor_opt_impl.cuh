@@ -351,7 +351,9 @@ actor_opt_kernel(const __grid_constant__ SysDev<T> Sd, const __grid_constant__ O
         bool accepted = true;
         if (!first) {
             ++nfev;
-            if (!(Jt <= J + T(1e-4) * gs)) {                            // Armijo test failed: halve, or give up
+            // projected Armijo test; after the projection g.(x+ - x) can be >= 0 (the descent components clipped away):
+            // a trial point is then only accepted if it does not raise the cost, which keeps the iteration monotone
+            if (!(Jt <= J + T(1e-4) * fmin(gs, T(0)))) {                // failed: halve, or give up
                 accepted = false;
                 if (++bt >= kOptMaxBacktracks) {
                     finished = true;

@@ -9,6 +9,8 @@
 // steps.  This translation unit is compiled with -fmad=false: the step
 // size feeds the fp64 time accumulation that decides on which solver step the controller
 // samples (section 3.3), so every multiply and add must round separately like numpy's.
+#include <cstdlib>
+
 #include "rcg_host.h"
 
 namespace rcg {
@@ -179,8 +181,8 @@ __device__ __forceinline__ void log_row(const LogDev &G, int64_t E, int64_t e, i
 // (96 registers) and 2tank 6 (74) without spilling; 3wrobot (35 state/stage doubles more) spills beyond 4.
 __host__ __device__ constexpr int rk45_min_blocks(int sys) { return sys == RCG_SYS_3WROBOT_NI ? 5 : sys == RCG_SYS_2TANK ? 6 : 4; }
 
-template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false>
-__global__ void __launch_bounds__(128, rk45_min_blocks(SYS))
+template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false, int BLOCK = 128>
+__global__ void __launch_bounds__(BLOCK, rk45_min_blocks(SYS) * (128 / BLOCK))
 rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
             const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
@@ -321,6 +323,13 @@ static int launch_rhs(const rcg_system_t *sys, int64_t E, const T *y, T *action,
     return check_launch("rcg_rhs");
 }
 
+static int rk45_block()
+{
+    static int b = -1;
+    if (b < 0) { const char *e = getenv("RCG_RK45_BLOCK"); b = e ? atoi(e) : 128; }
+    return b;
+}
+
 template <typename T, int SYS, bool CTRL>
 static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const SysDev<T> &S, const SolverDev &sol,
                             const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
@@ -341,7 +350,15 @@ static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const Sys
             return;
         }
     }
-    if (rdiag)
+    if (rdiag && rk45_block() == 64)
+        rk45_kernel<T, SYS, CTRL, true, false, 64><<<(unsigned)((E + 63) / 64), 64, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
+                                                             clock, sampling_time, max_steps, state_sys, accum, flag,
+                                                             nsamples);
+    else if (rdiag && rk45_block() == 32)
+        rk45_kernel<T, SYS, CTRL, true, false, 32><<<(unsigned)((E + 31) / 32), 32, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
+                                                             clock, sampling_time, max_steps, state_sys, accum, flag,
+                                                             nsamples);
+    else if (rdiag)
         rk45_kernel<T, SYS, CTRL, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
                                                              clock, sampling_time, max_steps, state_sys, accum, flag,
                                                              nsamples);

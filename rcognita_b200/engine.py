@@ -148,29 +148,34 @@ class ClosedLoopEngine:
 
     def _alloc(self):
         n, m, E, dt, dev = self.n, self.m, self.E, self.dtype, self.device
-        # All per-lane state lives in ONE device allocation (fields are typed views at 256-byte-aligned offsets):
-        # the lane fields first, the per-step results after them, so that a caller that owns its environments in
-        # host memory moves the whole state with one copy in (lane part) and one copy out (lane + result part).
-        es = torch.empty((), dtype=dt).element_size()
-        spec = [("y", (n, E), dt), ("f", (n, E), dt), ("state_sys", (n, E), dt), ("action", (m, E), dt),
-                ("t", (E,), torch.float64), ("h_abs", (E,), torch.float64), ("ctrl_clock", (E,), torch.float64),
-                ("accum", (E,), dt), ("status", (E,), torch.int32),
-                # results
-                ("nfev", (E,), torch.int32), ("nsteps", (E,), torch.int32), ("nsamples", (E,), torch.int32),
-                ("sample_flag", (E,), torch.int32), ("argmin", (E,), torch.int32), ("Jmin", (E,), dt)]
+        # All per-lane state lives in ONE device allocation (fields are typed views at 256-byte-aligned offsets) in
+        # three segments: what a caller that owns its environments in HOST memory hands in every step (the state and
+        # time that `Simulator.get_sim_step_data` returned to it, rcognita/simulator.py:187-195), what it reads back in
+        # addition (action, accumulated objective, status, arg-min), and the solver / controller internals that never
+        # leave the device (FSAL derivative, step size, state_sys, clocks, counters).  A host-staged step is ONE copy in
+        # (segment 1) and ONE copy out (segments 1 + 2).
+        spec = [("y", (n, E), dt), ("t", (E,), torch.float64),
+                # read back by the host in addition
+                ("action", (m, E), dt), ("accum", (E,), dt), ("status", (E,), torch.int32),
+                ("sample_flag", (E,), torch.int32), ("argmin", (E,), torch.int32),
+                # device-resident internals
+                ("f", (n, E), dt), ("state_sys", (n, E), dt), ("h_abs", (E,), torch.float64),
+                ("ctrl_clock", (E,), torch.float64), ("nfev", (E,), torch.int32), ("nsteps", (E,), torch.int32),
+                ("nsamples", (E,), torch.int32), ("Jmin", (E,), dt)]
         off, layout = 0, []
         for name, shape, dtype_ in spec:
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype_).element_size()
             layout.append((name, shape, dtype_, off, nbytes))
             off = (off + nbytes + 255) // 256 * 256
-            if name == "status":
-                self._lane_bytes = off
+            if name == "t":
+                self._in_bytes = off
+            if name == "argmin":
+                self._io_bytes = off
         self._blob_bytes = off
         self._layout = layout
         self._blob = torch.empty((off,), dtype=torch.uint8, device=dev)
         for name, shape, dtype_, o, nbytes in layout:
             setattr(self, name, self._blob[o:o + nbytes].view(dtype_).view(shape))
-        del es
         if self.critic_fit:
             dimc = self.w.shape[0]
             self.obs_buf = torch.empty((self.buffer_size, n, E), dtype=dt, device=dev)
@@ -268,10 +273,15 @@ class ClosedLoopEngine:
         # every fit starts from w_critic_init = ones (:1264); refit lanes store the result as w_critic and
         # w_critic_prev (:1470-1471).  Sampling lanes whose critic clock did not fire take w_critic_prev (:1479),
         # which already equals their w_critic (both were written by their last refit, or are still ones).
-        ops.critic_fit(self.obj, n, m, self.obs_buf, self.act_buf, self.w_prev, self.w_bounds[0], self.w_bounds[1],
-                       self.w, w_init=self.w_init, mask=self.critic_flag, max_evals=self.critic_fit_evals, update_prev=True,
-                       Jc_out=self.Jc)
+        self._critic_optimizer()
         self.nfits += self.critic_flag
+
+    def _critic_optimizer(self):
+        """``CtrlOptPred._critic_optimizer`` (controllers.py:1248-1271) + the ``w_critic_prev = w_critic`` hand-over
+        (:1470-1471) for the lanes whose critic clock fired (``critic_flag``): ``rcg_critic_fit`` in place of SLSQP."""
+        ops.critic_fit(self.obj, self.n, self.m, self.obs_buf, self.act_buf, self.w_prev, self.w_bounds[0],
+                       self.w_bounds[1], self.w, w_init=self.w_init, mask=self.critic_flag,
+                       max_evals=self.critic_fit_evals, update_prev=True, Jc_out=self.Jc)
 
     def _actor_launch(self):
         if self.critic_fit:
@@ -305,12 +315,21 @@ class ClosedLoopEngine:
     def run_interval(self, max_steps=1 << 30):
         """One control interval for every running lane: advance to the next sampling event,
         evaluate all candidates, pick the arg-min action."""
+        self.advance(max_steps)
+        self.control()
+
+    def advance(self, max_steps=1 << 30):
+        """First half of a control interval: every running lane integrates to its next sampling event
+        (``rcg_rk45_advance``: sim_step / receive_sys_state / upd_accum_obj with the held action)."""
         if not self._first_done:
             self._first_step()
         ops.rk45_advance(self.sysd, self.sol, self.obj, self.y, self.f, self.t, self.h_abs, self.status, self.action,
                          self.ctrl_clock, self.sampling_time, max_steps, state_sys=self.state_sys, accum=self.accum,
                          sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps, nsamples=self.nsamples,
                          log=self.log)
+
+    def control(self):
+        """Second half: ``compute_action`` of the sampling lanes (critic refit, actor, action hand-over)."""
         self._actor()
         if self.log is not None:            # the row of the sampling step: its action is known only now
             ops.log_rows(self.obj, self.n, self.m, self.log, self.t, self.y, self.action, self.accum, nsteps=self.nsteps,
@@ -389,101 +408,205 @@ class ClosedLoopEngine:
         }
 
 
-    # -- host-buffer form of one control interval: the lane state lives in PINNED HOST memory between calls (a
-    #    caller that owns its environments on the host, like the reference's Python loop does); every call copies
-    #    it in, runs the two kernels and copies state + results back.
-    LANE_FIELDS = ("y", "f", "state_sys", "action", "t", "h_abs", "ctrl_clock", "accum", "status")
-    RESULT_FIELDS = ("nfev", "nsteps", "nsamples", "sample_flag", "argmin", "Jmin")
+    # -- host-buffer form of one control interval: the caller owns its environments in PINNED HOST memory between
+    #    calls (like the reference's Python loop does): it hands in the state and time `get_sim_step_data` gave it and
+    #    reads back state, time, action, accumulated objective, status and arg-min; solver internals stay on the device.
+    HOST_IN_FIELDS = ("y", "t")
+    HOST_OUT_FIELDS = ("y", "t", "action", "accum", "status", "sample_flag", "argmin")
 
     def make_host_state(self):
-        """Pinned host mirror of the lane-state allocation (initialised from the current device state): a dict of
-        typed views per field plus the raw byte buffer under "_blob"."""
+        """Pinned host mirror of the caller-visible part of the lane state (initialised from the current device
+        state): a dict of typed views per field (``HOST_OUT_FIELDS``) plus the raw byte buffer under "_blob"."""
         if not self._first_done:
             self._first_step()
-        blob = torch.empty((self._blob_bytes,), dtype=torch.uint8).pin_memory()
-        blob.copy_(self._blob)
+        blob = torch.empty((self._io_bytes,), dtype=torch.uint8).pin_memory()
+        blob.copy_(self._blob[:self._io_bytes])
         host = {"_blob": blob}
         for name, shape, dtype_, o, nbytes in self._layout:
-            host[name] = blob[o:o + nbytes].view(dtype_).view(shape)
+            if o + nbytes <= self._io_bytes:
+                host[name] = blob[o:o + nbytes].view(dtype_).view(shape)
         return host
 
     def run_interval_host(self, host, sync=True):
-        """H2D lane state (one copy) -> rk45_advance + actor_cost -> D2H lane state and results (one copy), all
-        on the current stream; returns the bytes moved (h2d, d2h).  With ``sync`` the host buffers are valid on
-        return."""
-        nl = self._lane_bytes
-        self._blob[:nl].copy_(host["_blob"][:nl], non_blocking=True)
+        """H2D (y, t: one copy) -> rk45_advance + actor -> D2H (y, t, action, accum, status, sample_flag, argmin: one
+        copy), all on the current stream; returns the bytes moved (h2d, d2h).  With ``sync`` the host buffers are valid
+        on return."""
+        self._blob[:self._in_bytes].copy_(host["_blob"][:self._in_bytes], non_blocking=True)
         self.run_interval()
-        host["_blob"].copy_(self._blob, non_blocking=True)
+        host["_blob"].copy_(self._blob[:self._io_bytes], non_blocking=True)
         if sync:
             torch.cuda.current_stream().synchronize()
-        return nl, self._blob_bytes
+        return self._in_bytes, self._io_bytes
 
 
-class HostStagedLoop:
-    """The closed loop for a caller that owns its environments in HOST memory (like the reference's Python
-    loop does): the batch is split into ``nchunks`` contiguous blocks of environments, each with its own
-    ``ClosedLoopEngine`` and CUDA stream, so that the host->device copy of block i+1, the two kernels of block i
-    and the device->host copy of block i-1 overlap (PCIe is full duplex, kernels of different blocks may share
-    the GPU).  ``step()`` = one control interval of every environment, host buffers valid on return.
-    Candidate tables stay resident on the device (they are parameters of the controller, not per-step inputs)."""
+class _ChunkedLoop:
+    """E environments split into ``nchunks`` contiguous blocks, each a ``ClosedLoopEngine`` on its own CUDA stream.
+    Environments are independent, so the blocks never synchronise with each other: while one block's HBM-bound actor
+    launch streams its candidates, the latency-bound ``rk45_advance`` launch of another block runs beside it."""
 
-    def __init__(self, system, state_init, candidates, nchunks=4, device=None, **engine_kwargs):
+    def __init__(self, system, state_init, candidates, nchunks, device=None, align=1, **engine_kwargs):
         x0 = state_init if isinstance(state_init, torch.Tensor) else np.asarray(state_init, dtype=np.float64)
+        if x0.ndim == 1:
+            x0 = x0[None, :]
         E = x0.shape[0]
-        nchunks = max(1, min(int(nchunks), E))
-        bounds = [(E * i) // nchunks for i in range(nchunks + 1)]
-        per_env = candidates.ndim == 3 if not isinstance(candidates, torch.Tensor) else candidates.dim() == 3
-        self.engines, self.streams, self.hosts = [], [], []
+        nchunks = max(1, min(int(nchunks), max(1, E // max(1, align))))
+        bounds = [((E * i) // nchunks) // align * align for i in range(nchunks)] + [E]
+        per_env = candidates is not None and (candidates.ndim == 3 if not isinstance(candidates, torch.Tensor) else candidates.dim() == 3)
+        self.bounds = bounds
+        self.engines = []
         for a, b in zip(bounds[:-1], bounds[1:]):
             cand = candidates[a:b] if per_env else candidates
-            eng = ClosedLoopEngine(system, x0[a:b], cand, device=device, **engine_kwargs)
-            self.engines.append(eng)
-        dev = self.engines[0].device
-        with torch.cuda.device(dev):
-            for eng in self.engines:
-                self.streams.append(torch.cuda.Stream(device=dev))
-                self.hosts.append(eng.make_host_state())
-        torch.cuda.synchronize(dev)
+            kw = dict(engine_kwargs)
+            w = kw.get("w_critic")
+            if w is not None and getattr(w, "ndim", 1) == 2:
+                kw["w_critic"] = w[a:b]
+            self.engines.append(ClosedLoopEngine(system, x0[a:b], cand, device=device, **kw))
+        self.device = self.engines[0].device
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
+        torch.cuda.synchronize(self.device)
         self.E = E
+        self.nchunks = len(self.engines)
 
-    def _enqueue(self):
-        """Fork every block onto its stream, enqueue copy-in / kernels / copy-out, join back."""
-        h2d = d2h = 0
+    def synchronize(self):
+        """The calling stream waits for every block (results read afterwards are those of the last enqueued step)."""
         cur = torch.cuda.current_stream()
-        for eng, st, host in zip(self.engines, self.streams, self.hosts):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                a, b = eng.run_interval_host(host, sync=False)
-            h2d += a
-            d2h += b
         for st in self.streams:
             cur.wait_stream(st)
-        return h2d, d2h
 
-    def capture(self):
-        """Record one step (all blocks, all streams) into a CUDA graph: a replay costs one launch instead of
-        4 x nchunks Python-driven copies and kernel launches, which is what bounds the step once the batch is split
-        finely enough for the copies to hide behind the kernels."""
-        self._enqueue()                                    # warm-up outside capture (lazy per-kernel attributes)
-        torch.cuda.current_stream().synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._bytes = self._enqueue()
-        self._graph = g
-        return self
+    def field(self, name):
+        """Device view of one lane field over all blocks (lane axis last), after ``synchronize``."""
+        self.synchronize()
+        return torch.cat([getattr(eng, name) for eng in self.engines], dim=-1)
+
+    def results(self):
+        self.synchronize()
+        parts = [eng.results() for eng in self.engines]
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+
+class PipelinedLoop(_ChunkedLoop):
+    """Device-resident closed loop of ``nchunks`` environment blocks on ``nchunks`` streams.  ``step()`` enqueues one
+    control interval of every block and returns without synchronising; per block the order is rk45_advance -> actor,
+    and block i+1's rk45_advance additionally waits for block i's (``stagger``), so that in the steady state every
+    rk45_advance launch (FP64-latency-bound, a fraction of a wave) runs beside another block's actor launch
+    (HBM-bound) instead of in front of it.  Results are bit-identical to one ``ClosedLoopEngine`` over the whole batch:
+    the arithmetic of an environment does not depend on its block."""
+
+    def __init__(self, system, state_init, candidates, nchunks=2, device=None, stagger=True, align=1024, **engine_kwargs):
+        super().__init__(system, state_init, candidates, nchunks, device=device, align=align, **engine_kwargs)
+        self.stagger = bool(stagger) and self.nchunks > 1
+        self.actor_events = None            # set to a list to record (start, end) CUDA events per actor launch
+        # rk45_advance goes to a HIGH-PRIORITY stream per block: its few hundred blocks are then placed as soon as
+        # blocks of the running actor launch retire, instead of queueing behind the other block's pending actor blocks
+        with torch.cuda.device(self.device):
+            self.rk_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in self.engines]
+        cur = torch.cuda.current_stream()
+        for eng, st in zip(self.engines, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                eng._first_step()
+        self.synchronize()
 
     def step(self):
-        if getattr(self, "_graph", None) is not None:
-            self._graph.replay()
-            torch.cuda.current_stream().synchronize()
-            for eng in self.engines:
-                eng.intervals += 1
-            return self._bytes
-        out = self._enqueue()
-        torch.cuda.current_stream().synchronize()
-        return out
+        prev = None
+        for eng, st, rk in zip(self.engines, self.streams, self.rk_streams):
+            rk.wait_stream(st)                                  # this block's previous actor launch
+            if prev is not None:
+                rk.wait_stream(prev)                            # stagger: the previous block's rk45_advance
+            with torch.cuda.stream(rk):
+                eng.advance()
+            if self.stagger:
+                prev = rk
+            st.wait_stream(rk)
+            with torch.cuda.stream(st):
+                if self.actor_events is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record(st)
+                    eng.control()
+                    ev[1].record(st)
+                    self.actor_events.append(ev)
+                else:
+                    eng.control()
+
+    def run(self, intervals):
+        for _ in range(int(intervals)):
+            self.step()
+        self.synchronize()
+
+
+class HostStagedLoop(_ChunkedLoop):
+    """The closed loop for a caller that owns its environments in HOST memory (like the reference's Python loop
+    does).  Per block and control interval: ONE host->device copy of what the caller holds (state and time, the values
+    ``Simulator.get_sim_step_data`` returned), rk45_advance + actor, ONE device->host copy of what the caller reads
+    (state, time, action, accumulated objective, status, arg-min), replayed as one CUDA graph per block.  The solver
+    and controller internals (FSAL derivative, step size, ``state_sys``, clocks, counters) and the candidate sets stay
+    on the device.
+
+    ``step()`` runs one control interval of every block and returns when all host buffers are valid.
+    ``run(K, on_block=None)`` pipelines the blocks: block b's interval k+1 is enqueued as soon as ITS interval-k results
+    are on the host (``on_block(b, k, host_views)`` is called at that point -- the caller's chance to read or modify
+    its environments), while the other blocks' copies and kernels keep the GPU and both PCIe directions busy."""
+
+    def __init__(self, system, state_init, candidates, nchunks=8, device=None, graph=True, **engine_kwargs):
+        super().__init__(system, state_init, candidates, nchunks, device=device, **engine_kwargs)
+        with torch.cuda.device(self.device):
+            self.hosts = [eng.make_host_state() for eng in self.engines]
+            self.done = [torch.cuda.Event() for _ in self.engines]
+        torch.cuda.synchronize(self.device)
+        self.graphs = None
+        self.h2d_bytes = sum(eng._in_bytes for eng in self.engines)
+        self.d2h_bytes = sum(eng._io_bytes for eng in self.engines)
+        if graph:
+            self.capture()
+
+    def capture(self):
+        """One CUDA graph per block (copy in, two kernels, copy out): a replay costs one launch instead of four
+        Python-driven enqueues, which is what bounds the step once the batch is split finely."""
+        graphs = []
+        for eng, st, host in zip(self.engines, self.streams, self.hosts):
+            with torch.cuda.stream(st):
+                eng.run_interval_host(host, sync=False)          # warm-up outside capture (lazy per-kernel attributes)
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                eng.run_interval_host(host, sync=False)
+            graphs.append(g)
+        self.graphs = graphs
+        self.warmup_intervals = 1
+        return self
+
+    def _enqueue(self, b):
+        st = self.streams[b]
+        with torch.cuda.stream(st):
+            if self.graphs is not None:
+                self.graphs[b].replay()
+                self.engines[b].intervals += 1
+            else:
+                self.engines[b].run_interval_host(self.hosts[b], sync=False)
+            self.done[b].record(st)
+
+    def step(self):
+        for b in range(self.nchunks):
+            self._enqueue(b)
+        for ev in self.done:
+            ev.synchronize()
+        return self.h2d_bytes, self.d2h_bytes
+
+    def run(self, intervals, on_block=None):
+        for k in range(int(intervals)):
+            for b in range(self.nchunks):
+                if k > 0:
+                    self.done[b].synchronize()                    # block b's previous results are on the host
+                    if on_block is not None:
+                        on_block(b, k - 1, self.hosts[b])
+                self._enqueue(b)
+        for b in range(self.nchunks):
+            self.done[b].synchronize()
+            if on_block is not None:
+                on_block(b, int(intervals) - 1, self.hosts[b])
+        return self.h2d_bytes * int(intervals), self.d2h_bytes * int(intervals)
 
     def host_field(self, name):
-        """Concatenated host view of one lane field over all blocks (lane axis last)."""
+        """Concatenated host view of one caller-visible lane field over all blocks (lane axis last)."""
         return torch.cat([h[name] for h in self.hosts], dim=-1)

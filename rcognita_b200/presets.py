@@ -108,10 +108,11 @@ def make_parser(system: str) -> argparse.ArgumentParser:
     p.add_argument('--seed', type=int, default=1, help='seed of the candidate table (and of the initial-state spread)')
     p.add_argument('--candidate_table', type=str, default='random', choices=['random', 'structured'],
                    help='candidate action sequences: uniform random, or constant sequences on a log-spaced grid + random fill')
-    p.add_argument('--actor', type=str, default='candidates', choices=['candidates', 'opt'],
-                   help='stand-in for the SLSQP actor: arg-min over candidates, or the batched bounded minimiser')
-    p.add_argument('--opt_start', type=str, default='argmin', choices=['argmin', 'init'],
-                   help='start point of --actor opt: the arg-min candidate, or action_sqn_init like the reference')
+    p.add_argument('--actor', type=str, default='opt', choices=['candidates', 'opt'],
+                   help='stand-in for the SLSQP actor: the batched bounded minimiser (default: the reference\'s semantics), or '
+                        'arg-min over a candidate table (the throughput form)')
+    p.add_argument('--opt_start', type=str, default='init', choices=['argmin', 'init'],
+                   help='start point of --actor opt: action_sqn_init like the reference (default), or the arg-min candidate')
     p.add_argument('--opt_iters', type=int, default=300, help='iteration cap of --actor opt (reference SLSQP: maxiter 300)')
     p.add_argument('--state_spread', type=float, default=0.0,
                    help='std of the Gaussian spread of the initial states around state_init when num_envs > 1')
@@ -154,7 +155,7 @@ def build(system: str, args):
                                       critic_period=critic_period, critic_struct=args.critic_struct,
                                       stage_obj_struct=args.stage_obj_struct, stage_obj_pars=[R1, R2][:1 if args.stage_obj_struct == 'quadratic' else 2],
                                       observation_target=S["target"], num_candidates=args.num_candidates, seed=args.seed,
-                                      candidates='structured' if args.candidate_table == 'structured' else None,
+                                      candidates=args.candidate_table if (args.actor == 'candidates' or args.opt_start == 'argmin') else None,
                                       actor=args.actor, opt_start=args.opt_start, opt_iters=args.opt_iters)
     my_sim = simulator.Simulator(sys_type="diff_eqn", closed_loop_rhs=my_sys.closed_loop_rhs, sys_out=my_sys.out,
                                  state_init=x0, disturb_init=[], action_init=np.zeros(m), t0=0, t1=args.t1, dt=args.dt,

@@ -50,7 +50,7 @@ def make_sys(name):
 
 def make_ctrl(name, my_sys, mode, Nactor, critic_struct="quad-nomix", gamma=1.0, R1=None, R2=None,
               stage_obj_struct="quadratic", target=None, state_sys=None, pred_step=None, buffer_size=10,
-              Ncritic=4, action_init=()):
+              Ncritic=4, action_init=(), critic_period=None):
     cfg = SYSTEMS[name]
     R1 = np.diag(np.array(cfg["R1_diag"], dtype=float)) if R1 is None else R1
     pars = [R1] if R2 is None else [R1, R2]
@@ -63,7 +63,7 @@ def make_ctrl(name, my_sys, mode, Nactor, critic_struct="quad-nomix", gamma=1.0,
         state_sys=np.array(cfg["x0"], dtype=float) if state_sys is None else state_sys,
         prob_noise_pow=False, is_est_model=0, model_est_stage=1.0, model_est_period=cfg["dt"],
         buffer_size=buffer_size, model_order=5, model_est_checks=0, gamma=gamma, Ncritic=Ncritic,
-        critic_period=cfg["dt"], critic_struct=critic_struct, stage_obj_struct=stage_obj_struct,
+        critic_period=cfg["dt"] if critic_period is None else critic_period, critic_struct=critic_struct, stage_obj_struct=stage_obj_struct,
         stage_obj_pars=pars, observation_target=tgt)
 
 
@@ -240,6 +240,80 @@ def gen_closed_loop():
 
 
 
+
+# --------------------------------------------------------------------------- closed loop WITH the reference's own critic refit (a18)
+def closed_loop_refit(name, mode, Nactor, t1, critic_struct, gamma=1.0, C=64, seed=1, x0=None, action_init=(),
+                      critic_period=None, buffer_size=10, Ncritic=4):
+    """The RQL/SQL branch of compute_action (controllers.py:1455-1479) run by the UNMODIFIED reference, SLSQP
+    `_critic_optimizer` included; only `_actor_optimizer` is the candidate/arg-min stand-in of App. A.4.  Every
+    refit is recorded (solver time, FIFO buffers after the push, w_critic_prev before the fit, the fitted weights,
+    `_critic_cost` at w_critic_init and at the fit) so that a loop which LOADS the recorded weights instead of fitting must
+    reproduce buffers, critic-clock firings, arg-min picks, trajectory and accumulated objective."""
+    cfg = SYSTEMS[name]
+    my_sys = make_sys(name)
+    x0 = np.array(cfg["x0"], dtype=float) if x0 is None else np.array(x0, dtype=float)
+    ctrl = make_ctrl(name, my_sys, mode, Nactor, critic_struct=critic_struct, gamma=gamma, state_sys=x0,
+                     action_init=action_init, critic_period=critic_period, buffer_size=buffer_size, Ncritic=Ncritic)
+    sim = make_sim(name, my_sys, t1, x0=x0)
+    Ctab = np.random.default_rng(seed).uniform(ctrl.action_sqn_min, ctrl.action_sqn_max, size=(C, Nactor * cfg["m"]))
+    picks, fits = [], []
+
+    def opt(observation):
+        J = [ctrl._actor_cost(u, observation) for u in Ctab]
+        i = int(np.argmin(J))
+        picks.append([i, float(J[i])])
+        return Ctab[i, :cfg["m"]].copy()
+
+    ctrl._actor_optimizer = opt
+    orig_fit = ctrl._critic_optimizer
+    now = [0.0]
+
+    def fit():
+        w_prev = np.array(ctrl.w_critic_prev, dtype=float)
+        w = orig_fit()
+        fits.append(dict(t=float(now[0]), obs_buf=L(ctrl.observation_buffer), act_buf=L(ctrl.action_buffer), w_prev=L(w_prev),
+                         w=L(w), J_init=float(ctrl._critic_cost(ctrl.w_critic_init)), J_fit=float(ctrl._critic_cost(w))))
+        return w
+
+    ctrl._critic_optimizer = fit
+    rows = []
+    while True:
+        sim.sim_step()
+        t, state, observation, state_full = sim.get_sim_step_data()
+        now[0] = t
+        npk, nft = len(picks), len(fits)
+        action = controllers.ctrl_selector(t, observation, None, None, ctrl, mode)
+        my_sys.receive_action(action)
+        ctrl.receive_sys_state(my_sys._state)
+        ctrl.upd_accum_obj(observation, action)
+        rows.append([t] + L(state_full) + L(action) + [float(ctrl.accum_obj_val), int(len(picks) > npk), int(len(fits) > nft)])
+        if t >= t1:
+            break
+    return dict(system=name, mode=mode, Nactor=Nactor, t1=t1, critic_struct=critic_struct, gamma=gamma, C=C, seed=seed,
+                x0=L(x0), action_init=L(ctrl.action_min / 10) if len(action_init) == 0 else L(action_init),
+                critic_period=float(ctrl.critic_period), buffer_size=int(buffer_size), Ncritic=int(ctrl.Ncritic),
+                cand=L(Ctab), rows=rows, picks=picks, fits=fits, nfev=int(sim.ODE_solver.nfev),
+                w_final=L(ctrl.w_critic), w_prev_final=L(ctrl.w_critic_prev),
+                obs_buf_final=L(ctrl.observation_buffer), act_buf_final=L(ctrl.action_buffer))
+
+
+def gen_closed_loop_refit():
+    out = {}
+    # BASELINE configs 3 and 4 at E = 1
+    out["3wrobot_RQL_quadratic_N10"] = closed_loop_refit("3wrobot", "RQL", 10, 0.6, "quadratic")
+    out["2tank_SQL_nomix_N8"] = closed_loop_refit("2tank", "SQL", 8, 12.0, "quad-nomix", action_init=0.5 * np.ones(1))
+    # critic clock slower than the sampling clock: the `w_critic = w_critic_prev` branch (:1478-1479); gamma < 1
+    out["NI_RQL_quadlin_N5_period3"] = closed_loop_refit("3wrobotNI", "RQL", 5, 0.5, "quad-lin", gamma=0.95,
+                                                         critic_period=0.03, x0=[2.0, -3.0, 0.7])
+    out["NI_SQL_quadmix_N3_Ncritic6"] = closed_loop_refit("3wrobotNI", "SQL", 3, 0.4, "quad-mix", critic_period=0.02,
+                                                          buffer_size=8, Ncritic=6, x0=[-1.0, 2.0, -2.0])
+    for k, v in out.items():
+        print("closed_loop_refit", k, len(v["rows"]), "steps", len(v["picks"]), "samples", len(v["fits"]), "fits, accum",
+              v["rows"][-1][-3], "J_fit range", min(f["J_fit"] for f in v["fits"]), max(f["J_fit"] for f in v["fits"]))
+    with open(os.path.join(HERE, "closed_loop_refit.json"), "w") as fh:
+        json.dump(out, fh)
+
+
 # --------------------------------------------------------------------------- critic fit (reference SLSQP as the bar)
 def gen_critic_fit():
     """Reference `_critic_optimizer` (SLSQP, controllers.py:1248-1271) on seeded buffers: the fitted cost is
@@ -413,13 +487,16 @@ def gen_config1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "config1", "critic_fit", "actor_opt", "nominal"]
+    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "closed_loop_refit", "config1", "critic_fit", "actor_opt",
+                             "nominal"]
     if "functions" in which:
         gen_functions()
     if "integrator" in which:
         gen_integrator()
     if "closed_loop" in which:
         gen_closed_loop()
+    if "closed_loop_refit" in which:
+        gen_closed_loop_refit()
     if "config1" in which:
         gen_config1()
     if "critic_fit" in which:

@@ -708,8 +708,9 @@ def test_empty_batch_is_a_no_op(rb):
 
 @pytest.mark.parametrize("graph,actor", [(False, "candidates"), (True, "candidates"), (True, "opt")])
 def test_host_staged_loop_equals_resident_loop(rb, graph, actor):
-    """engine.HostStagedLoop (lane state owned by pinned host memory, several environment blocks on their own
-    streams, optionally replayed as one CUDA graph per step) takes exactly the same steps as the device-resident
+    """engine.HostStagedLoop (the caller owns state and time in pinned host memory and reads back state, time, action,
+    accumulated objective, status and arg-min; solver internals stay on the device; several environment blocks on their
+    own streams, optionally one CUDA graph per block) takes exactly the same steps as the device-resident
     ClosedLoopEngine: identical state, clocks, counters and picks on every lane after every control interval."""
     from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop
     name, N, C_, E = "3wrobotNI", 6, 64, 1000
@@ -718,17 +719,75 @@ def test_host_staged_loop_equals_resident_loop(rb, graph, actor):
     cand = random_cands(name, (E, C_), N, 72)
     kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.4, R1=p["R1_diag"], actor=actor)
     ref = ClosedLoopEngine(name, x0, cand, **kw)
-    loop = HostStagedLoop(name, x0, cand, nchunks=3, **kw)
+    loop = HostStagedLoop(name, x0, cand, nchunks=3, graph=graph, **kw)
     if graph:
-        loop.capture()
         ref.run_interval()                      # capture() itself advances the loop by one warm-up interval
+    assert set(ClosedLoopEngine.HOST_OUT_FIELDS) <= set(loop.hosts[0]) and "f" not in loop.hosts[0] and "h_abs" not in loop.hosts[0]
     for k in range(12):
         ref.run_interval()
         h2d, d2h = loop.step()
-        torch.cuda.synchronize()
-        assert h2d > 0 and d2h > h2d
-        for f in ("y", "f", "state_sys", "action", "t", "h_abs", "ctrl_clock", "accum", "status", "nsteps", "nsamples",
-                  "nfev", "argmin", "Jmin", "sample_flag"):
-            got = loop.host_field(f).numpy()
-            want = getattr(ref, f).cpu().numpy()
-            assert np.array_equal(got, want, equal_nan=True), (k, f)
+        assert 0 < h2d < d2h
+        assert h2d <= E * (3 * 8 + 8) + 3 * 2 * 256 and d2h <= E * (3 * 8 + 8 + 2 * 8 + 8 + 3 * 4) + 3 * 7 * 256
+        for f in ClosedLoopEngine.HOST_OUT_FIELDS:                       # valid on return, no device access
+            assert np.array_equal(loop.host_field(f).numpy(), getattr(ref, f).cpu().numpy(), equal_nan=True), (k, f)
+        for f in ("f", "state_sys", "h_abs", "ctrl_clock", "nsteps", "nsamples", "nfev", "Jmin"):
+            assert np.array_equal(loop.field(f).cpu().numpy(), getattr(ref, f).cpu().numpy(), equal_nan=True), (k, f)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_staged_pipelined_run_equals_resident_loop(rb, graph):
+    """HostStagedLoop.run: the blocks are pipelined (block b's interval k+1 is enqueued as soon as its interval-k results
+    are on the host); the callback sees every block's results after every interval, and they are the resident loop's."""
+    from rcognita_b200.engine import ClosedLoopEngine, HostStagedLoop
+    name, N, C_, E, K = "3wrobotNI", 6, 32, 640, 9
+    p = PRESET[name]
+    x0 = random_states(name, E, 73)
+    cand = random_cands(name, (E, C_), N, 74)
+    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.4, R1=p["R1_diag"])
+    ref = ClosedLoopEngine(name, x0, cand, **kw)
+    loop = HostStagedLoop(name, x0, cand, nchunks=4, graph=graph, **kw)
+    if graph:
+        ref.run_interval()
+    want = []
+    for k in range(K):
+        ref.run_interval()
+        want.append({f: getattr(ref, f).cpu().numpy().copy() for f in ClosedLoopEngine.HOST_OUT_FIELDS})
+    seen = set()
+
+    def on_block(b, k, host):
+        a, z = loop.bounds[b], loop.bounds[b + 1]
+        for f in ClosedLoopEngine.HOST_OUT_FIELDS:
+            assert np.array_equal(host[f].numpy(), want[k][f][..., a:z], equal_nan=True), (b, k, f)
+        seen.add((b, k))
+
+    h2d, d2h = loop.run(K, on_block=on_block)
+    assert seen == {(b, k) for b in range(loop.nchunks) for k in range(K)}
+    assert h2d == K * loop.h2d_bytes and d2h == K * loop.d2h_bytes
+
+
+@pytest.mark.parametrize("nchunks,stagger,per_env", [(2, True, True), (3, False, True), (4, True, False)])
+def test_pipelined_loop_equals_single_engine(rb, nchunks, stagger, per_env):
+    """engine.PipelinedLoop (environment blocks on their own streams, rk45_advance of one block beside the actor launch
+    of another) is bit-identical to one ClosedLoopEngine over the whole batch, with and without events around the actor
+    launches."""
+    from rcognita_b200.engine import ClosedLoopEngine, PipelinedLoop
+    name, N, C_, E = "3wrobotNI", 6, 64, 4096
+    p = PRESET[name]
+    x0 = random_states(name, E, 75)
+    cand = random_cands(name, (E, C_) if per_env else (C_,), N, 76)
+    kw = dict(ctrl_bnds=p["bnds"], mode="MPC", Nactor=N, dt=p["dt"], t1=0.3, R1=p["R1_diag"])
+    ref = ClosedLoopEngine(name, x0, cand, **kw)
+    loop = PipelinedLoop(name, x0, cand, nchunks=nchunks, stagger=stagger, **kw)
+    assert loop.nchunks == nchunks and loop.bounds[-1] == E and all(b % 1024 == 0 for b in loop.bounds)
+    for k in range(40):
+        if k == 20:
+            loop.actor_events = []
+        ref.run_interval()
+        loop.step()
+    assert len(loop.actor_events) == 20 * nchunks
+    torch.cuda.synchronize()
+    assert all(a.elapsed_time(b) >= 0 for a, b in loop.actor_events)
+    got, want = loop.results(), ref.results()
+    assert got["status"].max() >= 1                      # the episode ended inside the test
+    for k in want:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k

@@ -88,7 +88,7 @@ def test_preset_main_reproduces_the_reference_episode(tmp_path):
     from rcognita_b200 import presets
     g = load("closed_loop.json")["NI_MPC_N6"]
     args = presets.make_parser("3wrobotNI").parse_args(["--ctrl_mode", "MPC", "--Nactor", "6", "--t1", "2.0", "--is_visualization", "",
-                                                        "--is_print_sim_step", "", "--is_log_data", "1"])
+                                                        "--is_print_sim_step", "", "--is_log_data", "1", "--actor", "candidates"])
     out = presets.run_headless("3wrobotNI", args, data_folder=str(tmp_path), quiet=True)
     assert len(out["datafiles"]) == 1 and os.path.basename(out["datafiles"][0]).startswith("3wrobotNI__MPC__")
     rows = list(csv.reader(open(out["datafiles"][0])))
@@ -116,7 +116,8 @@ def test_preset_batched_rql_runs_and_logs(tmp_path):
     from rcognita_b200 import presets
     args = presets.make_parser("2tank").parse_args(["--ctrl_mode", "SQL", "--Nactor", "8", "--t1", "3.0", "--is_visualization", "",
                                                     "--is_print_sim_step", "", "--is_log_data", "1", "--num_envs", "16",
-                                                    "--state_spread", "0.3", "--num_candidates", "32", "--Nruns", "2"])
+                                                    "--state_spread", "0.3", "--num_candidates", "32", "--Nruns", "2",
+                                                    "--actor", "candidates"])
     out = presets.run_headless("2tank", args, data_folder=str(tmp_path), quiet=True)
     assert len(out["runs"]) == 2 and len(out["datafiles"]) == 2
     for run, f in zip(out["runs"], out["datafiles"]):
@@ -158,8 +159,10 @@ def test_preset_mpc_with_optimizer_actor_runs(tmp_path):
                                                         "--is_print_sim_step", "", "--actor", "opt", "--num_envs", "8",
                                                         "--state_spread", "0.5"])
     out = presets.run_headless("3wrobotNI", args, quiet=True)
+    assert args.opt_start == "init"                      # the reference's protocol is the default
     args_c = presets.make_parser("3wrobotNI").parse_args(["--ctrl_mode", "MPC", "--Nactor", "6", "--t1", "1.0", "--is_visualization", "",
-                                                          "--is_print_sim_step", "", "--num_envs", "8", "--state_spread", "0.5"])
+                                                          "--is_print_sim_step", "", "--num_envs", "8", "--state_spread", "0.5",
+                                                          "--actor", "candidates"])
     out_c = presets.run_headless("3wrobotNI", args_c, quiet=True)
     a, c = np.array(out["runs"][0]["accum_obj"]), np.array(out_c["runs"][0]["accum_obj"])
     # per sample the refined sequence is never costlier than the arg-min candidate it starts from; over the closed
