@@ -102,6 +102,18 @@ typedef struct rcg_log {
     int32_t  every;
 } rcg_log_t;
 
+/* Disturbance lanes, System(is_disturb = 1) (rcognita/systems.py:139-145, :228-231, :247-248, :325-345, :384-394): the
+ * full state is [state, disturb] with dim_disturb = 2 for the two robots and 1 for Sys2Tank (the presets' values);
+ * pars_disturb = [sigma_disturb, mu_disturb, tau_disturb].  The reference draws randn() from numpy's global stream once
+ * per component and RHS call -- irreproducible by construction; here every environment has a counter-based stream:
+ * Philox4x32-10 block (RHS call number, global environment index) under key `seed`, Box-Muller with specified log /
+ * sincos, so that a run does not depend on sharding and is reproduced bit for bit by the CPU checker. */
+typedef struct rcg_disturb {
+    double   sigma[2], mu[2], tau[2];
+    uint64_t seed;
+    int64_t  env_offset;         /* global index of lane 0 of this call (rank offset when the batch is sharded) */
+} rcg_disturb_t;
+
 int         rcg_version(void);
 const char *rcg_last_error_string(void);
 /* Number of CUDA devices visible, or a negative RCG_E* code (never touches a kernel). */
@@ -124,6 +136,28 @@ int rcg_rhs_f32(const rcg_system_t *sys, int64_t E, const float *y, float *actio
 /* System._state_dyn alone (no clipping): dstate[n][E] = _state_dyn(state, action). */
 int rcg_state_dyn(const rcg_system_t *sys, int64_t E, const double *state, const double *action,
                   double *dstate, void *stream);
+
+/* System.closed_loop_rhs with is_disturb = 1 on the full state y_full[n + nd][E] (rcognita/systems.py:213-253): clips
+ * action IN PLACE when clip != 0, f_out[:n] = _state_dyn(t, state, action, disturb) (:316-318, :373-376), f_out[n:] =
+ * _disturb_dyn(t, disturb) (:341-343, :390-392) = -tau * (disturb + sigma * (z + mu)).  The draws z: normals[2][E] when
+ * given (parity with the reference under a patched randn()), else the environment's stream at RHS call number call[e]
+ * (0 when call is NULL).  clip = 0 and normals given evaluates _state_dyn / _disturb_dyn alone. */
+int rcg_rhs_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, int64_t E, const double *y_full, double *action,
+                      const int32_t *call, const double *normals, double *f_out, int32_t clip, void *stream);
+/* The two standard-normal draws of RHS call number call[e] (call_all when call is NULL) of every environment:
+ * normals[2][E]. */
+int rcg_disturb_normals(const rcg_disturb_t *dist, int64_t E, const int32_t *call, int32_t call_all, double *normals,
+                        void *stream);
+/* rcg_rk45_step / rcg_rk45_advance on the full state [n + nd][E] of a disturbed system; nfev[E] is required: it numbers
+ * the RHS calls, i.e. the random draws (1 after Simulator.__init__, += 6 per attempt). */
+int rcg_rk45_step_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, const rcg_solver_t *sol, int64_t E,
+                            double *y_full, double *f_full, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                            double *action, void *stream);
+int rcg_rk45_advance_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, const rcg_solver_t *sol,
+                               const rcg_objective_t *obj, int64_t E, double *y_full, double *f_full, double *t, double *h_abs,
+                               int32_t *status, int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
+                               double sampling_time, int32_t max_steps, double *state_sys, double *accum,
+                               int32_t *sample_flag, int32_t *nsamples, void *stream);
 
 /* Simulator.sim_step, 'diff_eqn' branch (rcognita/simulator.py:161-168) = scipy
  * RK45.step() (scipy base.py:179-212, rk.py:111-176, rk.py:61-71): exactly ONE accepted

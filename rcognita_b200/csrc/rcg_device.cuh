@@ -147,6 +147,116 @@ __device__ __forceinline__ void state_dyn(const SysDev<T> &S, const T *x, const 
     }
 }
 
+// ---- disturbance lanes (is_disturb = 1): rcognita/systems.py:228-231, :247-248, :316-318, :373-376, :325-345, :384-394
+// dim_disturb is 2 for the two robots and 1 for the two-tank system (the presets' values).
+template <int SYS> struct DistDim { static constexpr int nd = (SYS == RCG_SYS_2TANK) ? 1 : 2; };
+
+struct DistDev {
+    double sigma[2], mu[2], tau[2];          // pars_disturb = [sigma_disturb, mu_disturb, tau_disturb]
+    unsigned long long seed;                 // Philox key
+    long long env_offset;                    // global index of lane 0 (sharding does not change an environment's stream)
+};
+
+// _state_dyn(t, state, action, disturb) with a disturbance: Sys3WRobotNI adds disturb[0] to BOTH position rates and
+// disturb[1] to the heading rate (systems.py:373-376, literally), Sys3WRobot adds the disturbance to force and moment
+// before the division (:316-318), Sys2Tank ignores it (:412-419).
+template <int SYS>
+__device__ __forceinline__ void state_dyn_disturbed(const SysDev<double> &S, const double *x, const double *a, const double *q, double *d)
+{
+    if constexpr (SYS == RCG_SYS_3WROBOT_NI) {
+        double s, c;
+        det_sincos(x[2], &s, &c);
+        d[0] = a[0] * c + q[0];
+        d[1] = a[0] * s + q[0];
+        d[2] = a[1] + q[1];
+    } else if constexpr (SYS == RCG_SYS_3WROBOT) {
+        double s, c;
+        det_sincos(x[2], &s, &c);
+        d[0] = x[3] * c;
+        d[1] = x[3] * s;
+        d[2] = x[4];
+        d[3] = (1.0 / S.pars[0]) * (a[0] + q[0]);
+        d[4] = (1.0 / S.pars[1]) * (a[1] + q[1]);
+    } else {
+        state_dyn<double, SYS>(S, x, a, d);
+    }
+}
+
+// _disturb_dyn GIVEN the draws z[k] = randn(): Ddisturb[k] = -tau[k] * (disturb[k] + sigma[k] * (z[k] + mu[k]))
+// (systems.py:341-343, :390-392; note the multiplication by tau).  Sys2Tank: zeros (:421-424).
+template <int SYS>
+__device__ __forceinline__ void disturb_dyn(const DistDev &D, const double *q, const double *z, double *dq)
+{
+    if constexpr (SYS == RCG_SYS_2TANK) {
+        dq[0] = 0.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) dq[k] = -D.tau[k] * (q[k] + D.sigma[k] * (z[k] + D.mu[k]));
+    }
+}
+
+// Natural logarithm from IEEE operations only (the fdlibm / musl algorithm: x = 2^k (1 + f), s = f / (2 + f), a degree-14
+// even polynomial in s), for normal positive x: the same operation sequence as the CPU checker, so the normal draws below
+// agree bit for bit between the two.
+__device__ __forceinline__ double det_log(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    unsigned int hx = (unsigned int)(bits >> 32);
+    hx += 0x3ff00000u - 0x3fe6a09eu;
+    const int k = (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+    bits = ((unsigned long long)hx << 32) | (bits & 0xffffffffull);
+    const double f = __dadd_rn(__longlong_as_double((long long)bits), -1.0);
+    const double hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+    const double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+    const double z = __dmul_rn(s, s), w = __dmul_rn(z, z);
+    const double t1 = __dmul_rn(w, __dadd_rn(Lg2, __dmul_rn(w, __dadd_rn(Lg4, __dmul_rn(w, Lg6)))));
+    const double t2 = __dmul_rn(z, __dadd_rn(Lg1, __dmul_rn(w, __dadd_rn(Lg3, __dmul_rn(w, __dadd_rn(Lg5, __dmul_rn(w, Lg7)))))));
+    const double R = __dadd_rn(t2, t1);
+    const double dk = (double)k;
+    // s*(hfsq+R) + dk*ln2_lo - hfsq + f + dk*ln2_hi, left to right
+    double r = __dadd_rn(__dmul_rn(s, __dadd_rn(hfsq, R)), __dmul_rn(dk, ln2_lo));
+    r = __dadd_rn(r, -hfsq);
+    r = __dadd_rn(r, f);
+    return __dadd_rn(r, __dmul_rn(dk, ln2_hi));
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0, k1) -> four 32-bit words.
+__device__ __forceinline__ void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int lo0 = 0xD2511F53u * c[0], hi0 = __umulhi(0xD2511F53u, c[0]);
+        const unsigned int lo1 = 0xCD9E8D57u * c[2], hi1 = __umulhi(0xCD9E8D57u, c[2]);
+        const unsigned int n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// The two standard-normal draws of RHS call number `call` of global environment `env` (what the reference takes from
+// numpy's global randn(), systems.py:343 / :392 -- irreproducible there by construction; here a counter-based stream):
+// Philox block (call, env) under key `seed` -> two uniforms in (0, 1) with 64 random bits each -> Box-Muller with the
+// specified log / sincos above.
+__device__ __forceinline__ void det_normal2(unsigned long long seed, unsigned long long env, unsigned int call, double *z)
+{
+    unsigned int c[4] = {call, 0u, (unsigned int)env, (unsigned int)(env >> 32)};
+    philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+    // (x + 0.5) / 2^64 with x the 64-bit word: top 53 bits kept, the half keeps u away from 0
+    const double u1 = __dmul_rn(__dadd_rn((double)((((unsigned long long)c[0] << 32) | c[1]) >> 11), 0.5), 1.1102230246251565e-16);
+    const double u2 = __dmul_rn(__dadd_rn((double)((((unsigned long long)c[2] << 32) | c[3]) >> 11), 0.5), 1.1102230246251565e-16);
+    const double r = sqrt(__dmul_rn(-2.0, det_log(u1)));
+    double sn, cs;
+    det_sincos(__dmul_rn(6.283185307179586, u2), &sn, &cs);
+    z[0] = __dmul_rn(r, cs);
+    z[1] = __dmul_rn(r, sn);
+}
+
 // The clipping of System.closed_loop_rhs (rcognita/systems.py:241-243): np.clip(a, lo, hi).
 template <typename T, int M>
 __device__ __forceinline__ void clip_action(const SysDev<T> &S, T *a)

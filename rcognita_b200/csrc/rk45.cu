@@ -10,6 +10,7 @@
 // size feeds the fp64 time accumulation that decides on which solver step the controller
 // samples (section 3.3), so every multiply and add must round separately like numpy's.
 #include <cstdlib>
+#include <type_traits>
 
 #include "rcg_host.h"
 
@@ -63,11 +64,33 @@ static __constant__ Tableau kRK = {
 
 // One scipy RK45.step() for one lane.  Returns false if the step failed (TOO_SMALL_STEP).
 // On success t, h_abs, y, f are advanced and *attempts holds the number of rk_step calls.
-template <typename T, int SYS>
-__device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDev &sol, const T *a,
-                                              double &t, double &h_abs, T *y, T *f, int &attempts)
+// Full-state dimension: the state, followed by the disturbance when is_disturb (systems.py:139-145).
+template <int SYS, bool DIST> struct FullDim { static constexpr int n = SysDim<SYS>::n + (DIST ? DistDim<SYS>::nd : 0); };
+
+// The right-hand side the solver integrates.  DIST = false: _state_dyn of the state.  DIST = true:
+// System.closed_loop_rhs with is_disturb (systems.py:228-231, :247-248): state rows from _state_dyn(.., disturb), disturbance
+// rows from _disturb_dyn with the two normal draws of RHS call number `call` of this environment.
+template <typename T, int SYS, bool DIST>
+__device__ __forceinline__ void rhs_eval(const SysDev<T> &S, const DistDev &D, unsigned long long env, unsigned int call,
+                                         const T *y, const T *a, T *out)
 {
-    constexpr int N = SysDim<SYS>::n;
+    if constexpr (!DIST) {
+        state_dyn<T, SYS>(S, y, a, out);
+    } else {
+        constexpr int N = SysDim<SYS>::n;
+        state_dyn_disturbed<SYS>(S, y, a, y + N, out);
+        double z[2] = {0.0, 0.0};
+        if constexpr (SYS != RCG_SYS_2TANK) det_normal2(D.seed, env, call, z);
+        disturb_dyn<SYS>(D, y + N, z, out + N);
+    }
+}
+
+template <typename T, int SYS, bool DIST = false>
+__device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDev &sol, const T *a,
+                                              double &t, double &h_abs, T *y, T *f, int &attempts,
+                                              const DistDev &D = DistDev{}, unsigned long long env = 0, unsigned int call0 = 0)
+{
+    constexpr int N = FullDim<SYS, DIST>::n;
     const double t0 = t;
     const double min_step = 10 * fabs(nextafter(t0, (double)INFINITY) - t0);   // rk.py:118
     double ha;
@@ -94,30 +117,30 @@ __device__ __forceinline__ bool rk45_one_step(const SysDev<T> &S, const SolverDe
         for (int i = 0; i < N; ++i) K[0][i] = f[i];                            // FSAL, never refreshed
 #pragma unroll
         for (int i = 0; i < N; ++i) yt[i] = y[i] + (T(0) + K[0][i] * T(RK_A10)) * hT;
-        state_dyn<T, SYS>(S, yt, a, K[1]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 0u, yt, a, K[1]);
 #pragma unroll
         for (int i = 0; i < N; ++i) yt[i] = y[i] + ((T(0) + K[0][i] * T(RK_A20)) + K[1][i] * T(RK_A21)) * hT;
-        state_dyn<T, SYS>(S, yt, a, K[2]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 1u, yt, a, K[2]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yt[i] = y[i] + (((T(0) + K[0][i] * T(RK_A30)) + K[1][i] * T(RK_A31)) + K[2][i] * T(RK_A32)) * hT;
-        state_dyn<T, SYS>(S, yt, a, K[3]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 2u, yt, a, K[3]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yt[i] = y[i] + ((((T(0) + K[0][i] * T(RK_A40)) + K[1][i] * T(RK_A41)) + K[2][i] * T(RK_A42)) +
                             K[3][i] * T(RK_A43)) * hT;
-        state_dyn<T, SYS>(S, yt, a, K[4]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 3u, yt, a, K[4]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yt[i] = y[i] + (((((T(0) + K[0][i] * T(RK_A50)) + K[1][i] * T(RK_A51)) + K[2][i] * T(RK_A52)) +
                              K[3][i] * T(RK_A53)) + K[4][i] * T(RK_A54)) * hT;
-        state_dyn<T, SYS>(S, yt, a, K[5]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 4u, yt, a, K[5]);
         // y_new = y + h * np.dot(K[:-1].T, B)
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = y[i] + hT * ((((((T(0) + K[0][i] * T(RK_B0)) + K[1][i] * T(RK_B1)) + K[2][i] * T(RK_B2)) +
                                    K[3][i] * T(RK_B3)) + K[4][i] * T(RK_B4)) + K[5][i] * T(RK_B5));
-        state_dyn<T, SYS>(S, yn, a, K[6]);
+        rhs_eval<T, SYS, DIST>(S, D, env, call0 + 6u * (unsigned)(attempts - 1) + 5u, yn, a, K[6]);
 
         // error norm: rk.py:105-109, :146-147; common.py:63-65
         T sq = T(0);
@@ -181,17 +204,19 @@ __device__ __forceinline__ void log_row(const LogDev &G, int64_t E, int64_t e, i
 // (96 registers) and 2tank 6 (74) without spilling; 3wrobot (35 state/stage doubles more) spills beyond 4.
 __host__ __device__ constexpr int rk45_min_blocks(int sys) { return sys == RCG_SYS_3WROBOT_NI ? 5 : sys == RCG_SYS_2TANK ? 6 : 4; }
 
-template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false, int BLOCK = 128>
-__global__ void __launch_bounds__(BLOCK, rk45_min_blocks(SYS) * (128 / BLOCK))
+template <typename T, int SYS, bool CTRL, bool RDIAG, bool LOG = false, int BLOCK = 128, bool DIST = false>
+__global__ void __launch_bounds__(BLOCK, DIST ? 3 : rk45_min_blocks(SYS) * (128 / BLOCK))
 rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverDev sol,
             const __grid_constant__ ObjDev<T> O, int64_t E, T *__restrict__ y_g, T *__restrict__ f_g,
             double *__restrict__ t_g, double *__restrict__ h_g, int32_t *__restrict__ status_g,
             int32_t *__restrict__ nfev_g, int32_t *__restrict__ nsteps_g, T *__restrict__ action_g,
             double *__restrict__ clock_g, double sampling_time, int max_steps, T *__restrict__ state_sys_g,
             T *__restrict__ accum_g, int32_t *__restrict__ flag_g, int32_t *__restrict__ nsamples_g,
-            const __grid_constant__ LogDev G = LogDev{nullptr, nullptr, 0, 0})
+            const __grid_constant__ LogDev G = LogDev{nullptr, nullptr, 0, 0},
+            const __grid_constant__ DistDev D = DistDev{})
 {
-    constexpr int N = SysDim<SYS>::n, M = SysDim<SYS>::m;
+    // NS: rows of the state proper (stage_obj, state_sys, log); N: rows the solver integrates (+ the disturbance)
+    constexpr int NS = SysDim<SYS>::n, N = FullDim<SYS, DIST>::n, M = SysDim<SYS>::m;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     int st = status_g[e];
@@ -200,6 +225,7 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
         return;
     }
     T y[N], f[N], a[M], yprev[N];
+    const unsigned int call_base = DIST ? (unsigned int)nfev_g[e] : 0u;      // RHS calls made so far (1 at construction)
 #pragma unroll
     for (int i = 0; i < N; ++i) { y[i] = y_g[i * E + e]; f[i] = f_g[i * E + e]; yprev[i] = y[i]; }
 #pragma unroll
@@ -217,7 +243,8 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
 #pragma unroll
         for (int i = 0; i < N; ++i) yprev[i] = y[i];
         int attempts;
-        const bool ok = rk45_one_step<T, SYS>(S, sol, a, t, h_abs, y, f, attempts);
+        const bool ok = rk45_one_step<T, SYS, DIST>(S, sol, a, t, h_abs, y, f, attempts, D,
+                                                    (unsigned long long)(D.env_offset + e), call_base + (unsigned int)nf);
         nf += 6 * attempts;
         if (!ok) { st = RCG_FAILED; break; }                                   // base.py:203-204
         ++ns;
@@ -229,10 +256,10 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
                 break;
             }
             // held action: compute_action returns action_curr (:1492-1493); upd_accum_obj (:1093)
-            const T so = stage_obj<T, N, M, RDIAG>(O, y, a);
+            const T so = stage_obj<T, NS, M, RDIAG>(O, y, a);
             acc += so * (T)sampling_time;
             if constexpr (LOG) {                   // the row of a held-action step; sampling steps: rcg_log_rows
-                if ((step0 + ns) % G.every == 0) log_row<T, N, M>(G, E, e, log_cnt, t, y, so, acc, a);
+                if ((step0 + ns) % G.every == 0) log_row<T, NS, M>(G, E, e, log_cnt, t, y, so, acc, a);
             }
         }
     }
@@ -257,7 +284,7 @@ rk45_kernel(const __grid_constant__ SysDev<T> S, const __grid_constant__ SolverD
             // (receive_sys_state runs after compute_action, main_3wrobot_NI.py:421-424);
             // other lanes: receive_sys_state(y) has already happened for this step.
 #pragma unroll
-            for (int i = 0; i < N; ++i) state_sys_g[i * E + e] = flag ? yprev[i] : y[i];
+            for (int i = 0; i < NS; ++i) state_sys_g[i * E + e] = flag ? yprev[i] : y[i];
         }
     }
 }
@@ -305,6 +332,58 @@ rhs_kernel(const __grid_constant__ SysDev<T> S, int64_t E, const T *__restrict__
     for (int i = 0; i < N; ++i) f_g[i * E + e] = d[i];
 }
 
+static DistDev make_dist_dev(const rcg_disturb_t *d)
+{
+    DistDev D{};
+    for (int k = 0; k < 2; ++k) { D.sigma[k] = d->sigma[k]; D.mu[k] = d->mu[k]; D.tau[k] = d->tau[k]; }
+    D.seed = d->seed;
+    D.env_offset = d->env_offset;
+    return D;
+}
+
+// System.closed_loop_rhs with is_disturb = 1 on the full state [n + nd][E]; draws numbered by call_g (0 if NULL).
+// GIVEN != 0: the draws are taken from z_g [2][E] instead (parity with the reference under a patched randn()).
+template <int SYS>
+__global__ void __launch_bounds__(256)
+rhs_disturbed_kernel(const __grid_constant__ SysDev<double> S, const __grid_constant__ DistDev D, int64_t E,
+                     const double *__restrict__ y_g, double *action_g, const int32_t *__restrict__ call_g,
+                     const double *__restrict__ z_g, double *__restrict__ f_g, int clip)
+{
+    constexpr int N = SysDim<SYS>::n, ND = DistDim<SYS>::nd, M = SysDim<SYS>::m;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double y[N + ND], a[M], d[N + ND];
+#pragma unroll
+    for (int i = 0; i < N + ND; ++i) y[i] = y_g[i * E + e];
+#pragma unroll
+    for (int j = 0; j < M; ++j) a[j] = action_g[j * E + e];
+    if (clip) {
+        clip_action<double, M>(S, a);
+#pragma unroll
+        for (int j = 0; j < M; ++j) action_g[j * E + e] = a[j];
+    }
+    if (z_g) {
+        double z[2] = {z_g[e], ND > 1 ? z_g[E + e] : 0.0};
+        state_dyn_disturbed<SYS>(S, y, a, y + N, d);
+        disturb_dyn<SYS>(D, y + N, z, d + N);
+    } else {
+        rhs_eval<double, SYS, true>(S, D, (unsigned long long)(D.env_offset + e), call_g ? (unsigned int)call_g[e] : 0u, y, a, d);
+    }
+#pragma unroll
+    for (int i = 0; i < N + ND; ++i) f_g[i * E + e] = d[i];
+}
+
+__global__ void __launch_bounds__(256)
+normals_kernel(const __grid_constant__ DistDev D, int64_t E, const int32_t *__restrict__ call_g, int32_t call, double *__restrict__ z_g)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double z[2];
+    det_normal2(D.seed, (unsigned long long)(D.env_offset + e), call_g ? (unsigned int)call_g[e] : (unsigned int)call, z);
+    z_g[e] = z[0];
+    z_g[E + e] = z[1];
+}
+
 template <typename T, bool CLIP>
 static int launch_rhs(const rcg_system_t *sys, int64_t E, const T *y, T *action, T *f_out, void *stream)
 {
@@ -335,8 +414,22 @@ static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const Sys
                             const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
                             int32_t *nfev, int32_t *nsteps, T *action, double *clock, double sampling_time,
                             int max_steps, T *state_sys, T *accum, int32_t *flag, int32_t *nsamples,
-                            const LogDev *log = nullptr)
+                            const LogDev *log = nullptr, const DistDev *dist = nullptr)
 {
+    if constexpr (std::is_same<T, double>::value) {
+        if (dist) {                                // disturbance lanes: full state [n + dim_disturb][E]
+            const LogDev nolog{nullptr, nullptr, 0, 0};
+            if (rdiag)
+                rk45_kernel<T, SYS, CTRL, true, false, 128, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                                                      action, clock, sampling_time, max_steps, state_sys,
+                                                                                      accum, flag, nsamples, nolog, *dist);
+            else
+                rk45_kernel<T, SYS, CTRL, false, false, 128, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
+                                                                                       action, clock, sampling_time, max_steps, state_sys,
+                                                                                       accum, flag, nsamples, nolog, *dist);
+            return;
+        }
+    }
     if constexpr (CTRL) {
         if (log) {
             if (rdiag)
@@ -373,9 +466,15 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
                        int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status, int32_t *nfev,
                        int32_t *nsteps, T *action, double *clock, double sampling_time, int max_steps,
                        T *state_sys, T *accum, int32_t *flag, int32_t *nsamples, void *stream,
-                       const rcg_log_t *log_h = nullptr)
+                       const rcg_log_t *log_h = nullptr, const rcg_disturb_t *dist_h = nullptr)
 {
     RCG_REQUIRE(sys && sol_h && (E <= 0 || (y && f && t && h_abs && status && action)), "%s: null argument", what);
+    DistDev distd{};
+    if (dist_h) {
+        RCG_REQUIRE(!log_h && (nfev || E <= 0), "%s: disturbance lanes need nfev (it numbers the random draws) and no log", what);
+        distd = make_dist_dev(dist_h);
+    }
+    const DistDev *distp = dist_h ? &distd : nullptr;
     LogDev logd{nullptr, nullptr, 0, 0};
     if (log_h) {
         RCG_REQUIRE(CTRL && (E <= 0 || (log_h->rows && log_h->count && nsteps && accum)), "%s: log needs rows, count, nsteps and accum", what);
@@ -408,15 +507,15 @@ static int launch_rk45(const char *what, const rcg_system_t *sys, const rcg_solv
     switch (sys->sys_id) {
     case RCG_SYS_3WROBOT_NI:
         launch_rk45_sys<T, RCG_SYS_3WROBOT_NI, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
+                                                      action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp, distp);
         break;
     case RCG_SYS_3WROBOT:
         launch_rk45_sys<T, RCG_SYS_3WROBOT, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
+                                                   action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp, distp);
         break;
     default:
         launch_rk45_sys<T, RCG_SYS_2TANK, CTRL>(rdiag, grid, s, S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps,
-                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp);
+                                                 action, clock, sampling_time, max_steps, state_sys, accum, flag, nsamples, logp, distp);
         break;
     }
     return check_launch(what);
@@ -499,6 +598,57 @@ int rcg_rk45_advance_logged(const rcg_system_t *sys, const rcg_solver_t *sol, co
     return rcg::launch_rk45<double, true>("rcg_rk45_advance_logged", sys, sol, obj, E, y, f, t, h_abs, status, nfev, nsteps,
                                           action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
                                           nsamples, stream, log);
+}
+
+int rcg_rhs_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, int64_t E, const double *y_full, double *action,
+                      const int32_t *call, const double *normals, double *f_out, int32_t clip, void *stream)
+{
+    using namespace rcg;
+    RCG_REQUIRE(sys && dist && (E <= 0 || (y_full && action && f_out)), "rcg_rhs_disturbed: null argument");
+    RCG_REQUIRE(sys_n(sys->sys_id) > 0, "rcg_rhs_disturbed: unknown sys_id %d", sys->sys_id);
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    const SysDev<double> S = make_sys_dev<double>(sys);
+    const DistDev D = make_dist_dev(dist);
+    const unsigned grid = (unsigned)((E + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (sys->sys_id) {
+    case RCG_SYS_3WROBOT_NI: rhs_disturbed_kernel<RCG_SYS_3WROBOT_NI><<<grid, 256, 0, s>>>(S, D, E, y_full, action, call, normals, f_out, clip); break;
+    case RCG_SYS_3WROBOT:    rhs_disturbed_kernel<RCG_SYS_3WROBOT><<<grid, 256, 0, s>>>(S, D, E, y_full, action, call, normals, f_out, clip); break;
+    default:                 rhs_disturbed_kernel<RCG_SYS_2TANK><<<grid, 256, 0, s>>>(S, D, E, y_full, action, call, normals, f_out, clip); break;
+    }
+    return check_launch("rcg_rhs_disturbed");
+}
+
+int rcg_disturb_normals(const rcg_disturb_t *dist, int64_t E, const int32_t *call, int32_t call_all, double *normals, void *stream)
+{
+    using namespace rcg;
+    RCG_REQUIRE(dist && (E <= 0 || normals), "rcg_disturb_normals: null argument");
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    normals_kernel<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_dist_dev(dist), E, call, call_all, normals);
+    return check_launch("rcg_disturb_normals");
+}
+
+int rcg_rk45_step_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, const rcg_solver_t *sol, int64_t E,
+                            double *y_full, double *f_full, double *t, double *h_abs, int32_t *status, int32_t *nfev,
+                            double *action, void *stream)
+{
+    RCG_REQUIRE(dist, "rcg_rk45_step_disturbed: null disturbance descriptor");
+    return rcg::launch_rk45<double, false>("rcg_rk45_step_disturbed", sys, sol, nullptr, E, y_full, f_full, t, h_abs, status, nfev,
+                                           nullptr, action, nullptr, 0.0, 1, nullptr, nullptr, nullptr, nullptr, stream, nullptr, dist);
+}
+
+int rcg_rk45_advance_disturbed(const rcg_system_t *sys, const rcg_disturb_t *dist, const rcg_solver_t *sol,
+                               const rcg_objective_t *obj, int64_t E, double *y_full, double *f_full, double *t, double *h_abs,
+                               int32_t *status, int32_t *nfev, int32_t *nsteps, double *action, double *ctrl_clock,
+                               double sampling_time, int32_t max_steps, double *state_sys, double *accum,
+                               int32_t *sample_flag, int32_t *nsamples, void *stream)
+{
+    RCG_REQUIRE(dist, "rcg_rk45_advance_disturbed: null disturbance descriptor");
+    return rcg::launch_rk45<double, true>("rcg_rk45_advance_disturbed", sys, sol, obj, E, y_full, f_full, t, h_abs, status, nfev,
+                                          nsteps, action, ctrl_clock, sampling_time, max_steps, state_sys, accum, sample_flag,
+                                          nsamples, stream, nullptr, dist);
 }
 
 int rcg_rk45_advance_f32(const rcg_system_t *sys, const rcg_solver_t *sol, const rcg_objective_t *obj, int64_t E,

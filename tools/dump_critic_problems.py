@@ -21,10 +21,10 @@ for name in ("config3", "config4"):
     eng = ClosedLoopEngine(c["system"], x0, cand, pars=c["pars"], ctrl_bnds=c["bnds"], mode=c["mode"], Nactor=c["N"],
                            dt=c["dt"], pred_step_size=c["dt"] * c["psm"], t1=1e9, R1=c["R1"], observation_target=c["target"],
                            critic_struct=c["cs"], critic_fit=True, Ncritic=4, buffer_size=10, action_init=c["a_init"])
-    for k in range(1, 41):
+    for k in range(1, 181):
         wprev_before = eng.w_prev.clone()
         eng.run_interval()
-        if k in (3, 8, 12, 20, 40):
+        if k in (3, 8, 12, 20, 40, 100, 180):
             out[f"{name}_k{k}_obs_buf"] = eng.obs_buf.cpu().numpy()
             out[f"{name}_k{k}_act_buf"] = eng.act_buf.cpu().numpy()
             out[f"{name}_k{k}_w_prev"] = wprev_before.cpu().numpy()
