@@ -313,6 +313,11 @@ int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E,
                     const double *obs_buf, const double *act_buf, const double *w, const double *w_prev,
                     double *Jc_out, void *stream);
 
+/* fp32 twin of rcg_critic_cost (the fp64-vs-fp32 tolerance report of BASELINE config 4). */
+int rcg_critic_cost_f32(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W,
+                        const float *obs_buf, const float *act_buf, const float *w, const float *w_prev,
+                        float *Jc_out, void *stream);
+
 /* CtrlOptPred._critic_optimizer (rcognita/controllers.py:1248-1271) for E environments: the minimiser of
  * _critic_cost(w) subject to w_min <= w_i <= w_max (the reference's Bounds(Wmin, Wmax), controllers.py:1024-1039,
  * uniform per structure), started from w_init [dimc] (w_critic_init, shared by all environments; NULL = start

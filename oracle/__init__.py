@@ -54,6 +54,16 @@ class Rk45T(C.Structure):
                 ("status", C.c_int), ("nfev", C.c_long)]
 
 
+class DistT(C.Structure):
+    _fields_ = [("sigma", C.c_double * 2), ("mu", C.c_double * 2), ("tau", C.c_double * 2), ("seed", C.c_ulonglong)]
+
+
+class Rk45dT(C.Structure):
+    _fields_ = [("t", C.c_double), ("t_bound", C.c_double), ("h_abs", C.c_double), ("max_step", C.c_double),
+                ("rtol", C.c_double), ("atol", C.c_double), ("y", C.c_double * 7), ("f", C.c_double * 7),
+                ("status", C.c_int), ("nfull", C.c_int), ("nfev", C.c_long), ("env", C.c_ulonglong)]
+
+
 class EnvT(C.Structure):
     _fields_ = [("r", Rk45T), ("sys_action", C.c_double * MAX_M), ("action_curr", C.c_double * MAX_M),
                 ("state_sys", C.c_double * MAX_N), ("ctrl_clock", C.c_double), ("accum", C.c_double),
@@ -64,7 +74,7 @@ class EnvT(C.Structure):
 def build(force: bool = False) -> str:
     """Compile ``librcg_oracle.so`` (gcc; OpenMP if the toolchain has it)."""
     srcs = [os.path.join(_HERE, "rcg_oracle.c"), os.path.join(_HERE, "rcg_oracle_opt.c"),
-            os.path.join(_HERE, "rcg_oracle_critic.c")]
+            os.path.join(_HERE, "rcg_oracle_critic.c"), os.path.join(_HERE, "rcg_oracle_disturb.c")]
     hdr = os.path.join(_HERE, "rcg_oracle.h")
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(f) for f in srcs + [hdr])):
@@ -134,6 +144,20 @@ def lib():
                                              + [C.c_double] * 10 + [C.c_int, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp,
                                                                     dp, dp, dp, C.c_int, ip])
         L.orc_closed_loop_critic.restype = C.c_longlong
+        L.orc_state_dyn_disturbed.argtypes = [C.POINTER(SysT), dp, dp, dp, dp]
+        L.orc_state_dyn_disturbed.restype = None
+        L.orc_disturb_dyn.argtypes = [C.POINTER(SysT), C.POINTER(DistT), dp, dp, dp]
+        L.orc_disturb_dyn.restype = None
+        L.orc_log.argtypes = [C.c_double]
+        L.orc_log.restype = C.c_double
+        L.orc_normal2.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint, dp]
+        L.orc_normal2.restype = None
+        L.orc_closed_loop_rhs_disturbed.argtypes = [C.POINTER(SysT), C.POINTER(DistT), dp, dp, C.c_ulonglong, C.c_uint, dp, dp]
+        L.orc_closed_loop_rhs_disturbed.restype = None
+        L.orc_rk45d_init.argtypes = [C.POINTER(Rk45dT), C.POINTER(SysT), C.POINTER(DistT), C.c_ulonglong, dp, dp] + [C.c_double] * 6
+        L.orc_rk45d_init.restype = None
+        L.orc_rk45d_step.argtypes = [C.POINTER(Rk45dT), C.POINTER(SysT), C.POINTER(DistT), dp]
+        L.orc_rk45d_step.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
         L.orc_has_openmp.restype = C.c_int
         L.orc_sincos.argtypes = [C.c_double, dp, dp]
@@ -450,6 +474,96 @@ def closed_loop_critic(c, s, state_init, cand, action_init, sampling_time, t0, t
         raise ValueError("buffer_size exceeds the oracle's ORC_MAX_BUF")
     return {"y": yf, "t": tf, "accum": acc, "nsteps": nst, "nsamples": nsa, "nfits": nft, "w_critic": wf, "Jc": Jc,
             "obs_buf": obf, "act_buf": abf, "traj": traj[: rows.value], "total_steps": int(total)}
+
+
+DIST_DIM = {0: 2, 1: 2, 2: 1}
+
+
+def make_dist(pars_disturb, seed=0) -> DistT:
+    """``pars_disturb = [sigma_disturb, mu_disturb, tau_disturb]`` (each ``[dim_disturb]``) + the key of the draw stream."""
+    d = DistT()
+    p = np.zeros((3, 2))
+    for i, row in enumerate(pars_disturb):
+        r = np.atleast_1d(np.asarray(row, dtype=np.float64))
+        p[i, : r.size] = r[:2]
+    for k in range(2):
+        d.sigma[k], d.mu[k], d.tau[k] = p[0, k], p[1, k], p[2, k]
+    d.seed = int(seed)
+    return d
+
+
+def state_dyn_disturbed(s, state, action, disturb):
+    st, stp = _d(state)
+    ac, acp = _d(np.atleast_1d(action))
+    q, qp = _d(np.resize(np.atleast_1d(np.asarray(disturb, dtype=np.float64)), 2))
+    out = np.zeros(s.n)
+    lib().orc_state_dyn_disturbed(C.byref(s), stp, acp, qp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def disturb_dyn(s, dist, disturb, z):
+    """``_disturb_dyn`` given the draws ``z`` (one ``randn()`` per component)."""
+    nd = DIST_DIM[s.sys_id]
+    q, qp = _d(np.resize(np.atleast_1d(np.asarray(disturb, dtype=np.float64)), 2))
+    zz, zp = _d(np.resize(np.atleast_1d(np.asarray(z, dtype=np.float64)), 2))
+    out = np.zeros(2)
+    lib().orc_disturb_dyn(C.byref(s), C.byref(dist), qp, zp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[:nd]
+
+
+def closed_loop_rhs_disturbed(s, dist, state_full, action, env=0, call=0, z=None):
+    """(rhs_full, clipped action) of ``closed_loop_rhs`` with ``is_disturb = 1``; ``z`` given = patched ``randn``."""
+    nd = DIST_DIM[s.sys_id]
+    y, yp = _d(state_full)
+    ac = np.array(np.atleast_1d(action), dtype=np.float64)
+    zz, zp = (None, _null()) if z is None else _d(np.resize(np.atleast_1d(np.asarray(z, dtype=np.float64)), 2))
+    out = np.zeros(s.n + 2)
+    lib().orc_closed_loop_rhs_disturbed(C.byref(s), C.byref(dist), yp, ac.ctypes.data_as(C.POINTER(C.c_double)), int(env), int(call),
+                                        zp, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out[: s.n + nd], ac
+
+
+def normal2(seed, env, call):
+    """The two standard-normal draws of RHS call ``call`` of global environment ``env`` (the specified stream)."""
+    z = np.zeros(2)
+    lib().orc_normal2(int(seed), int(env), int(call), z.ctypes.data_as(C.POINTER(C.c_double)))
+    return z
+
+
+def det_log(x):
+    return lib().orc_log(float(x))
+
+
+class RK45Disturbed:
+    """scipy-RK45-like solver lane on the full state ``[state, disturb]`` of a disturbed system."""
+
+    def __init__(self, s, dist, y0_full, t0, t_bound, max_step, env=0, first_step=1e-6, rtol=1e-3, atol=1e-5, action=None):
+        self.s, self.dist = s, dist
+        self.r = Rk45dT()
+        self.action = np.zeros(MAX_M) if action is None else np.array(action, dtype=np.float64)
+        y0a, y0p = _d(y0_full)
+        lib().orc_rk45d_init(C.byref(self.r), C.byref(s), C.byref(dist), int(env), y0p, self._ap(), t0, t_bound, max_step,
+                             first_step, rtol, atol)
+
+    def _ap(self):
+        return self.action.ctypes.data_as(C.POINTER(C.c_double))
+
+    def receive_action(self, action):
+        a = np.atleast_1d(np.asarray(action, dtype=np.float64))
+        self.action[: a.size] = a
+
+    def step(self):
+        rc = lib().orc_rk45d_step(C.byref(self.r), C.byref(self.s), C.byref(self.dist), self._ap())
+        if rc < 0:
+            raise RuntimeError("Attempt to step on a failed or finished solver.")
+        return rc
+
+    t = property(lambda self: self.r.t)
+    h_abs = property(lambda self: self.r.h_abs)
+    nfev = property(lambda self: self.r.nfev)
+    status = property(lambda self: STATUS[self.r.status])
+    y = property(lambda self: np.array(self.r.y[: self.r.nfull]))
+    f = property(lambda self: np.array(self.r.f[: self.r.nfull]))
 
 
 def sincos(x):

@@ -160,6 +160,29 @@ long long orc_closed_loop_critic(const orc_ctrl_t *c, const orc_sys_t *s, int E,
                                  int nthreads, const double *w_replay, int n_replay, double *y_final, double *t_final,
                                  double *accum, int *nsteps, int *nsamples, int *nfits, double *w_final, double *Jc_final,
                                  double *obs_buf_final, double *act_buf_final, double *traj, int traj_cap, int *traj_rows);
+/* rcg_oracle_disturb.c: disturbance lanes, System(is_disturb = 1) (ref: systems.py:228-231, :247-248, :316-318, :373-376,
+ * :325-345, :384-394); the normal draws come from a counter-based stream shared (as a specification) with the CUDA kernels. */
+#define ORC_MAX_NFULL 7
+typedef struct {
+    double sigma[2], mu[2], tau[2];     /* pars_disturb = [sigma_disturb, mu_disturb, tau_disturb] */
+    unsigned long long seed;
+} orc_dist_t;
+typedef struct {
+    double t, t_bound, h_abs, max_step, rtol, atol;
+    double y[ORC_MAX_NFULL], f[ORC_MAX_NFULL];
+    int status, nfull;
+    long nfev;
+    unsigned long long env;
+} orc_rk45d_t;
+void   orc_state_dyn_disturbed(const orc_sys_t *s, const double *x, const double *a, const double *q, double *d);
+void   orc_disturb_dyn(const orc_sys_t *s, const orc_dist_t *D, const double *q, const double *z, double *dq);
+double orc_log(double x);
+void   orc_normal2(unsigned long long seed, unsigned long long env, unsigned int call, double *z);
+void   orc_closed_loop_rhs_disturbed(const orc_sys_t *s, const orc_dist_t *D, const double *y_full, double *action,
+                                     unsigned long long env, unsigned int call, const double *z_given, double *rhs);
+void   orc_rk45d_init(orc_rk45d_t *r, const orc_sys_t *s, const orc_dist_t *D, unsigned long long env, const double *y0_full,
+                      double *action, double t0, double t_bound, double max_step, double first_step, double rtol, double atol);
+int    orc_rk45d_step(orc_rk45d_t *r, const orc_sys_t *s, const orc_dist_t *D, double *action);
 void   orc_nominal_ni(double ctrl_gain, const orc_sys_t *s, const double *obs, double *action);
 int       orc_num_threads(void);
 int       orc_has_openmp(void);

@@ -40,6 +40,14 @@ class RcgObjective(C.Structure):
                 ("target", C.c_double * MAX_N)]
 
 
+class RcgDisturb(C.Structure):
+    _fields_ = [("sigma", C.c_double * 2), ("mu", C.c_double * 2), ("tau", C.c_double * 2), ("seed", C.c_uint64),
+                ("env_offset", C.c_int64)]
+
+
+DIST_DIM = {0: 2, 1: 2, 2: 1}          # dim_disturb per system (the presets' values)
+
+
 class RcgLog(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("count", C.c_void_p), ("capacity", C.c_int32), ("every", C.c_int32)]
 
@@ -72,6 +80,11 @@ def _load():
         getattr(L, name).argtypes = [sysp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp, vp]
     L.rcg_rk45_advance_logged.argtypes = ([sysp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp,
                                                                                 C.POINTER(RcgLog), vp])
+    distp = C.POINTER(RcgDisturb)
+    L.rcg_rhs_disturbed.argtypes = [sysp, distp, i64, vp, vp, vp, vp, vp, i32, vp]
+    L.rcg_disturb_normals.argtypes = [distp, i64, vp, i32, vp, vp]
+    L.rcg_rk45_step_disturbed.argtypes = [sysp, distp, solp, i64] + [vp] * 7 + [vp]
+    L.rcg_rk45_advance_disturbed.argtypes = [sysp, distp, solp, objp, i64] + [vp] * 9 + [dbl, i32, vp, vp, vp, vp, vp]
     L.rcg_log_rows.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, vp, vp, C.POINTER(RcgLog), vp]
     for name in ("rcg_actor_cost", "rcg_actor_cost_f32"):
         getattr(L, name).argtypes = [sysp, objp, i64, i32, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, dbl, vp]
@@ -88,6 +101,7 @@ def _load():
     L.rcg_stage_obj.argtypes = [objp, i32, i32, i64, vp, vp, vp, vp, dbl, vp]
     L.rcg_critic.argtypes = [objp, i32, i32, i64, vp, vp, vp, i32, vp, vp]
     L.rcg_critic_cost.argtypes = [objp, i32, i32, i64, i32, vp, vp, vp, vp, vp, vp]
+    L.rcg_critic_cost_f32.argtypes = [objp, i32, i32, i64, i32, vp, vp, vp, vp, vp, vp]
     L.rcg_critic_fit.argtypes = [objp, i32, i32, i64, vp, vp, vp, dbl, dbl, vp, vp, vp, i32, i32, vp, vp]
     L.rcg_ctrl_sample.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
     L.rcg_push_buffers.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, vp, vp]
@@ -99,8 +113,9 @@ lib = _load()
 EXPORTS = [
     "rcg_version", "rcg_last_error_string", "rcg_device_count", "rcg_dim_state", "rcg_dim_input", "rcg_dim_critic",
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
-    "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_rk45_advance_logged", "rcg_log_rows", "rcg_actor_cost", "rcg_actor_cost_f32",
-    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_actor_ilqr_workspace_bytes", "rcg_actor_ilqr", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
+    "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_rk45_advance_logged", "rcg_log_rows",
+    "rcg_rhs_disturbed", "rcg_disturb_normals", "rcg_rk45_step_disturbed", "rcg_rk45_advance_disturbed", "rcg_actor_cost", "rcg_actor_cost_f32",
+    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_actor_ilqr_workspace_bytes", "rcg_actor_ilqr", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_cost_f32", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 
 
@@ -126,6 +141,21 @@ def make_system(name: str, pars=(), ctrl_bnds=None) -> RcgSystem:
     for k in range(min(b.shape[0], MAX_M)):
         s.lo[k], s.hi[k] = b[k, 0], b[k, 1]
     return s
+
+
+def make_disturb(pars_disturb, seed=0, env_offset=0) -> RcgDisturb:
+    """Descriptor of ``pars_disturb = [sigma_disturb, mu_disturb, tau_disturb]`` (rcognita/systems.py:303-306, :366-369) plus the
+    key of the per-environment draw stream and the global index of lane 0."""
+    d = RcgDisturb()
+    rows = list(pars_disturb) if len(pars_disturb) else []
+    p = np.zeros((3, 2))
+    for i, row in enumerate(rows[:3]):
+        r = np.atleast_1d(np.asarray(row, dtype=np.float64)).reshape(-1)
+        p[i, : min(2, r.size)] = r[:2]
+    for k in range(2):
+        d.sigma[k], d.mu[k], d.tau[k] = p[0, k], p[1, k], p[2, k]
+    d.seed, d.env_offset = int(seed), int(env_offset)
+    return d
 
 
 def make_objective(n: int, m: int, mode="MPC", Nactor=1, pred_step_size=0.1, gamma=1.0, Ncritic=4, buffer_size=20,

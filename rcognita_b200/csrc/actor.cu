@@ -27,6 +27,18 @@ static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, 
         }
         encode = (EncodeFn)fn;
     }
+    // The descriptor depends only on (base, element size, shape, box): a controller calls with the same candidate array
+    // at every sample, so the last few descriptors are kept per thread instead of being re-encoded on every launch.
+    struct Key { const void *base; size_t elem; int64_t cols; int rows, box_rows; };
+    constexpr int kCache = 8;
+    static thread_local Key keys[kCache];
+    static thread_local CUtensorMap maps[kCache];
+    static thread_local int used = 0, next = 0;
+    for (int i = 0; i < used; ++i)
+        if (keys[i].base == base && keys[i].elem == elem && keys[i].cols == cols && keys[i].rows == rows && keys[i].box_rows == box_rows) {
+            *tm = maps[i];
+            return 0;
+        }
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)cols * elem};
     const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
@@ -39,6 +51,10 @@ static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, 
         set_error("rcg_actor_cost: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
         return RCG_EINVAL;
     }
+    keys[next] = Key{base, elem, cols, rows, box_rows};
+    maps[next] = *tm;
+    next = (next + 1) % kCache;
+    if (used < kCache) ++used;
     return 0;
 }
 
@@ -93,8 +109,6 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     L.grid = (unsigned)(blocks_needed < max_grid ? blocks_needed : max_grid);
     L.sms = sms;
     L.blocks_needed = blocks_needed;
-    L.ctas_per_sm_cap = 0;
-    if (const char *e = getenv("RCG_ACTOR_CTAS_PER_SM")) L.ctas_per_sm_cap = atoi(e);      // experiment: 0 = default, -1 = non-persistent
     // TMA-staged kernel: per-environment candidates, diagonal R, a specialised horizon, and a candidate
     // count whose lane mapping is a contiguous box (C a multiple of 32, or a power of two below 32)
     L.use_tma = false;

@@ -721,7 +721,6 @@ struct ActorLaunch {
     unsigned grid;
     int sms;
     int64_t blocks_needed;
-    int ctas_per_sm_cap;
     bool use_tma;              // per-env candidates staged by TMA (tmap valid)
     bool use_tma_rt;           // ... runtime-horizon variant (tmap box = kRtChunk stages)
     CUtensorMap tmap;
@@ -736,11 +735,8 @@ static void launch_actor_one(const ActorLaunch<T> &L)
             constexpr int LL = NA * SysDim<SYS>::m;
             auto kern = actor_cost_tma_kernel<T, SYS, MODE, CS, NA, LEAN>;
             const size_t smem = (size_t)tma_smem_bytes<T, LL>();
-            static bool configured = false;                   // per instantiation
-            if (!configured) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                configured = true;
-            }
+            static unsigned long long configured = 0;         // per instantiation, one bit per device
+            ensure_dyn_smem(kern, smem, configured);
             // Grid: at least one resident wave (sms x CTAs per SM); beyond that one CTA per kEnvsPerWarp environments
             // per warp rather than a persistent grid: short-lived CTAs let the block scheduler slot the concurrently
             // running rk45_advance launch of another environment block (engine.PipelinedLoop) between them as they
@@ -748,8 +744,6 @@ static void launch_actor_one(const ActorLaunch<T> &L)
             constexpr int kEnvsPerWarp = 4;
             int64_t pg = (int64_t)L.sms * tma_min_ctas<T, LL>();
             if (L.blocks_needed / kEnvsPerWarp > pg) pg = L.blocks_needed / kEnvsPerWarp;
-            if (L.ctas_per_sm_cap > 0) pg = (int64_t)L.sms * L.ctas_per_sm_cap;                      // RCG_ACTOR_CTAS_PER_SM: experiments
-            if (L.ctas_per_sm_cap < 0) pg = L.blocks_needed / (-L.ctas_per_sm_cap);
             const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
             kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,
                                                          L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
@@ -760,11 +754,8 @@ static void launch_actor_one(const ActorLaunch<T> &L)
         if (L.use_tma_rt) {
             auto kern = actor_cost_tma_rt_kernel<T, SYS, MODE, CS, LEAN>;
             const size_t smem = (size_t)tma_rt_smem_bytes<T, SysDim<SYS>::m>();
-            static bool configured = false;                   // per instantiation
-            if (!configured) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                configured = true;
-            }
+            static unsigned long long configured = 0;         // per instantiation, one bit per device
+            ensure_dyn_smem(kern, smem, configured);
             const int64_t pg = (int64_t)L.sms * 2;
             const unsigned grid = (unsigned)(L.blocks_needed < pg ? L.blocks_needed : pg);
             kern<<<grid, kActorThreads, smem, L.stream>>>(L.tmap, L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J,

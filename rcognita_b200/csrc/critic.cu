@@ -122,6 +122,38 @@ static int dims_ok(int n, int m) { return (n == 3 && m == 2) || (n == 5 && m == 
     else if (n == 5) { CALL(5, 2) }          \
     else { CALL(2, 1) }
 
+template <typename T>
+static int launch_critic_cost(const char *what, const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W,
+                              const T *obs_buf, const T *act_buf, const T *w, const T *w_prev, T *Jc_out, void *stream)
+{
+    RCG_REQUIRE(obj && (E <= 0 || (obs_buf && act_buf && w && w_prev && Jc_out)), "%s: null argument", what);
+    RCG_REQUIRE(dims_ok(n, m), "%s: unsupported dims n=%d m=%d", what, n, m);
+    RCG_REQUIRE(obj->critic_struct >= 0 && obj->critic_struct <= 3, "%s: unknown critic_struct %d", what, obj->critic_struct);
+    RCG_REQUIRE(W >= 1, "%s: W must be >= 1", what);
+    RCG_REQUIRE(obj->Ncritic >= 1 && obj->Ncritic <= obj->buffer_size, "%s: Ncritic %d must be in [1, buffer_size = %d]", what,
+                obj->Ncritic, obj->buffer_size);
+    if (int rc = require_device()) return rc;
+    if (E <= 0) return 0;
+    const ObjDev<T> O = make_obj_dev<T>(obj, n, m);
+    const bool rd = obj_rdiag(obj, n + m);
+    const unsigned grid = (unsigned)((E * (int64_t)W + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+#define CC(NN, MM, CS)                                                                                                  \
+    if (rd) critic_cost_kernel<T, NN, MM, CS, true><<<grid, 256, 0, s>>>(O, E, W, obs_buf, act_buf, w, w_prev, Jc_out); \
+    else critic_cost_kernel<T, NN, MM, CS, false><<<grid, 256, 0, s>>>(O, E, W, obs_buf, act_buf, w, w_prev, Jc_out);
+#define CALL(NN, MM)                     \
+    switch (obj->critic_struct) {        \
+    case 0: CC(NN, MM, 0) break;         \
+    case 1: CC(NN, MM, 1) break;         \
+    case 2: CC(NN, MM, 2) break;         \
+    default: CC(NN, MM, 3) break;        \
+    }
+    RCG_DISPATCH_NM(n, m, CALL)
+#undef CALL
+#undef CC
+    return check_launch(what);
+}
+
 }  // namespace rcg
 
 extern "C" {
@@ -174,34 +206,13 @@ int rcg_critic(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, cons
 int rcg_critic_cost(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W, const double *obs_buf,
                     const double *act_buf, const double *w, const double *w_prev, double *Jc_out, void *stream)
 {
-    using namespace rcg;
-    RCG_REQUIRE(obj && (E <= 0 || (obs_buf && act_buf && w && w_prev && Jc_out)), "rcg_critic_cost: null argument");
-    RCG_REQUIRE(dims_ok(n, m), "rcg_critic_cost: unsupported dims n=%d m=%d", n, m);
-    RCG_REQUIRE(obj->critic_struct >= 0 && obj->critic_struct <= 3, "rcg_critic_cost: unknown critic_struct %d",
-                obj->critic_struct);
-    RCG_REQUIRE(W >= 1, "rcg_critic_cost: W must be >= 1");
-    RCG_REQUIRE(obj->Ncritic >= 1 && obj->Ncritic <= obj->buffer_size,
-                "rcg_critic_cost: Ncritic %d must be in [1, buffer_size = %d]", obj->Ncritic, obj->buffer_size);
-    if (int rc = require_device()) return rc;
-    if (E <= 0) return 0;
-    const ObjDev<double> O = make_obj_dev<double>(obj, n, m);
-    const bool rd = obj_rdiag(obj, n + m);
-    const unsigned grid = (unsigned)((E * (int64_t)W + 255) / 256);
-    cudaStream_t s = (cudaStream_t)stream;
-#define CC(NN, MM, CS)                                                                                                  \
-    if (rd) critic_cost_kernel<double, NN, MM, CS, true><<<grid, 256, 0, s>>>(O, E, W, obs_buf, act_buf, w, w_prev, Jc_out); \
-    else critic_cost_kernel<double, NN, MM, CS, false><<<grid, 256, 0, s>>>(O, E, W, obs_buf, act_buf, w, w_prev, Jc_out);
-#define CALL(NN, MM)                     \
-    switch (obj->critic_struct) {        \
-    case 0: CC(NN, MM, 0) break;         \
-    case 1: CC(NN, MM, 1) break;         \
-    case 2: CC(NN, MM, 2) break;         \
-    default: CC(NN, MM, 3) break;        \
-    }
-    RCG_DISPATCH_NM(n, m, CALL)
-#undef CALL
-#undef CC
-    return check_launch("rcg_critic_cost");
+    return rcg::launch_critic_cost<double>("rcg_critic_cost", obj, n, m, E, W, obs_buf, act_buf, w, w_prev, Jc_out, stream);
+}
+
+int rcg_critic_cost_f32(const rcg_objective_t *obj, int32_t n, int32_t m, int64_t E, int32_t W, const float *obs_buf,
+                        const float *act_buf, const float *w, const float *w_prev, float *Jc_out, void *stream)
+{
+    return rcg::launch_critic_cost<float>("rcg_critic_cost_f32", obj, n, m, E, W, obs_buf, act_buf, w, w_prev, Jc_out, stream);
 }
 
 int rcg_ctrl_sample(int64_t E, const double *t, double *clock, double period, const int32_t *in_mask, int32_t *mask_out,

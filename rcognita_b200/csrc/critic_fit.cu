@@ -724,8 +724,8 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     {                                                                                                                     \
         auto kern = critic_fit3_kernel<NN, MM, CS, RD>;                                                                   \
         const size_t smem = (size_t)2 * dim_critic_c(CS, NN, MM) * 128 * sizeof(double);                                  \
-        static bool configured = false;                                                                                   \
-        if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; } \
+        static unsigned long long configured = 0;                                                                         \
+        ensure_dyn_smem(kern, smem, configured);                                                                          \
         kern<<<grid, 128, smem, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mask, mu_rel, outer, newton,  \
                                      evals, update_prev, Jc_out, max_ls, lane_list, lane_count, todo_list, todo_count);          \
     }

@@ -16,6 +16,20 @@ void set_error(const char *fmt, ...);
 int  check_launch(const char *what);          // cudaGetLastError() after a launch, counts it
 int  require_device();                        // 0, or RCG_ENODEV with the error string set
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: `done` (a static of the calling
+// instantiation) keeps one bit per device so that a second GPU in the same process gets it too.
+template <class K>
+inline void ensure_dyn_smem(K kern, size_t smem, unsigned long long &done)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done & bit)) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        done |= bit;
+    }
+}
+
 inline bool is_diag(const double *R, int p)
 {
     for (int i = 0; i < p; ++i)

@@ -402,13 +402,6 @@ static int launch_rhs(const rcg_system_t *sys, int64_t E, const T *y, T *action,
     return check_launch("rcg_rhs");
 }
 
-static int rk45_block()
-{
-    static int b = -1;
-    if (b < 0) { const char *e = getenv("RCG_RK45_BLOCK"); b = e ? atoi(e) : 128; }
-    return b;
-}
-
 template <typename T, int SYS, bool CTRL>
 static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const SysDev<T> &S, const SolverDev &sol,
                             const ObjDev<T> &O, int64_t E, T *y, T *f, double *t, double *h_abs, int32_t *status,
@@ -443,15 +436,7 @@ static void launch_rk45_sys(bool rdiag, unsigned grid, cudaStream_t s, const Sys
             return;
         }
     }
-    if (rdiag && rk45_block() == 64)
-        rk45_kernel<T, SYS, CTRL, true, false, 64><<<(unsigned)((E + 63) / 64), 64, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
-                                                             clock, sampling_time, max_steps, state_sys, accum, flag,
-                                                             nsamples);
-    else if (rdiag && rk45_block() == 32)
-        rk45_kernel<T, SYS, CTRL, true, false, 32><<<(unsigned)((E + 31) / 32), 32, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
-                                                             clock, sampling_time, max_steps, state_sys, accum, flag,
-                                                             nsamples);
-    else if (rdiag)
+    if (rdiag)
         rk45_kernel<T, SYS, CTRL, true><<<grid, 128, 0, s>>>(S, sol, O, E, y, f, t, h_abs, status, nfev, nsteps, action,
                                                              clock, sampling_time, max_steps, state_sys, accum, flag,
                                                              nsamples);

@@ -27,6 +27,10 @@ def _ptr(t, dtype=None, shape=None, name="tensor", optional=False):
         raise ValueError(f"{name} is required")
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (rcognita_b200 has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the current device's current stream: a tensor of another GPU would be an illegal address
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           f"wrap the call in `with torch.cuda.device({t.device.index}):`")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -75,6 +79,58 @@ def rk45_step(sysd, sol, y, f, t, h_abs, status, action, nfev=None):
                 _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),
                 _ptr(nfev, _I32, (E,), "nfev", optional=True), _ptr(action, y.dtype, (m, E), "action"), _stream()),
              "rcg_rk45_step")
+
+
+def rhs_disturbed(sysd, distd, y_full, action, call=None, normals=None, out=None, clip=True):
+    """``System.closed_loop_rhs`` with ``is_disturb = 1`` on the full state ``[n + nd, E]``: clips ``action`` in place
+    (``clip``), ``out[:n] = _state_dyn(state, action, disturb)``, ``out[n:] = _disturb_dyn(disturb)`` with the draws
+    ``normals`` ``[2, E]`` when given, else the environment's stream at RHS call number ``call`` ``[E]`` int32 (0 if None)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    nf = n + _C.DIST_DIM[sysd.sys_id]
+    E = y_full.shape[1]
+    out = torch.empty_like(y_full) if out is None else out
+    _C.check(_C.lib.rcg_rhs_disturbed(C.byref(sysd), C.byref(distd), E, _ptr(y_full, _F64, (nf, E), "y_full"),
+                                      _ptr(action, _F64, (m, E), "action"), _ptr(call, _I32, (E,), "call", optional=True),
+                                      _ptr(normals, _F64, (2, E), "normals", optional=True), _ptr(out, _F64, (nf, E), "out"),
+                                      int(bool(clip)), _stream()), "rcg_rhs_disturbed")
+    return out
+
+
+def disturb_normals(distd, E, call=0, device=None):
+    """The two standard-normal draws ``[2, E]`` of RHS call ``call`` (an int, or ``[E]`` int32) of every environment."""
+    per_lane = isinstance(call, torch.Tensor)
+    out = torch.empty((2, E), dtype=_F64, device=call.device if per_lane else device)
+    _C.check(_C.lib.rcg_disturb_normals(C.byref(distd), E, _ptr(call, _I32, (E,), "call") if per_lane else C.c_void_p(0),
+                                        0 if per_lane else int(call), _ptr(out), _stream()), "rcg_disturb_normals")
+    return out
+
+
+def rk45_step_disturbed(sysd, distd, sol, y_full, f_full, t, h_abs, status, action, nfev):
+    """``Simulator.sim_step`` of a disturbed system: one accepted RK45 step of the full state per running lane."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    nf = n + _C.DIST_DIM[sysd.sys_id]
+    E = y_full.shape[1]
+    _C.check(_C.lib.rcg_rk45_step_disturbed(C.byref(sysd), C.byref(distd), C.byref(sol), E, _ptr(y_full, _F64, (nf, E), "y_full"),
+                                            _ptr(f_full, _F64, (nf, E), "f_full"), _ptr(t, _F64, (E,), "t"),
+                                            _ptr(h_abs, _F64, (E,), "h_abs"), _ptr(status, _I32, (E,), "status"),
+                                            _ptr(nfev, _I32, (E,), "nfev"), _ptr(action, _F64, (m, E), "action"), _stream()),
+             "rcg_rk45_step_disturbed")
+
+
+def rk45_advance_disturbed(sysd, distd, sol, obj, y_full, f_full, t, h_abs, status, action, ctrl_clock, sampling_time, max_steps,
+                           nfev, state_sys=None, accum=None, sample_flag=None, nsteps=None, nsamples=None):
+    """``rk45_advance`` on the full state of a disturbed system (``state_sys`` / ``accum`` see the state rows only)."""
+    n, m = _C.SYS_DIMS[sysd.sys_id]
+    nf = n + _C.DIST_DIM[sysd.sys_id]
+    E = y_full.shape[1]
+    _C.check(_C.lib.rcg_rk45_advance_disturbed(
+        C.byref(sysd), C.byref(distd), C.byref(sol), C.byref(obj), E, _ptr(y_full, _F64, (nf, E), "y_full"),
+        _ptr(f_full, _F64, (nf, E), "f_full"), _ptr(t, _F64, (E,), "t"), _ptr(h_abs, _F64, (E,), "h_abs"),
+        _ptr(status, _I32, (E,), "status"), _ptr(nfev, _I32, (E,), "nfev"), _ptr(nsteps, _I32, (E,), "nsteps", optional=True),
+        _ptr(action, _F64, (m, E), "action"), _ptr(ctrl_clock, _F64, (E,), "ctrl_clock"), float(sampling_time), int(max_steps),
+        _ptr(state_sys, _F64, (n, E), "state_sys", optional=True), _ptr(accum, _F64, (E,), "accum", optional=True),
+        _ptr(sample_flag, _I32, (E,), "sample_flag", optional=True), _ptr(nsamples, _I32, (E,), "nsamples", optional=True),
+        _stream()), "rcg_rk45_advance_disturbed")
 
 
 class TrajectoryLog:
@@ -315,10 +371,11 @@ def critic_cost(obj, n, m, obs_buf, act_buf, w, w_prev, out=None):
     L, _, E = obs_buf.shape
     dimc = _C.lib.rcg_dim_critic(obj.critic_struct, n, m)
     W = w.shape[2]
-    out = torch.empty((E, W), dtype=_F64, device=obs_buf.device) if out is None else out
-    _C.check(_C.lib.rcg_critic_cost(C.byref(obj), n, m, E, W, _ptr(obs_buf, _F64, (L, n, E), "obs_buf"),
-                                    _ptr(act_buf, _F64, (L, m, E), "act_buf"), _ptr(w, _F64, (dimc, E, W), "w"),
-                                    _ptr(w_prev, _F64, (dimc, E), "w_prev"), _ptr(out, _F64, (E, W), "out"), _stream()),
+    dt = obs_buf.dtype                                     # fp64, or fp32 (rcg_critic_cost_f32: the tolerance report)
+    out = torch.empty((E, W), dtype=dt, device=obs_buf.device) if out is None else out
+    fn = getattr(_C.lib, "rcg_critic_cost" + _suffix(dt))
+    _C.check(fn(C.byref(obj), n, m, E, W, _ptr(obs_buf, dt, (L, n, E), "obs_buf"), _ptr(act_buf, dt, (L, m, E), "act_buf"),
+                _ptr(w, dt, (dimc, E, W), "w"), _ptr(w_prev, dt, (dimc, E), "w_prev"), _ptr(out, dt, (E, W), "out"), _stream()),
              "rcg_critic_cost")
     return out
 

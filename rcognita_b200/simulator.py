@@ -51,8 +51,8 @@ class Simulator:
             # simulator.py:170-185: discr_fnc / discr_prob are outside the hot path; anything else is invalid
             raise ValueError("Invalid system description" if sys_type not in ("discr_fnc", "discr_prob")
                              else f"sys_type {sys_type!r} is outside the B200 hot path (only 'diff_eqn')")
-        if is_disturb or is_dyn_ctrl:
-            raise NotImplementedError("is_disturb / is_dyn_ctrl are outside the B200 hot path")
+        if is_dyn_ctrl:
+            raise NotImplementedError("is_dyn_ctrl is outside the B200 hot path")
         owner = getattr(closed_loop_rhs, "__self__", None)
         if not isinstance(owner, System) or closed_loop_rhs.__func__ is not System.closed_loop_rhs:
             raise TypeError("closed_loop_rhs must be the bound `closed_loop_rhs` of a rcognita_b200 System "
@@ -63,12 +63,19 @@ class Simulator:
             raise ValueError("`first_step` must be positive.")                   # scipy common.py:10-16
         if first_step > abs(t1 - t0):
             raise ValueError("`first_step` exceeds bounds.")
+        if bool(is_disturb) != bool(owner.is_disturb):
+            raise ValueError("Simulator(is_disturb=...) must agree with the System's is_disturb")
+        self.is_disturb = int(bool(is_disturb))
         self._numpy_io = not isinstance(state_init, torch.Tensor)
-        n = owner.dim_state
-        y0, self._batched = to_soa(state_init, n, owner.device, "state_init")
+        ns = owner.dim_state
+        y0, self._batched = to_soa(state_init, ns, owner.device, "state_init")
+        if self.is_disturb:                                  # simulator.py:100-101: state_full_init = [state_init, disturb_init]
+            q0, _ = to_soa(disturb_init, owner.dim_disturb, owner.device, "disturb_init")
+            y0 = torch.cat([y0, q0.expand(owner.dim_disturb, y0.shape[1])], dim=0).contiguous()
+        n = y0.shape[0]                                       # rows the solver integrates
         self._y0 = y0.clone()
         self.E = E = y0.shape[1]
-        self.dim_state = n
+        self.dim_state = ns
         self.t0, self.t1, self.first_step = float(t0), float(t1), float(first_step)
         # simulator.py:150: max_step = dt/2 -- the constructor's own max_step argument is ignored there too
         self._sol = _C.make_solver(t1, dt / 2, rtol, atol)
@@ -79,7 +86,7 @@ class Simulator:
         self._h = torch.empty((E,), dtype=_F64, device=dev)
         self._status = torch.empty((E,), dtype=torch.int32, device=dev)
         self._nfev = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.state_full_init = state_init
+        self.state_full_init = state_init if not self.is_disturb else from_soa(self._y0, self._batched, self._numpy_io)
         self.ODE_solver = _SolverView(self)
         self._construct_solver()
 
@@ -98,8 +105,12 @@ class Simulator:
             if a_old.shape[1] == 1:
                 sysobj._action_soa.copy_(a_old.expand(sysobj.dim_input, self.E))
         sysobj._batched, sysobj._numpy_io = self._batched, self._numpy_io
-        ops.rhs(sysobj._sysd, self._y, sysobj._action_soa, out=self._f)
-        sysobj._state_soa = self._y
+        if self.is_disturb:                                   # RHS call number 0 of every environment's draw stream
+            ops.rhs_disturbed(sysobj._sysd, sysobj._distd, self._y, sysobj._action_soa, call=None, out=self._f)
+            sysobj._state_soa = self._y[: self.dim_state]
+        else:
+            ops.rhs(sysobj._sysd, self._y, sysobj._action_soa, out=self._f)
+            sysobj._state_soa = self._y
 
     # ---- reference interface ------------------------------------------------------------------
     def sim_step(self):
@@ -107,6 +118,11 @@ class Simulator:
         Raises like scipy (base.py:189-191) when no environment is running any more."""
         if self.E == 1 and int(self._status[0].item()) != _C.RUNNING:
             raise RuntimeError("Attempt to step on a failed or finished solver.")
+        if self.is_disturb:
+            ops.rk45_step_disturbed(self.sys._sysd, self.sys._distd, self._sol, self._y, self._f, self._t, self._h, self._status,
+                                    self.sys._action_soa, self._nfev)
+            self.sys._state_soa = self._y[: self.dim_state]
+            return
         ops.rk45_step(self.sys._sysd, self._sol, self._y, self._f, self._t, self._h, self._status,
                       self.sys._action_soa, nfev=self._nfev)
         self.sys._state_soa = self._y                                           # systems.py:251
@@ -119,7 +135,12 @@ class Simulator:
     def state_full(self):
         return from_soa(self._y, self._batched, self._numpy_io)
 
-    state = state_full
+    @property
+    def state(self):
+        """simulator.py:167: ``state_full[0:dim_state]``."""
+        if not self.is_disturb:
+            return self.state_full
+        return from_soa(self._y[: self.dim_state], self._batched, self._numpy_io)
 
     @property
     def observation(self):
@@ -127,8 +148,8 @@ class Simulator:
 
     def get_sim_step_data(self):
         """simulator.py:187-195 -> (t, state, observation, state_full)."""
-        state = self.state_full
-        return self.t, state, self.sys_out(state), state
+        state = self.state
+        return self.t, state, self.sys_out(state), (state if not self.is_disturb else self.state_full)
 
     def reset(self, literal=False, mask=None):
         """Documented intent of ``Simulator.reset`` (multi-episode runs): restore state_full_init, t0,
@@ -152,6 +173,8 @@ class Simulator:
         self._status.masked_fill_(sel, _C.RUNNING)
         if literal:
             return
+        if self.is_disturb:
+            raise NotImplementedError("masked non-literal reset of a disturbed system")
         self._y.copy_(torch.where(sel[None, :], self._y0, self._y))
         self._h.masked_fill_(sel, self.first_step)
         self._nfev.masked_fill_(sel, 1)

@@ -314,6 +314,43 @@ def gen_closed_loop_refit():
         json.dump(out, fh)
 
 
+
+# --------------------------------------------------------------------------- disturbance lanes (is_disturb = 1), function level
+def gen_disturb():
+    """`_state_dyn(t, state, action, disturb)` with a disturbance and `_disturb_dyn(t, disturb)` of the UNMODIFIED reference
+    (systems.py:316-318, :373-376, :341-343, :390-392, :421-424).  Two workarounds, neither touches the arithmetic:
+    `disturb` is passed as a Python LIST (under numpy 2 `ndarray != []` raises, which is also why the reference's own
+    closed loop cannot run with is_disturb = 1 and no loop-level golden exists), and `systems.randn` is replaced by a
+    function that replays recorded draws (the reference takes them from numpy's global stream)."""
+    out = {}
+    rng = np.random.default_rng(2024)
+    for name, cfg in SYSTEMS.items():
+        n, m = cfg["n"], cfg["m"]
+        nd = 2 if m == 2 else 1
+        dt = cfg["dt"]
+        pars_disturb = np.array([[200 * dt, 150 * dt], [0.0, 0.1], [0.3, 0.45]])[:, :nd] if nd == 2 else np.array([[0.2], [0.0], [0.3]])
+        cls = getattr(systems, cfg["cls"])
+        my_sys = cls(sys_type="diff_eqn", dim_state=n, dim_input=m, dim_output=n, dim_disturb=nd, pars=list(cfg["pars"]),
+                     ctrl_bnds=np.array(cfg["bnds"], dtype=float), is_dyn_ctrl=0, is_disturb=1, pars_disturb=pars_disturb)
+        assert my_sys._dim_full_state == n + nd
+        bn = np.array(cfg["bnds"], dtype=float)
+        cases = []
+        for _ in range(24):
+            state = rng.uniform(-3, 3, size=n)
+            action = rng.uniform(bn[:, 0], bn[:, 1])
+            disturb = rng.normal(size=nd) * 2.0
+            z = rng.normal(size=nd)
+            d_state = my_sys._state_dyn([], state, action, disturb=list(disturb))
+            it = iter(z)
+            systems.randn = lambda: float(next(it))
+            d_dist = my_sys._disturb_dyn([], list(disturb))
+            cases.append(dict(state=L(state), action=L(action), disturb=L(disturb), z=L(z), d_state=L(d_state), d_disturb=L(d_dist)))
+        out[name] = dict(pars=list(cfg["pars"]), bnds=cfg["bnds"], pars_disturb=L(pars_disturb), dim_disturb=nd,
+                         dim_full_state=int(my_sys._dim_full_state), cases=cases)
+        print("disturb", name, len(cases), "cases; d_disturb[0]", cases[0]["d_disturb"])
+    with open(os.path.join(HERE, "disturb.json"), "w") as fh:
+        json.dump(out, fh)
+
 # --------------------------------------------------------------------------- critic fit (reference SLSQP as the bar)
 def gen_critic_fit():
     """Reference `_critic_optimizer` (SLSQP, controllers.py:1248-1271) on seeded buffers: the fitted cost is
@@ -487,8 +524,8 @@ def gen_config1():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "closed_loop_refit", "config1", "critic_fit", "actor_opt",
-                             "nominal"]
+    which = sys.argv[1:] or ["functions", "integrator", "closed_loop", "closed_loop_refit", "disturb", "config1", "critic_fit",
+                             "actor_opt", "nominal"]
     if "functions" in which:
         gen_functions()
     if "integrator" in which:
@@ -497,6 +534,8 @@ if __name__ == "__main__":
         gen_closed_loop()
     if "closed_loop_refit" in which:
         gen_closed_loop_refit()
+    if "disturb" in which:
+        gen_disturb()
     if "config1" in which:
         gen_config1()
     if "critic_fit" in which:

@@ -706,6 +706,32 @@ def test_empty_batch_is_a_no_op(rb):
     ops.nominal_ni(sysd, y, 0.5, a)
 
 
+@pytest.mark.parametrize("name,cs", [("2tank", "quad-nomix"), ("3wrobot", "quadratic"), ("3wrobotNI", "quad-lin")])
+def test_critic_cost_f32_twin(rb, name, cs):
+    """rcg_critic_cost_f32 against the fp64 kernel on the same buffers: stated fp32 tolerance 2e-5 of the cost scale
+    (the sum of the squared TD terms' magnitudes: J_c is a difference of O(Q) terms, squared)."""
+    from rcognita_b200 import _C, ops
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E, W = 300, 3
+    rng = np.random.default_rng(9)
+    obj = _C.make_objective(n, m, mode="RQL", Nactor=4, gamma=0.95, Ncritic=4, buffer_size=10, critic_struct=cs,
+                            R1=p["R1_diag"], observation_target=p["target"])
+    dimc = _C.dim_critic(cs, n, m)
+    b = np.array(p["bnds"], dtype=float)
+    ob = torch.as_tensor(rng.normal(size=(10, n, E)), device="cuda")
+    ab = torch.as_tensor(rng.uniform(b[:, 0], b[:, 1], size=(E, 10, m)).transpose(1, 2, 0).copy(), device="cuda")
+    w = torch.as_tensor(rng.uniform(0, 2, size=(dimc, E, W)), device="cuda")
+    wp = torch.as_tensor(rng.uniform(0, 2, size=(dimc, E)), device="cuda")
+    J64 = ops.critic_cost(obj, n, m, ob, ab, w, wp)
+    J32 = ops.critic_cost(obj, n, m, ob.float(), ab.float(), w.float(), wp.float())
+    assert J32.dtype == torch.float32 and J32.shape == J64.shape
+    # scale of the terms that are differenced: |Q| of the largest row, squared
+    q = torch.stack([ops.critic(obj, n, m, ob[k].contiguous(), ab[k].contiguous(), wp, w_per_env=True).abs() for k in range(4)]).max(0).values
+    scale = torch.maximum(J64.abs(), (q * q)[:, None])
+    assert float(((J32.double() - J64).abs() / scale).max()) <= 2e-5
+
+
 @pytest.mark.parametrize("graph,actor", [(False, "candidates"), (True, "candidates"), (True, "opt")])
 def test_host_staged_loop_equals_resident_loop(rb, graph, actor):
     """engine.HostStagedLoop (the caller owns state and time in pinned host memory and reads back state, time, action,

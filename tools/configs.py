@@ -199,8 +199,9 @@ def pct(x):
 
 def run_fp32_report(a):
     """Config 4 in fp64 and fp32 on identical inputs: (i) one E x C actor-cost launch (J, arg-min agreement),
-    (ii) the closed loop with the critic weights pinned (trajectory / return divergence at t1).  _critic_cost
-    and the critic fit exist in fp64 only (the fit's Gram matrices need it), so J_c has no fp32 figure."""
+    (ii) the closed loop with the critic weights pinned (trajectory / return divergence at t1), (iii) `_critic_cost`
+    (J_c) in fp32 (rcg_critic_cost_f32) against fp64 on the FIFO buffers and weights the fp64 closed loop WITH critic
+    refit holds at several times of the episode.  The fit itself runs in fp64 only (its Gram matrices need it)."""
     c = CFG["config4"]
     n, m = _C.SYS_DIMS[_C.SYS_IDS[c["system"]]]
     E = (a.envs + 1023) // 1024 * 1024
@@ -226,13 +227,38 @@ def run_fp32_report(a):
     y64, y32 = e64.results(), e32.results()
     rel_y = np.abs(y32["y"].astype(np.float64) - y64["y"]) / np.maximum(np.abs(y64["y"]), 1e-2)
     rel_acc = np.abs(y32["accum"].astype(np.float64) - y64["accum"]) / np.abs(y64["accum"])
-    out = {"config": "config4-fp32-report", "E": E, "C": C, "t1": a.t1,
+    # (iii) J_c: fp64 closed loop with the critic refitted at every sample; at checkpoints evaluate _critic_cost at the
+    # current weights (and at w_critic_init = ones) in both precisions on the same buffers
+    eng = ClosedLoopEngine(c["system"], x0, cand, pars=c["pars"], ctrl_bnds=c["bnds"], mode=c["mode"], Nactor=c["N"], dt=c["dt"],
+                           pred_step_size=c["dt"] * c["psm"], t1=a.t1, R1=c["R1"], observation_target=c["target"],
+                           critic_struct=c["cs"], critic_fit=True, Ncritic=4, buffer_size=10, action_init=c["a_init"])
+    total = int(round(a.t1 / c["dt"]))
+    marks = sorted({max(8, total // 100), total // 10, total // 2, total - 2})
+    jc = {}
+    done = 0
+    for mk in marks:
+        for _ in range(mk - done):
+            eng.run_interval()
+        done = mk
+        for tag, wt in (("fitted_w", eng.w), ("w_init", torch.ones_like(eng.w))):
+            J64c = ops.critic_cost(obj, n, m, eng.obs_buf, eng.act_buf, wt[:, :, None].contiguous(), eng.w_prev)[:, 0]
+            J32c = ops.critic_cost(obj, n, m, eng.obs_buf.float(), eng.act_buf.float(), wt.float()[:, :, None].contiguous(),
+                                   eng.w_prev.float())[:, 0]
+            scale = J64c.abs().clamp_min(1e-300)
+            rel = ((J32c.double() - J64c).abs() / scale).cpu().numpy()
+            # fitted costs are often ~0 (the 3-row problem is feasible): absolute error against the cost at w_init as well
+            J0 = ops.critic_cost(obj, n, m, eng.obs_buf, eng.act_buf, torch.ones_like(eng.w)[:, :, None].contiguous(), eng.w_prev)[:, 0]
+            rel0 = ((J32c.double() - J64c).abs() / J0.abs().clamp_min(1e-300)).cpu().numpy()
+            jc[f"interval_{mk}_{tag}"] = {"rel_err": pct(rel[np.isfinite(rel)]), "err_over_Jc_at_w_init": pct(rel0[np.isfinite(rel0)]),
+                                          "Jc_fp64_median": float(J64c.median().item())}
+    del eng
+    out = {"config": "config4-fp32-report", "E": E, "C": C, "t1": a.t1, "critic_cost_fp32_vs_fp64": jc,
            "actor_cost_rel_err_fp32_vs_fp64": pct(relJ), "argmin_agreement": agree, "argmin_regret_rel": pct(regret),
            "closed_loop_state_rel_err_at_t1": pct(rel_y.reshape(-1)), "closed_loop_return_rel_err": pct(rel_acc),
            "same_step_counts": float((y32["nsteps"] == y64["nsteps"]).mean()),
            "fp64": {k: r64[k] for k in ("ms", "env_steps_per_s", "actor_evals_per_s")},
            "fp32": {k: r32[k] for k in ("ms", "env_steps_per_s", "actor_evals_per_s")},
-           "critic_cost_fp32": None, "note": "_critic_cost / critic fit are fp64-only"}
+           "note": "the critic FIT runs in fp64 only; _critic_cost has an fp32 twin (rcg_critic_cost_f32)"}
     print(json.dumps(out), flush=True)
 
 
@@ -256,10 +282,10 @@ def main():
         a.envs, a.t1 = a.envs or 1 << 20, a.t1 or 0.3
         run_config("config3", a)
     elif a.what == "config4":
-        a.envs, a.t1 = a.envs or 262144, a.t1 or 10.0
+        a.envs, a.t1 = a.envs or 262144, a.t1 or 100.0            # t1 = 100
         run_config("config4", a)
     else:
-        a.envs, a.t1 = a.envs or 262144, a.t1 or 10.0
+        a.envs, a.t1 = a.envs or 262144, a.t1 or 100.0
         run_fp32_report(a)
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Experiment (round 2): hiding the latency-bound `rcg_rk45_advance` launch behind the HBM-bound `rcg_actor_cost`
 launch of BASELINE config 2 with `engine.PipelinedLoop` (P environment blocks on P streams).  Prints ms per control
-interval for every (P, stagger) variant under the current RCG_ACTOR_CTAS_PER_SM setting and checks the final state
+interval for every (P, stagger) variant and checks the final state
 against the single-stream engine bit for bit.
 
     python tools/exp_overlap.py [--envs 65536] [--steps 240] [--variants 1,2,2n,3,4]
@@ -38,14 +38,11 @@ def main():
     torch.cuda.set_device(0)
     x0, cand = make_workload(args, 0, args.envs)
     W = 5
-    saved = os.environ.pop("RCG_ACTOR_CTAS_PER_SM", None)
     eng = ClosedLoopEngine("3wrobotNI", x0, cand, Nactor=args.nactor, **KW)
     for _ in range(W + args.steps):
         eng.run_interval()
     ref = eng.results()
     del eng
-    if saved is not None:
-        os.environ["RCG_ACTOR_CTAS_PER_SM"] = saved
     for name in args.variants.split(","):
         stagger = not name.endswith("n")
         P = int(name.rstrip("n"))
@@ -64,7 +61,6 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         res = loop.results()
         print(json.dumps({"P": P, "stagger": stagger, "ms_per_interval": ms, "evals_per_s": args.envs * args.cands / (ms * 1e-3),
-                          "grid": os.environ.get("RCG_ACTOR_CTAS_PER_SM", "default"),
                           "bit_identical": all(np.array_equal(res[k], ref[k], equal_nan=True) for k in ref)}), flush=True)
         del loop
 
