@@ -22,17 +22,29 @@ BOX = {"3wrobotNI": ([-10, -10, -np.pi], [10, 10, np.pi]), "3wrobot": ([-10, -10
        "2tank": ([-2, -2], [2, 2])}
 
 
+WORLD, RANK = 1, 0          # set by main() under torchrun (config-5 sweep at 2/4/8 GPUs: the environments are sharded)
+
+
 def time_it(fn, iters, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    ms = e0.elapsed_time(e1) / iters
+    if WORLD > 1:                                   # device time, max over ranks
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def actor_point(system, mode, cs, N, E, C, per_env, dtype=torch.float64, iters=10):
@@ -176,9 +188,30 @@ def actor_opt_point(system, mode, cs, N, E, state_scale=1.0, max_iter=300, iters
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "rk45", "rk45ni", "critic", "opt", "all"])
+    ap.add_argument("--what", default="headline", choices=["headline", "sweep", "sweep_multi", "rk45", "rk45ni", "critic", "opt", "all"])
     a = ap.parse_args()
+    global WORLD, RANK
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        WORLD, RANK = dist.get_world_size(), dist.get_rank()
     pts = []
+    if a.what == "sweep_multi":
+        # BASELINE config 5 at 1/2/4/8 GPUs: E TOTAL environments sharded over the ranks (strong scaling of one launch;
+        # no communication), a subset of the single-GPU sweep
+        for N in (5, 10, 20, 50):
+            for C in (64, 256):
+                for E in (65536, 1048576, 4194304):
+                    El = E // WORLD
+                    per_env = El * C * N * 2 * 8 <= 4e9
+
+                    def point(N=N, C=C, E=E, El=El, pe=per_env):
+                        r = actor_point("3wrobotNI", "MPC", "quad-nomix", N, El, C, pe, iters=4)
+                        r.update(E=E, E_per_gpu=El, n_gpus=WORLD, evals_per_s=E * C / r["ms"] * 1e3,
+                                 alg_GBps=r["alg_GBps"] * WORLD, scaling="strong")
+                        return r
+                    pts.append(point)
     if a.what in ("headline", "all"):
         pts += [lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 256, True),
                 lambda: actor_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 256, False),
@@ -189,9 +222,9 @@ def main():
     if a.what in ("sweep", "all"):
         for N in (5, 10, 20, 50):
             for C in (16, 64, 256, 1024):
-                for E in (4096, 65536, 1048576):
+                for E in (4096, 65536, 1048576, 4194304):
                     per_env = E * C * N * 2 * 8 <= 4e9
-                    if E * C > 3e8:
+                    if E * C > 4.4e9:
                         continue
                     pts.append(lambda N=N, C=C, E=E, pe=per_env: actor_point("3wrobotNI", "MPC", "quad-nomix", N, E, C, pe, iters=5))
     if a.what in ("rk45", "all"):
@@ -212,7 +245,12 @@ def main():
                 lambda: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 0.05, max_iter=100),
                 lambda: actor_opt_point("2tank", "SQL", "quad-nomix", 8, 262144, 0.5)]
     for p in pts:
-        print(json.dumps(p()), flush=True)
+        r = p()
+        if RANK == 0:
+            print(json.dumps(r), flush=True)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
