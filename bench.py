@@ -371,14 +371,17 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return int(t.item())
 
-    # ---- device-resident closed loop: warm-up, then exactly K timed steps
+    # ---- device-resident closed loop: warm-up, then exactly K timed steps.  The clock sampler is started BEFORE the
+    # warm-up so that nothing but the barrier sits between the last warm-up step and the first timed one (a 0.3 s pause
+    # there lets the GPU fall back to its idle clocks, which a 6 ms timed region then spends ramping up).
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0.0)
+    barrier()
     for _ in range(W):
         loop.step()
     loop.synchronize()
     barrier()
     steps0, samples0 = int(loop.field("nsteps").sum().item()), int(loop.field("nsamples").sum().item())
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    time.sleep(0.3 if rank == 0 else 0.0)
     barrier()
     rcognita_b200.reset_launch_count()
     loop.actor_events = []

@@ -140,6 +140,8 @@ def lib():
         L.orc_env_interval.restype = C.c_longlong
         L.orc_critic_fit.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp, C.c_int, ip]
         L.orc_critic_fit.restype = C.c_double
+        L.orc_critic_fit_ls.argtypes = [C.POINTER(CtrlT), C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp, C.c_int, C.c_int, ip]
+        L.orc_critic_fit_ls.restype = C.c_double
         L.orc_closed_loop_critic.argtypes = ([C.POINTER(CtrlT), C.POINTER(SysT), C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int]
                                              + [C.c_double] * 10 + [C.c_int, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp,
                                                                     dp, dp, dp, C.c_int, ip])
@@ -418,7 +420,7 @@ def closed_loop(c, s, state_init, cand, action_init, sampling_time, t0, t1, max_
             "traj": traj[: rows.value], "total_steps": int(total), "total_evals": int(evals.value)}
 
 
-def critic_fit(c, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w_init=None, max_evals=0):
+def critic_fit(c, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w_init=None, max_evals=0, ls_mode=None):
     """Bounded least-squares stand-in for ``_critic_optimizer`` (rcg_oracle_critic.c: the algorithm of the product's
     ``rcg_critic_fit`` restated in scalar C).  Buffers ``[buffer_size, n]`` / ``[buffer_size, m]`` (row 0 = oldest).
     Returns (w, J_c(w), dual passes)."""
@@ -430,8 +432,12 @@ def critic_fit(c, n, m, obs_buf, act_buf, w_prev, w_min, w_max, w_init=None, max
     wi, wip = _d(wi)
     w = np.zeros(D)
     ev = C.c_int(0)
-    J = lib().orc_critic_fit(C.byref(c), n, m, obp, abp, wvp, float(w_min), float(w_max), wip,
-                             w.ctypes.data_as(C.POINTER(C.c_double)), int(max_evals), C.byref(ev))
+    if ls_mode is None:      # like rcg_critic_fit: exact line search on the two-phase path (K <= 3, >= 10 weights, to convergence)
+        J = lib().orc_critic_fit(C.byref(c), n, m, obp, abp, wvp, float(w_min), float(w_max), wip,
+                                 w.ctypes.data_as(C.POINTER(C.c_double)), int(max_evals), C.byref(ev))
+    else:
+        J = lib().orc_critic_fit_ls(C.byref(c), n, m, obp, abp, wvp, float(w_min), float(w_max), wip,
+                                    w.ctypes.data_as(C.POINTER(C.c_double)), int(max_evals), int(ls_mode), C.byref(ev))
     return w, J, ev.value
 
 

@@ -149,6 +149,9 @@ typedef struct {
 double orc_critic_fit(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
                       const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
                       int max_evals, int *evals_out);
+double orc_critic_fit_ls(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
+                         const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
+                         int max_evals, int ls_mode, int *evals_out);
 void   orc_critic_state_init(orc_critic_state_t *k, int dimc, double t0);
 int    orc_env_iterate_critic(orc_env_t *v, orc_critic_state_t *k, const orc_ctrl_t *c, const orc_sys_t *s, int C,
                               const double *tab, int buffer_size, double w_lo, double w_hi, double sampling_time,

@@ -104,9 +104,68 @@ static int clip_state(double z, double lo, double hi)
  * [buffer_size, m] row-major (row 0 = oldest); w_init NULL = start from w_out's content.  Constants are the
  * product's: mu_rel = 1e-3 shrinking 100x per stage, 5 stages, 20 Newton steps, 40 halvings.  max_evals <= 0: to
  * convergence.  Returns _critic_cost at the fitted weights; *evals_out (may be NULL) = dual passes spent. */
+/* g(a) = d . grad D(lam + a d) along the Newton direction: c0 + c1 a + sum_j s_j clip(z_j + a s_j) -- piecewise linear and
+ * increasing in a. */
+static double ls_g(const fit_ctx_t *f, const double *z, const double *s, double c0, double c1, double a)
+{
+    double acc = 0;
+    for (int j = 0; j < f->D; ++j) acc = fma(s[j], clipw(f, fma(a, s[j], z[j])), acc);
+    return fma(c1, a, c0) + acc;
+}
+
+/* Exact minimiser of the dual along d (the product's warp-per-environment kernel does the same, critic_fit.cu): every weight
+ * contributes up to two breakpoints a > 0 where z_j + a s_j crosses lo or hi; g is evaluated at every breakpoint, the
+ * bracket [a_L, a_R] = (largest breakpoint with g < 0, smallest with g >= 0) is the linear piece that holds the root.
+ * Returns the step, or a negative number if there is none. */
+static double ls_exact(const fit_ctx_t *f, const double *lam, const double *dl, double slope)
+{
+    double z[ORC_MAX_W], s[ORC_MAX_W];
+    double c0 = 0, c1 = 0;
+    for (int r = 0; r < f->K; ++r) { c0 = fma(f->mu * lam[r] - f->b[r], dl[r], c0); c1 = fma(f->mu * dl[r], dl[r], c1); }
+    for (int j = 0; j < f->D; ++j) {
+        z[j] = zj(f, lam, j);
+        double sj = 0;
+        for (int r = 0; r < f->K; ++r) sj = fma(f->Phi[r * f->D + j], dl[r], sj);
+        s[j] = sj;
+    }
+    double aL = 0.0, gL = slope, aR = INFINITY, gR = 0.0;
+    for (int j = 0; j < f->D; ++j) {
+        if (s[j] == 0.0) continue;
+        for (int side = 0; side < 2; ++side) {
+            const double a = ((side ? f->hi : f->lo) - z[j]) / s[j];
+            if (!(a > 0.0) || !isfinite(a)) continue;
+            const double g = ls_g(f, z, s, c0, c1, a);
+            if (g < 0.0) { if (a > aL) { aL = a; gL = g; } }
+            else if (a < aR) { aR = a; gR = g; }
+        }
+    }
+    if (aR < INFINITY) {
+        if (!(aR > aL)) return aR;
+        return (gR > gL) ? aL + (aR - aL) * (-gL) / (gR - gL) : aR;
+    }
+    /* beyond the last breakpoint g is linear with the slope of its last piece */
+    const double g1 = ls_g(f, z, s, c0, c1, aL + 1.0);
+    const double sl = g1 - gL;
+    return (sl > 0.0) ? aL - gL / sl : -1.0;
+}
+
+/* ls_mode 0: Armijo backtracking (one-lane kernels, any K); 1: unit step if it passes the Armijo test, else the exact
+ * minimiser along the Newton direction (the two-phase path of rcg_critic_fit: K <= 3 and >= 10 weights). */
+double orc_critic_fit_ls(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
+                         const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
+                         int max_evals, int ls_mode, int *evals_out);
+
 double orc_critic_fit(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
                       const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
                       int max_evals, int *evals_out)
+{
+    const int exact = max_evals <= 0 && c->Ncritic - 1 <= 3 && orc_dim_critic(c->critic_struct, n, m) >= 10;
+    return orc_critic_fit_ls(c, n, m, obs_buf, act_buf, w_prev, lo, hi, w_init, w_out, max_evals, exact, evals_out);
+}
+
+double orc_critic_fit_ls(const orc_ctrl_t *c, int n, int m, const double *obs_buf, const double *act_buf,
+                         const double *w_prev, double lo, double hi, const double *w_init, double *w_out,
+                         int max_evals, int ls_mode, int *evals_out)
 {
     const int K = c->Ncritic - 1, D = orc_dim_critic(c->critic_struct, n, m);
     const int max_outer = 5, max_newton = 20, max_ls = 40;
@@ -191,6 +250,15 @@ double orc_critic_fit(const orc_ctrl_t *c, int n, int m, const double *obs_buf, 
                     ++evals;
                     for (int r = 0; r < K; ++r) lt[r] = fma(a, dl[r], lam[r]);
                     if (dual(&f, lt) <= D0 + 1e-4 * a * slope + 1e-14 * fabs(D0)) { ok = 1; break; }
+                    if (ls_mode == 1) {                      /* the unit step failed: exact minimiser along dl */
+                        evals += 3;
+                        a = ls_exact(&f, lam, dl, slope);
+                        if (a > 0.0 && isfinite(a)) {
+                            for (int r = 0; r < K; ++r) lt[r] = fma(a, dl[r], lam[r]);
+                            ok = 1;
+                        }
+                        break;
+                    }
                     a *= 0.5;
                 }
                 if (!ok) break;
