@@ -41,6 +41,11 @@ class ClosedLoopEngine:
     ``CtrlNominal3WRobotNI`` with ``ctrl_gain`` (Sys3WRobotNI only; ``action_init`` defaults to zeros like the
     reference's ``action_curr``, candidates unused).
 
+    ``pars_disturb = [sigma, mu, tau]`` switches the disturbance lanes on (``System(is_disturb=1)``, rcognita/systems.py:228-231,
+    :247-248, :325-345, :384-394): the solver integrates ``[state, disturb]`` from ``[state_init, disturb_init]``, the normal
+    draws of ``_disturb_dyn`` come from the counter-based stream of environment ``env_offset + e`` under key ``seed``; the
+    controller still sees (and predicts with) the undisturbed state rows only, like the reference's ``sys_rhs([], state, action)``.
+
     ``log_every`` > 0 keeps a device-side trajectory ring for EVERY environment: one row
     (t, state, stage_obj, accum_obj, action -- the rows of rcognita/loggers.py) per ``log_every``-th solver step,
     the last ``log_capacity`` rows per environment (``trajectory(e)``, ``shard.gather_trajectories``).
@@ -52,7 +57,7 @@ class ClosedLoopEngine:
                  w_critic=None, action_init=(), device=None, dtype=torch.float64, critic_fit=False, Ncritic=4,
                  buffer_size=10, critic_period=None, critic_fit_evals=0, actor="candidates", opt_start="argmin",
                  opt_iters=300, opt_pg_tol=1e-7, opt_f_tol=1e-12, opt_presweeps=0, ctrl_gain=0.5, log_every=0,
-                 log_capacity=0):
+                 log_capacity=0, pars_disturb=None, disturb_init=(), seed=0, env_offset=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ClosedLoopEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -68,6 +73,14 @@ class ClosedLoopEngine:
         if first_step > abs(t1 - t0):
             raise ValueError("`first_step` exceeds bounds.")
         self.sol = _C.make_solver(t1, dt / 2, rtol, atol)
+        self.distd = None
+        self.nf = n                                                    # rows the solver integrates
+        if pars_disturb is not None:
+            if dtype != torch.float64 or log_every > 0:
+                raise ValueError("disturbance lanes run in fp64 and without the trajectory ring")
+            self.nd = _C.DIST_DIM[self.sysd.sys_id]
+            self.nf = n + self.nd
+            self.distd = _C.make_disturb(pars_disturb, seed=seed, env_offset=env_offset)
         self.obj = _C.make_objective(n, m, mode=mode, Nactor=Nactor,
                                      pred_step_size=dt if pred_step_size is None else pred_step_size, gamma=gamma,
                                      Ncritic=Ncritic, buffer_size=buffer_size, critic_struct=critic_struct, stage_obj_struct=stage_obj_struct, R1=R1, R2=R2,
@@ -80,6 +93,12 @@ class ClosedLoopEngine:
                 raise ValueError(f"state_init must be [E, {n}]")
             self.E = E = x0.shape[0]
             self.y0 = x0.t().contiguous()                                  # [n, E]
+            if self.distd is not None:                                     # state_full_init = [state_init, disturb_init]
+                q0 = _as_dev(np.zeros(self.nd) if len(disturb_init) == 0 else disturb_init, dtype, self.device)
+                q0 = q0[None, :] if q0.dim() == 1 else q0
+                if q0.shape[1] != self.nd or q0.shape[0] not in (1, E):
+                    raise ValueError(f"disturb_init must be [{self.nd}] or [E, {self.nd}]")
+                self.y0 = torch.cat([self.y0, q0.t().expand(self.nd, E)], dim=0).contiguous()
             L = Nactor * m
             if actor not in ("candidates", "opt", "nominal") or opt_start not in ("argmin", "init"):
                 raise ValueError("actor must be 'candidates', 'opt' or 'nominal'; opt_start 'argmin' or 'init'")
@@ -154,12 +173,13 @@ class ClosedLoopEngine:
         # addition (action, accumulated objective, status, arg-min), and the solver / controller internals that never
         # leave the device (FSAL derivative, step size, state_sys, clocks, counters).  A host-staged step is ONE copy in
         # (segment 1) and ONE copy out (segments 1 + 2).
-        spec = [("y", (n, E), dt), ("t", (E,), torch.float64),
+        nf = self.nf
+        spec = [("y_full", (nf, E), dt), ("t", (E,), torch.float64),
                 # read back by the host in addition
                 ("action", (m, E), dt), ("accum", (E,), dt), ("status", (E,), torch.int32),
                 ("sample_flag", (E,), torch.int32), ("argmin", (E,), torch.int32),
                 # device-resident internals
-                ("f", (n, E), dt), ("state_sys", (n, E), dt), ("h_abs", (E,), torch.float64),
+                ("f", (nf, E), dt), ("state_sys", (n, E), dt), ("h_abs", (E,), torch.float64),
                 ("ctrl_clock", (E,), torch.float64), ("nfev", (E,), torch.int32), ("nsteps", (E,), torch.int32),
                 ("nsamples", (E,), torch.int32), ("Jmin", (E,), dt)]
         off, layout = 0, []
@@ -176,6 +196,7 @@ class ClosedLoopEngine:
         self._blob = torch.empty((off,), dtype=torch.uint8, device=dev)
         for name, shape, dtype_, o, nbytes in layout:
             setattr(self, name, self._blob[o:o + nbytes].view(dtype_).view(shape))
+        self.y = self.y_full[:n]                           # the state rows (all of y_full without disturbance lanes)
         if self.critic_fit:
             dimc = self.w.shape[0]
             self.obs_buf = torch.empty((self.buffer_size, n, E), dtype=dt, device=dev)
@@ -200,8 +221,8 @@ class ClosedLoopEngine:
     def reset(self):
         """Documented intent of ``Simulator.reset`` + ``CtrlOptPred.reset``: restore y0, t0,
         f(t0, y0) with zero action, h_abs = first_step, clocks and accumulators."""
-        self.y.copy_(self.y0)
-        self.state_sys.copy_(self.y0)
+        self.y_full.copy_(self.y0)
+        self.state_sys.copy_(self.y0[:self.n])
         self.action.zero_()                                # System.action = zeros (systems.py:134)
         self.t.fill_(self.t0)
         self.h_abs.fill_(self.first_step)
@@ -225,7 +246,10 @@ class ClosedLoopEngine:
             self.nfits.zero_()
         if self.log is not None:
             self.log.reset()
-        ops.rhs(self.sysd, self.y, self.action, out=self.f)               # RK45.__init__: f = fun(t0, y0)
+        if self.distd is not None:                                        # RHS call number 0 of every draw stream
+            ops.rhs_disturbed(self.sysd, self.distd, self.y_full, self.action, call=None, out=self.f)
+        else:
+            ops.rhs(self.sysd, self.y, self.action, out=self.f)           # RK45.__init__: f = fun(t0, y0)
         self.intervals = 0
         self._first_done = False
         self.actor_events = None        # set to a list to record (start, end) CUDA events per actor launch
@@ -233,7 +257,11 @@ class ClosedLoopEngine:
     # -- the very first solver step runs with System.action = 0; only afterwards does the
     #    system receive the controller's initial action (main_3wrobot_NI.py:417-424).
     def _first_step(self):
-        ops.rk45_step(self.sysd, self.sol, self.y, self.f, self.t, self.h_abs, self.status, self.action, nfev=self.nfev)
+        if self.distd is not None:
+            ops.rk45_step_disturbed(self.sysd, self.distd, self.sol, self.y_full, self.f, self.t, self.h_abs, self.status,
+                                    self.action, self.nfev)
+        else:
+            ops.rk45_step(self.sysd, self.sol, self.y, self.f, self.t, self.h_abs, self.status, self.action, nfev=self.nfev)
         self.nsteps += 1
         # compute_action's clock test (controllers.py:1440-1442): sets sample_flag and moves ctrl_clock where it fires
         ops.ctrl_sample(self.t, self.ctrl_clock, self.sampling_time, mask_out=self.sample_flag)
@@ -323,6 +351,12 @@ class ClosedLoopEngine:
         (``rcg_rk45_advance``: sim_step / receive_sys_state / upd_accum_obj with the held action)."""
         if not self._first_done:
             self._first_step()
+        if self.distd is not None:
+            ops.rk45_advance_disturbed(self.sysd, self.distd, self.sol, self.obj, self.y_full, self.f, self.t, self.h_abs,
+                                       self.status, self.action, self.ctrl_clock, self.sampling_time, max_steps, self.nfev,
+                                       state_sys=self.state_sys, accum=self.accum, sample_flag=self.sample_flag,
+                                       nsteps=self.nsteps, nsamples=self.nsamples)
+            return
         ops.rk45_advance(self.sysd, self.sol, self.obj, self.y, self.f, self.t, self.h_abs, self.status, self.action,
                          self.ctrl_clock, self.sampling_time, max_steps, state_sys=self.state_sys, accum=self.accum,
                          sample_flag=self.sample_flag, nfev=self.nfev, nsteps=self.nsteps, nsamples=self.nsamples,
@@ -403,6 +437,7 @@ class ClosedLoopEngine:
             "status": self.status.cpu().numpy(), "nfev": self.nfev.cpu().numpy(),
             "nsteps": self.nsteps.cpu().numpy(), "nsamples": self.nsamples.cpu().numpy(),
             "argmin": self.argmin.cpu().numpy(), "Jmin": self.Jmin.cpu().numpy(),
+            **({"disturb": self.y_full[self.n:].t().contiguous().cpu().numpy()} if self.distd is not None else {}),
             **({"w_critic": self.w.t().contiguous().cpu().numpy(), "nfits": self.nfits.cpu().numpy(),
                 "Jc": self.Jc.cpu().numpy()} if self.critic_fit else {}),
         }
@@ -411,7 +446,7 @@ class ClosedLoopEngine:
     # -- host-buffer form of one control interval: the caller owns its environments in PINNED HOST memory between
     #    calls (like the reference's Python loop does): it hands in the state and time `get_sim_step_data` gave it and
     #    reads back state, time, action, accumulated objective, status and arg-min; solver internals stay on the device.
-    HOST_IN_FIELDS = ("y", "t")
+    HOST_IN_FIELDS = ("y", "t")                    # ("y" = the state rows of "y_full"; with disturbance lanes the host holds y_full)
     HOST_OUT_FIELDS = ("y", "t", "action", "accum", "status", "sample_flag", "argmin")
 
     def make_host_state(self):
@@ -425,6 +460,7 @@ class ClosedLoopEngine:
         for name, shape, dtype_, o, nbytes in self._layout:
             if o + nbytes <= self._io_bytes:
                 host[name] = blob[o:o + nbytes].view(dtype_).view(shape)
+        host["y"] = host["y_full"][:self.n]
         return host
 
     def run_interval_host(self, host, sync=True):

@@ -238,3 +238,60 @@ def test_disturbed_advance_is_sharding_invariant_and_equals_stepping(cuda):
     for w, s_ in zip(whole, stepped):
         assert np.array_equal(w[..., :256], s_)
     assert whole[5].min() >= 6                              # several steps per interval were taken
+
+
+@gpu
+def test_engine_with_disturbance_equals_class_loop_and_is_sharding_invariant(cuda):
+    """ClosedLoopEngine(pars_disturb=...) -- MPC over a candidate table on disturbed Sys3WRobotNI environments, fused
+    rk45_advance_disturbed + actor launches -- takes exactly the steps of the reference-style loop over the drop-in classes
+    (System(is_disturb=1) / Simulator(is_disturb=1) / CtrlOptPred), and a batch split in two with env_offset reproduces it."""
+    from rcognita_b200 import controllers, simulator, systems
+    from rcognita_b200.engine import ClosedLoopEngine
+    name, n, m, nd = "3wrobotNI", 3, 2, 2
+    bn = np.array([[-25, 25], [-5, 5]], dtype=float)
+    pd = np.array([[0.4, 0.3], [0.0, 0.1], [0.3, 0.45]])
+    rng = np.random.default_rng(8)
+    E, N, C_, t1, dt, seed = 96, 5, 48, 0.12, 0.01, 31
+    x0 = rng.uniform([-5, -5, -3], [5, 5, 3], size=(E, n))
+    q0 = np.array([0.2, -0.1])
+    cand = rng.uniform(np.tile(bn[:, 0], N), np.tile(bn[:, 1], N), size=(C_, N * m))
+    kw = dict(ctrl_bnds=bn, mode="MPC", Nactor=N, dt=dt, t1=t1, R1=[1, 10, 1, 0, 0], pars_disturb=pd, disturb_init=q0, seed=seed)
+    eng = ClosedLoopEngine(name, x0, cand, **kw)
+    eng.run()
+    got = eng.results()
+    assert got["disturb"].shape == (E, nd) and (got["status"] == 1).all()
+
+    parts = [ClosedLoopEngine(name, x0[a:b], cand, env_offset=a, **kw) for a, b in ((0, 32), (32, E))]
+    for p in parts:
+        p.run()
+    for k in ("y", "disturb", "t", "accum", "nsteps", "nsamples", "argmin", "nfev"):
+        assert np.array_equal(got[k], np.concatenate([p.results()[k] for p in parts], axis=0)), k
+
+    my_sys = systems.Sys3WRobotNI(sys_type="diff_eqn", dim_state=n, dim_input=m, dim_output=n, dim_disturb=nd, pars=[], ctrl_bnds=bn,
+                                  is_dyn_ctrl=0, is_disturb=1, pars_disturb=pd, seed=seed)
+    ctrl = controllers.CtrlOptPred(m, n, "MPC", ctrl_bnds=bn, action_init=[], t0=0, sampling_time=dt, Nactor=N, pred_step_size=dt,
+                                   sys_rhs=my_sys._state_dyn, sys_out=my_sys.out, state_sys=x0, gamma=1, stage_obj_struct="quadratic",
+                                   stage_obj_pars=[np.diag([1.0, 10, 1, 0, 0])], observation_target=[], candidates=cand)
+    sim = simulator.Simulator("diff_eqn", my_sys.closed_loop_rhs, my_sys.out, x0, disturb_init=q0, action_init=np.zeros(m), t0=0, t1=t1,
+                              dt=dt, max_step=dt / 2, first_step=1e-6, atol=1e-5, rtol=1e-3, is_disturb=1, is_dyn_ctrl=0)
+    nsteps = np.zeros(E, dtype=np.int64)
+    for _ in range(100000):
+        running = np.array([st == "running" for st in sim.ODE_solver.status])
+        if not running.any():
+            break
+        sim.sim_step()
+        nsteps += running
+        t, state, observation, state_full = sim.get_sim_step_data()
+        keep_a, keep_acc = ctrl._action_curr.clone(), ctrl._accum.clone()
+        action = controllers.ctrl_selector(t, observation, None, None, ctrl, "MPC")
+        my_sys.receive_action(action)
+        ctrl.receive_sys_state(my_sys._state)
+        ctrl.upd_accum_obj(observation, action)
+        if not running.all():                      # finished lanes are no longer driven (the reference loop breaks at t >= t1)
+            done = torch.as_tensor(~running, device=cuda)
+            ctrl._action_curr[:, done] = keep_a[:, done]
+            ctrl._accum[done] = keep_acc[done]
+    assert np.array_equal(nsteps, got["nsteps"])
+    assert np.array_equal(sim._t.cpu().numpy(), got["t"])
+    assert np.array_equal(sim._y.t().cpu().numpy(), np.concatenate([got["y"], got["disturb"]], axis=1))
+    assert np.max(np.abs(ctrl._accum.cpu().numpy() - got["accum"]) / np.abs(got["accum"])) <= 1e-12
