@@ -478,14 +478,15 @@ critic_fit3_warp_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, con
                         const double *__restrict__ winit_g, double *__restrict__ w_g, double mu_rel0, int max_outer,
                         int max_newton, int max_evals, int update_prev, double *__restrict__ Jc_out, int max_ls,
                         const int32_t *__restrict__ lane_list, const int32_t *__restrict__ lane_count,
-                        int32_t *__restrict__ queue)
+                        int32_t *__restrict__ queue, const int32_t *__restrict__ mask = nullptr)
 {
     constexpr int D = dim_critic_c(CS, N, M), P = N + M;
     constexpr int SLOTS = (D + 31) / 32;                    // weights per lane (1, or 2 for the 35-weight critic)
     using FI = FeatIdx<CS, N, M>;
     const int lane = threadIdx.x & 31;
     const int K = O.Ncritic - 1;
-    const int count = *lane_count;
+    // work items: the compacted list of a first phase, or (lane_list == NULL) every environment with mask != 0
+    const int count = lane_list ? *lane_count : (int)E;
     auto clipw = [&](double z) { return z < lo ? lo : (z > hi ? hi : z); };
 
     for (;;) {
@@ -493,7 +494,8 @@ critic_fit3_warp_kernel(const __grid_constant__ ObjDev<double> O, int64_t E, con
         if (lane == 0) item = atomicAdd(queue, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= count) return;
-        const int64_t e = lane_list[item];
+        const int64_t e = lane_list ? (int64_t)lane_list[item] : (int64_t)item;
+        if (!lane_list && mask && mask[e] == 0) continue;
 
         // rows u[r] = [chi(o[k-1], a[k-1]), 1] and right-hand sides b[r] (every lane keeps a copy: 3 x 8 doubles)
         double u[3][P + 1], b[3];
@@ -767,7 +769,10 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
     // warp that holds one of them waits for it (ncu: 3.3 of 32 lanes active on average).  Phase 1 gives every
     // environment kPhase1Budget evaluations; those that run out are queued (and write nothing), phase 2 restarts
     // exactly them, packed densely into warps.  Each environment's result is what the single-phase kernel computes.
-    constexpr int kPhase1Budget = 32;           // 4 ... 48 measured within 5 % of each other (config 3)
+    // (round 2, exact line search in the second phase: budgets 4 ... 32 and "no first phase at all" -- every masked
+    //  environment straight to the warp kernel -- measure within 5 % of each other: 12.95 ... 14.1 ms per 1 M in-loop fits)
+    constexpr int kPhase1Budget = 32;
+    constexpr bool warp_only = false;
     // Measured on B200 (profiles/r01_critic_fit_two_phase.txt): 23.0 -> 20.8 ms per 1 M fits of the 28-weight critic
     // inside config 3's loop -- the rest of the tail is the serial dependency chain of the environments that run
     // into the iteration caps, not idle lanes; for small critics the second launch costs more than it saves
@@ -797,13 +802,16 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
         }
     }
     const int nphases = todo ? 2 : 1;
+    const int first_phase = (todo && warp_only && fast) ? 1 : 0;
     const bool warp_phase2 = getenv("RCG_FIT_LANE_PHASE2") == nullptr;      // second phase: one warp per environment
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int phase = 0; phase < nphases; ++phase) {
+    for (int phase = first_phase; phase < nphases; ++phase) {
         const int evals = (todo && phase == 0) ? kPhase1Budget : (max_evals > 0 ? max_evals : 0x7fffffff);
-        const int32_t *lane_list = (todo && phase == 1) ? todo : nullptr, *lane_count = (todo && phase == 1) ? todo + E : nullptr;
+        const bool listed = todo && phase == 1 && first_phase == 0;
+        const int32_t *lane_list = listed ? todo : nullptr, *lane_count = listed ? todo + E : nullptr;
+        const bool warp_phase = todo && phase == 1;
         int32_t *todo_list = (todo && phase == 0) ? todo : nullptr, *todo_count = (todo && phase == 0) ? todo + E : nullptr;
 #define FIT3(NN, MM, CS, RD)                                                                                              \
     {                                                                                                                     \
@@ -817,9 +825,9 @@ extern "C" int rcg_critic_fit(const rcg_objective_t *obj, int32_t n, int32_t m, 
 #define FIT3W(NN, MM, CS, RD)                                                                                             \
     critic_fit3_warp_kernel<NN, MM, CS, RD><<<(unsigned)(sms * 8), 128, 0, s>>>(                                         \
         O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, mu_rel, outer, newton, evals, update_prev, Jc_out,      \
-        max_ls, lane_list, lane_count, todo + E + 1);
+        max_ls, lane_list, lane_count, todo + E + 1, mask);
 #define FIT(NN, MM, CS)                                                                                                   \
-    if (fast && lane_list && warp_phase2) { if (rd) FIT3W(NN, MM, CS, true) else FIT3W(NN, MM, CS, false) }               \
+    if (fast && warp_phase && warp_phase2) { if (rd) FIT3W(NN, MM, CS, true) else FIT3W(NN, MM, CS, false) }              \
     else if (fast) { if (rd) FIT3(NN, MM, CS, true) else FIT3(NN, MM, CS, false) }                                        \
     else if (rd) critic_fit_kernel<NN, MM, CS, true><<<grid, 128, 0, s>>>(O, E, obs_buf, act_buf, w_prev, w_min, w_max, w_init, w, \
                                                                      mask, mu_rel, outer, newton, evals, update_prev, Jc_out,      \
