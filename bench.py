@@ -395,6 +395,7 @@ def run_b200(args):
     barrier()
     t_wall1 = time.time()
     launches = rcognita_b200.launch_count()
+    actor_kernel_name = rcognita_b200.last_actor_kernel()       # what the library dispatched to, not a literal
     ms_total = ev0.elapsed_time(ev1)
     actor_ms = [a.elapsed_time(b) for a, b in loop.actor_events]
     # time during which at least one actor launch was running (the blocks' launches overlap each other and the other
@@ -542,7 +543,7 @@ def run_b200(args):
     evals_region = d_evals
     achieved = evals_region * bytes_per_eval / (actor_union_ms * 1e-3) / 1e9
     per_launch = evals_per_actor_launch * bytes_per_eval / (actor_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "actor_cost_tma_kernel" if not args.shared_cands else "actor_cost_kernel",
+    roofline = {"bound": "hbm", "kernel": actor_kernel_name, "kernel_source": "rcg_last_actor_kernel() after the timed region",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel: read + write)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_eval": bytes_per_eval,

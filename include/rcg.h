@@ -226,6 +226,10 @@ int rcg_actor_cost(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t 
                    const double *w_critic, int32_t w_per_env, const int32_t *mask,
                    double *J_out, int32_t *argmin_out, double *Jmin_out, double *action_out,
                    double *accum, double sampling_time, void *stream);
+/* Name of the kernel variant the calling thread's last rcg_actor_cost(_f32) dispatched to: "actor_cost_tma_kernel"
+ * (per-environment candidates staged by TMA, compile-time horizon), "actor_cost_tma_rt_kernel" (runtime horizon) or
+ * "actor_cost_kernel" (direct loads: shared tables, dense R, unaligned shapes).  For benchmarks and tests. */
+const char *rcg_last_actor_kernel(void);
 int rcg_actor_cost_f32(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t C,
                        const float *state_sys, const float *obs, const float *cand, int32_t cand_per_env,
                        const float *w_critic, int32_t w_per_env, const int32_t *mask,

@@ -26,6 +26,12 @@ def reset_launch_count() -> None:
     _C.lib.rcg_reset_launch_count()
 
 
+def last_actor_kernel() -> str:
+    """Kernel variant the last ``rcg_actor_cost`` call of this thread dispatched to (``rcg_last_actor_kernel``)."""
+    from . import _C
+    return (_C.lib.rcg_last_actor_kernel() or b"").decode()
+
+
 def last_error() -> str:
     from . import _C
     return _C.last_error()

@@ -7,6 +7,8 @@
 
 namespace rcg {
 
+static thread_local const char *g_last_actor_kernel = "";       // variant dispatched by the last rcg_actor_cost of this thread
+
 // 2-D tensor map of a per-environment candidate array [rows = Nactor*m][cols = E*C] (row-major, cols
 // contiguous), box = 32 columns x all rows.  cuTensorMapEncodeTiled is resolved through the runtime so
 // that the library does not link against libcuda directly.
@@ -130,6 +132,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
         }
     }
     L.stream = (cudaStream_t)stream;
+    g_last_actor_kernel = L.use_tma ? "actor_cost_tma_kernel" : L.use_tma_rt ? "actor_cost_tma_rt_kernel" : "actor_cost_kernel";
     int rc;
     switch (sys->sys_id) {
     case RCG_SYS_3WROBOT_NI: rc = launch_actor_ni(L); break;
@@ -143,6 +146,8 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
 }  // namespace rcg
 
 extern "C" {
+
+const char *rcg_last_actor_kernel(void) { return rcg::g_last_actor_kernel; }
 
 int rcg_actor_cost(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E, int32_t C, const double *state_sys,
                    const double *obs, const double *cand, int32_t cand_per_env, const double *w_critic,

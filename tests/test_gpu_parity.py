@@ -791,6 +791,23 @@ def test_host_staged_pipelined_run_equals_resident_loop(rb, graph):
     assert h2d == K * loop.h2d_bytes and d2h == K * loop.d2h_bytes
 
 
+def test_last_actor_kernel_names_the_dispatched_variant(rb):
+    """rcg_last_actor_kernel: per-environment candidates with a specialised horizon -> the TMA-staged kernel, a runtime
+    horizon -> its runtime twin, a shared table -> the direct kernel (what bench.py reports as roofline.kernel)."""
+    import rcognita_b200
+    from rcognita_b200 import _C, ops
+    name, n, m = "3wrobotNI", 3, 2
+    p = PRESET[name]
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    E, C_ = 64, 32
+    x = torch.as_tensor(random_states(name, E, 5).T.copy(), device="cuda")
+    for N, per_env, want in ((6, True, "actor_cost_tma_kernel"), (7, True, "actor_cost_tma_rt_kernel"), (6, False, "actor_cost_kernel")):
+        obj = _C.make_objective(n, m, mode="MPC", Nactor=N, pred_step_size=0.01, R1=p["R1_diag"])
+        cand = torch.as_tensor(random_cands(name, (E * C_,) if per_env else (C_,), N, 6).T.copy(), device="cuda")
+        ops.actor_cost(sysd, obj, x, x, cand, per_env, C_, want_J=False)
+        assert rcognita_b200.last_actor_kernel() == want
+
+
 @pytest.mark.parametrize("nchunks,stagger,per_env", [(2, True, True), (3, False, True), (4, True, False)])
 def test_pipelined_loop_equals_single_engine(rb, nchunks, stagger, per_env):
     """engine.PipelinedLoop (environment blocks on their own streams, rk45_advance of one block beside the actor launch
