@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     src = r'''
     #include <stdio.h>
     #include "rcg.h"
-    int main(void) { printf("%zu %zu %zu %zu\n", sizeof(rcg_system_t), sizeof(rcg_objective_t), sizeof(rcg_solver_t), sizeof(rcg_log_t)); return 0; }
+    int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(rcg_system_t), sizeof(rcg_objective_t), sizeof(rcg_solver_t), sizeof(rcg_log_t), sizeof(rcg_disturb_t)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -49,7 +49,7 @@ def test_struct_layouts_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_C.RcgSystem), ctypes.sizeof(_C.RcgObjective), ctypes.sizeof(_C.RcgSolver),
-                     ctypes.sizeof(_C.RcgLog)]
+                     ctypes.sizeof(_C.RcgLog), ctypes.sizeof(_C.RcgDisturb)]
 
 
 def test_dim_helpers_and_descriptors():
@@ -94,6 +94,21 @@ def test_no_device_is_a_loud_error():
     assert rc == -2 and "no CPU fallback" in _C.last_error()
     rc = _C.lib.rcg_state_dyn(ctypes.byref(sysd), 4, None, p, p, None)
     assert rc == -1 and "null" in _C.last_error()
+    # round-2 entry points: disturbance lanes, fp32 critic cost
+    distd = _C.make_disturb([[1, 1], [0, 0], [0.3, 0.3]], seed=3, env_offset=7)
+    assert distd.seed == 3 and distd.env_offset == 7 and distd.tau[1] == 0.3
+    rc = _C.lib.rcg_rhs_disturbed(ctypes.byref(sysd), ctypes.byref(distd), 4, p, p, None, None, p, 1, None)
+    assert rc == -2 and "no CPU fallback" in _C.last_error()
+    assert _C.lib.rcg_rhs_disturbed(ctypes.byref(sysd), None, 4, p, p, None, None, p, 1, None) == -1
+    assert _C.lib.rcg_disturb_normals(ctypes.byref(distd), 4, None, 0, p, None) == -2
+    sol = _C.make_solver(1.0, 0.005, 1e-3, 1e-5)
+    assert _C.lib.rcg_rk45_step_disturbed(ctypes.byref(sysd), None, ctypes.byref(sol), 4, p, p, p, p, p, p, p, None) == -1
+    assert "disturbance" in _C.last_error()
+    assert _C.lib.rcg_rk45_step_disturbed(ctypes.byref(sysd), ctypes.byref(distd), ctypes.byref(sol), 4, p, p, p, p, p, None, p, None) == -1
+    assert "nfev" in _C.last_error()                      # nfev numbers the random draws: required
+    obj = _C.make_objective(3, 2, mode="RQL", Nactor=3, R1=[1, 10, 1, 0, 0])
+    assert _C.lib.rcg_critic_cost_f32(ctypes.byref(obj), 3, 2, 4, 1, p, p, p, p, p, None) == -2
+    assert _C.lib.rcg_last_actor_kernel() in (b"", b"actor_cost_kernel", b"actor_cost_tma_kernel", b"actor_cost_tma_rt_kernel")
     from rcognita_b200.engine import ClosedLoopEngine
     with pytest.raises(RuntimeError, match="CUDA device"):
         ClosedLoopEngine("3wrobotNI", np.zeros((2, 3)), np.zeros((4, 12)))
