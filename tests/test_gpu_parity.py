@@ -704,6 +704,16 @@ def test_empty_batch_is_a_no_op(rb):
     ops.ctrl_sample(z(0), z(0), 0.01)
     ops.push_buffers(3, 2, z(10, 3, 0), z(10, 2, 0), y, a)
     ops.nominal_ni(sysd, y, 0.5, a)
+    # round-2 entry points: disturbance lanes, fp32 critic cost
+    distd = _C.make_disturb([[1, 1], [0, 0], [0.3, 0.3]], seed=1)
+    yf = z(5, 0)
+    ops.rhs_disturbed(sysd, distd, yf, a)
+    assert ops.disturb_normals(distd, 0, 3, device="cuda").shape == (2, 0)
+    ops.rk45_step_disturbed(sysd, distd, sol, yf, z(5, 0), z(0), z(0), z(0, dt=i32), a, z(0, dt=i32))
+    ops.rk45_advance_disturbed(sysd, distd, sol, obj, yf, z(5, 0), z(0), z(0), z(0, dt=i32), a, z(0), 0.01, 4, z(0, dt=i32),
+                               state_sys=z(3, 0), accum=z(0), sample_flag=z(0, dt=i32))
+    f32 = torch.float32
+    assert ops.critic_cost(obj, 3, 2, z(10, 3, 0, dt=f32), z(10, 2, 0, dt=f32), z(5, 0, 1, dt=f32), z(5, 0, dt=f32)).shape == (0, 1)
 
 
 @pytest.mark.parametrize("name,cs", [("2tank", "quad-nomix"), ("3wrobot", "quadratic"), ("3wrobotNI", "quad-lin")])
