@@ -117,7 +117,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     L.use_tma_rt = false;
     {
         const int na = obj->Nactor;
-        const bool na_ok = na == 3 || na == 5 || na == 6 || na == 8 || na == 10;
+        const bool na_ok = na >= 3 && na <= 10;                   // horizons with a compile-time instantiation
         const bool c_ok = (C % 32 == 0) || (C < 32 && (C & (C - 1)) == 0);
         const int64_t cols = E * (int64_t)C;
         if (cand_per_env && L.rdiag && na_ok && c_ok && cols % (16 / (int)sizeof(T)) == 0 && cols < (int64_t)1 << 31 &&

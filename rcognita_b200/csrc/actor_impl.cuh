@@ -767,8 +767,8 @@ static void launch_actor_one(const ActorLaunch<T> &L)
         L.S, L.O, L.A, L.state_sys, L.obs, L.cand, L.w, L.mask, L.J, L.argmin, L.Jmin, L.action, L.accum, L.sampling_time);
 }
 
-// Horizon specialisations (diagonal R, the presets' case): the Nactor values of BASELINE.json's
-// configs (6, 10, 8) and of the presets' defaults (3, 5, 10); everything else runs the runtime loop.
+// Horizon specialisations (diagonal R, the presets' case): every Nactor from 3 to 10 (BASELINE.json's configs use 6, 10, 8,
+// the presets default to 3, 5, 10); everything else runs the runtime loop.
 template <typename T, int SYS, int MODE, int CS>
 static void launch_actor_mc(const ActorLaunch<T> &L)
 {
@@ -777,9 +777,12 @@ static void launch_actor_mc(const ActorLaunch<T> &L)
         if (L.lean) {
             switch (L.O.Nactor) {
             case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3, true>(L); return;
+            case 4:  launch_actor_one<T, SYS, MODE, CS, true, 4, true>(L); return;
             case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5, true>(L); return;
             case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6, true>(L); return;
+            case 7:  launch_actor_one<T, SYS, MODE, CS, true, 7, true>(L); return;
             case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8, true>(L); return;
+            case 9:  launch_actor_one<T, SYS, MODE, CS, true, 9, true>(L); return;
             case 10: launch_actor_one<T, SYS, MODE, CS, true, 10, true>(L); return;
             default: launch_actor_one<T, SYS, MODE, CS, true, 0, true>(L); return;      // runtime horizon, lean
             }
@@ -787,9 +790,12 @@ static void launch_actor_mc(const ActorLaunch<T> &L)
     }
     switch (L.O.Nactor) {
     case 3:  launch_actor_one<T, SYS, MODE, CS, true, 3>(L); return;
+    case 4:  launch_actor_one<T, SYS, MODE, CS, true, 4>(L); return;
     case 5:  launch_actor_one<T, SYS, MODE, CS, true, 5>(L); return;
     case 6:  launch_actor_one<T, SYS, MODE, CS, true, 6>(L); return;
+    case 7:  launch_actor_one<T, SYS, MODE, CS, true, 7>(L); return;
     case 8:  launch_actor_one<T, SYS, MODE, CS, true, 8>(L); return;
+    case 9:  launch_actor_one<T, SYS, MODE, CS, true, 9>(L); return;
     case 10: launch_actor_one<T, SYS, MODE, CS, true, 10>(L); return;
     default: break;
     }

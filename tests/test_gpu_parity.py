@@ -217,8 +217,9 @@ def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
     ("3wrobotNI", "MPC", "quad-nomix", 5, 2502, 8), ("3wrobot", "RQL", "quadratic", 10, 1500, 64),
     ("2tank", "SQL", "quad-nomix", 8, 6000, 32), ("2tank", "MPC", "quad-nomix", 3, 7001, 2),
     ("3wrobotNI", "SQL", "quad-lin", 6, 1000, 1024),
-    # horizons without a compile-time specialisation: the runtime-horizon TMA kernel (boxes of 4 stages; the last box
-    # of Nactor = 7, 13, 50, 1 reaches past the array and is zero-filled by the tensor map)
+    # horizons without a compile-time specialisation (anything outside 3..10): the runtime-horizon TMA kernel (boxes of 4
+    # stages; the last box of Nactor = 13, 50, 1 reaches past the array and is zero-filled by the tensor map); Nactor = 7
+    # has had its own instantiation since round 2
     ("3wrobotNI", "MPC", "quad-nomix", 7, 3001, 256), ("3wrobot", "RQL", "quadratic", 20, 700, 64),
     ("2tank", "SQL", "quad-nomix", 1, 5000, 32), ("3wrobotNI", "SQL", "quad-lin", 50, 300, 16),
     ("3wrobot", "MPC", "quad-nomix", 13, 1203, 8), ("2tank", "RQL", "quad-mix", 12, 900, 96),
@@ -811,7 +812,8 @@ def test_last_actor_kernel_names_the_dispatched_variant(rb):
     sysd = _C.make_system(name, p["pars"], p["bnds"])
     E, C_ = 64, 32
     x = torch.as_tensor(random_states(name, E, 5).T.copy(), device="cuda")
-    for N, per_env, want in ((6, True, "actor_cost_tma_kernel"), (7, True, "actor_cost_tma_rt_kernel"), (6, False, "actor_cost_kernel")):
+    for N, per_env, want in ((6, True, "actor_cost_tma_kernel"), (7, True, "actor_cost_tma_kernel"), (12, True, "actor_cost_tma_rt_kernel"),
+                             (6, False, "actor_cost_kernel")):
         obj = _C.make_objective(n, m, mode="MPC", Nactor=N, pred_step_size=0.01, R1=p["R1_diag"])
         cand = torch.as_tensor(random_cands(name, (E * C_,) if per_env else (C_,), N, 6).T.copy(), device="cuda")
         ops.actor_cost(sysd, obj, x, x, cand, per_env, C_, want_J=False)
