@@ -264,6 +264,15 @@ int rcg_actor_opt(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E
                   double *J_out, int32_t *iters_out, int32_t *nfev_out, int32_t *best_out, double *Jmin_out,
                   double *action_out, double *accum, double sampling_time, void *stream);
 
+/* Kernel variant behind rcg_actor_opt.  Default (0): horizons 3..10 with diagonal R run `actor_opt_quad_kernel` -- four
+ * lanes per problem, quasi-Newton pairs / iterate / rollout in shared memory, distributed inner products, the line search's
+ * trial points evaluated side by side; everything else runs `actor_opt_kernel` (one lane per problem, state in registers and
+ * the workspace).  lanes = 1 forces the one-lane kernel, 4 or 0 restore the default; other values are ignored.  Returns the
+ * previous setting.  Both variants run the same iteration; results agree up to the summation order of inner products.
+ * rcg_last_actor_opt_kernel names the variant the calling thread's last rcg_actor_opt dispatched to. */
+int         rcg_actor_opt_lanes(int32_t lanes);
+const char *rcg_last_actor_opt_kernel(void);
+
 /* _actor_cost and its exact gradient w.r.t. the action sequence for E x S sequences (the adjoint sweep the
  * optimiser uses; what SLSQP approximates by forward differences): J_out[E*S], grad_out[Nactor*m][E*S].
  * `workspace` as for rcg_actor_opt (only read when the horizon/cost structure has no specialised kernel). */

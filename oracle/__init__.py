@@ -117,6 +117,8 @@ def lib():
         L.orc_actor_opt.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
                                     ip, ip]
         L.orc_actor_opt.restype = C.c_double
+        L.orc_actor_opt_set_lanes.argtypes = [C.c_int]
+        L.orc_actor_opt_set_lanes.restype = None
         L.orc_actor_opt_hybrid.argtypes = [C.POINTER(CtrlT), C.POINTER(SysT), dp, dp, dp, dp, C.c_int, C.c_int, C.c_double,
                                            C.c_double, ip, ip]
         L.orc_actor_opt_hybrid.restype = C.c_double
@@ -317,8 +319,11 @@ def actor_grad(c, s, action_sqn, observation, state_sys, w_critic=None):
     return J, g
 
 
-def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_iter=100, pg_tol=1e-6, f_tol=1e-9):
-    """Bounded minimiser of ``_actor_cost`` (SPG, rcg_oracle_opt.c).  Returns (x, J, iters, nfev)."""
+def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_iter=100, pg_tol=1e-6, f_tol=1e-9, lanes=1):
+    """Bounded minimiser of ``_actor_cost`` (projected L-BFGS, rcg_oracle_opt.c).  Returns (x, J, iters, nfev).
+    ``lanes``: summation order of the inner products (1 = index order, the one-lane kernel; 4 = strided partial sums combined
+    pairwise, the four-lanes-per-problem kernel)."""
+    lib().orc_actor_opt_set_lanes(int(lanes))
     a = np.array(action_sqn_init, dtype=np.float64).reshape(-1).copy()
     o, op = _d(observation)
     x, xp = _d(state_sys)
@@ -326,6 +331,7 @@ def actor_opt(c, s, action_sqn_init, observation, state_sys, w_critic=None, max_
     it, nf = C.c_int(0), C.c_int(0)
     J = lib().orc_actor_opt(C.byref(c), C.byref(s), a.ctypes.data_as(C.POINTER(C.c_double)), op, xp, wp,
                             int(max_iter), float(pg_tol), float(f_tol), C.byref(it), C.byref(nf))
+    lib().orc_actor_opt_set_lanes(1)
     return a, J, it.value, nf.value
 
 

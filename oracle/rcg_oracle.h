@@ -128,6 +128,7 @@ long long orc_env_interval(orc_env_t *envs, const orc_ctrl_t *c, const orc_sys_t
  * minimiser standing in for CtrlOptPred._actor_optimizer (ref: controllers.py:1330-1427). */
 double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *action_sqn, const double *observation,
                       const double *state_sys, const double *w_critic, double *grad);
+void orc_actor_opt_set_lanes(int lanes);
 double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
                      const double *state_sys, const double *w_critic, int max_iter, double pg_tol, double f_tol,
                      int *iters_out, int *nfev_out);

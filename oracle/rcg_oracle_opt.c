@@ -178,6 +178,25 @@ double orc_actor_grad(const orc_ctrl_t *c, const orc_sys_t *s, const double *act
 #define ORC_OPT_MEM 6
 #define ORC_OPT_LMAX (ORC_MAX_NACTOR * ORC_MAX_M)
 
+/* Summation order of the inner products.  rcg_actor_opt has two kernels behind it that run this same iteration: one lane
+ * per problem (sums in index order: lanes = 1, the default here) and G = 4 lanes per problem (actor_opt_quad.cuh: lane r
+ * sums the components r, r + G, ... in order, the G partial sums are combined by an xor-butterfly, i.e. pairwise).  The
+ * minimiser of a flat problem moves with the rounding of these sums; orc_actor_opt_set_lanes lets the tests measure by
+ * how much on the checker itself. */
+static _Thread_local int orc_opt_lanes = 1;
+void orc_actor_opt_set_lanes(int lanes) { orc_opt_lanes = (lanes == 2 || lanes == 4 || lanes == 8) ? lanes : 1; }
+
+static double orc_sum_free(const double *u, const double *v, const int *fr, int L)
+{
+    const int G = orc_opt_lanes;
+    double part[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < L; ++i)
+        if (!fr || fr[i]) part[i % G] += u[i] * v[i];
+    for (int st = 1; st < G; st <<= 1)
+        for (int r = 0; r < G; r += 2 * st) part[r] += part[r + st];
+    return part[0];
+}
+
 double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const double *observation,
                      const double *state_sys, const double *w_critic, int max_iter, double pg_tol, double f_tol,
                      int *iters_out, int *nfev_out)
@@ -216,9 +235,8 @@ double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const d
         int have_scale = 0;
         for (int j = 0; j < npairs; ++j) {
             const int k = (head - 1 - j + 2 * ORC_OPT_MEM) % ORC_OPT_MEM;
-            double a = 0.0, ss = 0.0, yy = 0.0, sq = 0.0;
-            for (int i = 0; i < L; ++i)
-                if (fr[i]) { a += S[k][i] * Y[k][i]; ss += S[k][i] * S[k][i]; yy += Y[k][i] * Y[k][i]; sq += S[k][i] * d[i]; }
+            const double a = orc_sum_free(S[k], Y[k], fr, L), ss = orc_sum_free(S[k], S[k], fr, L);
+            const double yy = orc_sum_free(Y[k], Y[k], fr, L), sq = orc_sum_free(S[k], d, fr, L);
             sy[j] = (a > 1e-10 * sqrt(ss * yy)) ? a : 0.0;
             if (sy[j] > 0.0) {
                 al[j] = sq / sy[j];
@@ -230,13 +248,12 @@ double orc_actor_opt(const orc_ctrl_t *c, const orc_sys_t *s, double *x, const d
         for (int j = npairs - 1; j >= 0; --j) {
             if (!(sy[j] > 0.0)) continue;
             const int k = (head - 1 - j + 2 * ORC_OPT_MEM) % ORC_OPT_MEM;
-            double yr = 0.0;
-            for (int i = 0; i < L; ++i) if (fr[i]) yr += Y[k][i] * d[i];
+            const double yr = orc_sum_free(Y[k], d, fr, L);
             const double b = yr / sy[j];
             for (int i = 0; i < L; ++i) if (fr[i]) d[i] += (al[j] - b) * S[k][i];
         }
-        double gd = 0.0;
-        for (int i = 0; i < L; ++i) { d[i] = -d[i]; gd += g[i] * d[i]; }
+        for (int i = 0; i < L; ++i) d[i] = -d[i];
+        const double gd = orc_sum_free(g, d, NULL, L);
         if (!(gd < 0.0) || !isfinite(gd)) {
             npairs = 0;
             for (int i = 0; i < L; ++i) d[i] = fr[i] ? -g[i] * (step0 / pg) : 0.0;

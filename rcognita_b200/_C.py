@@ -68,6 +68,9 @@ def _load():
     L.rcg_last_error_string.restype = C.c_char_p
     L.rcg_device_count.restype = C.c_int
     L.rcg_last_actor_kernel.restype = C.c_char_p
+    L.rcg_last_actor_opt_kernel.restype = C.c_char_p
+    L.rcg_actor_opt_lanes.argtypes = [i32]
+    L.rcg_actor_opt_lanes.restype = C.c_int
     L.rcg_dim_state.argtypes = [i32]
     L.rcg_dim_input.argtypes = [i32]
     L.rcg_dim_critic.argtypes = [i32, i32, i32]
@@ -116,7 +119,7 @@ EXPORTS = [
     "rcg_launch_count", "rcg_reset_launch_count", "rcg_last_actor_kernel", "rcg_rhs", "rcg_rhs_f32", "rcg_state_dyn", "rcg_rk45_step",
     "rcg_rk45_step_f32", "rcg_rk45_advance", "rcg_rk45_advance_f32", "rcg_rk45_advance_logged", "rcg_log_rows",
     "rcg_rhs_disturbed", "rcg_disturb_normals", "rcg_rk45_step_disturbed", "rcg_rk45_advance_disturbed", "rcg_actor_cost", "rcg_actor_cost_f32",
-    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_grad", "rcg_actor_ilqr_workspace_bytes", "rcg_actor_ilqr", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_cost_f32", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
+    "rcg_actor_opt_workspace_bytes", "rcg_actor_opt", "rcg_actor_opt_lanes", "rcg_last_actor_opt_kernel", "rcg_actor_grad", "rcg_actor_ilqr_workspace_bytes", "rcg_actor_ilqr", "rcg_gather_sqn", "rcg_nominal_ni", "rcg_stage_obj", "rcg_critic", "rcg_critic_cost", "rcg_critic_cost_f32", "rcg_critic_fit", "rcg_ctrl_sample", "rcg_push_buffers",
 ]
 
 

@@ -32,6 +32,19 @@ def last_actor_kernel() -> str:
     return (_C.lib.rcg_last_actor_kernel() or b"").decode()
 
 
+def last_actor_opt_kernel() -> str:
+    """Kernel variant the last ``rcg_actor_opt`` call of this thread dispatched to (``rcg_last_actor_opt_kernel``)."""
+    from . import _C
+    return (_C.lib.rcg_last_actor_opt_kernel() or b"").decode()
+
+
+def actor_opt_lanes(lanes: int = 0) -> int:
+    """Select the ``rcg_actor_opt`` kernel variant (``rcg_actor_opt_lanes``): 0 / 4 = four lanes per problem where an
+    instantiation exists (default), 1 = the one-lane kernel.  Returns the previous setting."""
+    from . import _C
+    return int(_C.lib.rcg_actor_opt_lanes(int(lanes)))
+
+
 def last_error() -> str:
     from . import _C
     return _C.last_error()

@@ -27,11 +27,12 @@ SOURCES = {
     "actor_ni_f64.cu": [], "actor_3w_f64.cu": [], "actor_2t_f64.cu": [],
     "actor_ni_f32.cu": [], "actor_3w_f32.cu": [], "actor_2t_f32.cu": [],
     "actor_opt.cu": [], "actor_opt_ni.cu": [], "actor_opt_3w.cu": [], "actor_opt_2t.cu": [], "actor_ilqr.cu": [],
+    "actor_optq_ni.cu": [], "actor_optq_3w.cu": [], "actor_optq_2t.cu": [],
     "critic.cu": ["-fmad=false"],
     "nominal.cu": ["-fmad=false"],
     "critic_fit.cu": [],
 }
-HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", "actor_opt_impl.cuh", "actor_ilqr_core.cuh", os.path.join(INCLUDE, "rcg.h")]
+HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", "actor_opt_impl.cuh", "actor_opt_quad.cuh", "actor_ilqr_core.cuh", os.path.join(INCLUDE, "rcg.h")]
 
 
 def _nvcc() -> str:

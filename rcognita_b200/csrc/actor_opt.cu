@@ -2,9 +2,12 @@
 // sizing, launch geometry and dispatch to the per-system instantiations (actor_opt_impl.cuh, actor_opt_{ni,3w,2t}.cu).
 #include <cstdint>
 
-#include "actor_opt_impl.cuh"
+#include "actor_opt_quad.cuh"
 
 namespace rcg {
+
+static int g_opt_lanes = 0;                                   // rcg_actor_opt_lanes: 0 = default (4 where instantiated), 1 = one lane
+static thread_local const char *g_last_opt_kernel = "";      // variant dispatched by the last rcg_actor_opt of this thread
 
 // sqn_out[i][e] = cand[i][(e*C if per-env) + idx[e]]: the start point of the optimiser = the arg-min candidate.
 __global__ void gather_sqn_kernel(int L, int64_t E, int C, const double *__restrict__ cand, int cand_per_env,
@@ -94,11 +97,22 @@ static int launch_opt(const char *what, const rcg_system_t *sys, const rcg_objec
     const int64_t threads = E * S;
     L.grid = (unsigned)((threads + kOptThreads - 1) / kOptThreads);
     L.stream = (cudaStream_t)stream;
-    int rc;
-    switch (sys->sys_id) {
-    case RCG_SYS_3WROBOT_NI: rc = launch_opt_ni(L); break;
-    case RCG_SYS_3WROBOT:    rc = launch_opt_3w(L); break;
-    default:                 rc = launch_opt_2t(L); break;
+    int rc = 1;
+    if (!grad_only && !generic && g_opt_lanes != 1) {          // G lanes per problem, state in shared memory (actor_opt_quad.cuh)
+        switch (sys->sys_id) {
+        case RCG_SYS_3WROBOT_NI: rc = launch_optq_ni(L); break;
+        case RCG_SYS_3WROBOT:    rc = launch_optq_3w(L); break;
+        default:                 rc = launch_optq_2t(L); break;
+        }
+        if (rc == 0) g_last_opt_kernel = "actor_opt_quad_kernel";
+    }
+    if (rc == 1) {                                             // one lane per problem (generic shapes, rcg_actor_grad)
+        switch (sys->sys_id) {
+        case RCG_SYS_3WROBOT_NI: rc = launch_opt_ni(L); break;
+        case RCG_SYS_3WROBOT:    rc = launch_opt_3w(L); break;
+        default:                 rc = launch_opt_2t(L); break;
+        }
+        if (!grad_only) g_last_opt_kernel = "actor_opt_kernel";
     }
     if (rc) { set_error("%s: bad mode/critic_struct", what); return rc; }
     return check_launch(what);
@@ -136,6 +150,15 @@ int rcg_actor_opt(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E
                            pg_tol, f_tol, workspace, workspace_bytes, J_out, nullptr, iters_out, nfev_out, best_out,
                            Jmin_out, action_out, accum, sampling_time, stream);
 }
+
+int rcg_actor_opt_lanes(int32_t lanes)
+{
+    const int prev = rcg::g_opt_lanes;
+    if (lanes == 0 || lanes == 1 || lanes == 4) rcg::g_opt_lanes = lanes;
+    return prev;
+}
+
+const char *rcg_last_actor_opt_kernel(void) { return rcg::g_last_opt_kernel; }
 
 int rcg_gather_sqn(int32_t L, int64_t E, int32_t C, const double *cand, int32_t cand_per_env, const int32_t *idx,
                    const int32_t *mask, double *sqn_out, void *stream)

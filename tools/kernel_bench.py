@@ -142,7 +142,7 @@ def critic_fit_point(system, cs, E, iters=5):
             "fits_per_s": E / ms * 1e3, "median_cost_ratio_fit_over_init": float((Jc / J0.clamp_min(1e-300)).median().item())}
 
 
-def actor_opt_point(system, mode, cs, N, E, state_scale=1.0, max_iter=300, iters=4):
+def actor_opt_point(system, mode, cs, N, E, state_scale=1.0, max_iter=300, iters=4, lanes=0):
     """rcg_actor_opt (the batched stand-in for _actor_optimizer) from action_sqn_init for E environments.  States
     are drawn from BOX scaled by `state_scale` around the target (small scale = near the goal = interior minimisers,
     more iterations).  Reports solves/s and gradient (forward + adjoint sweep) evaluations/s."""
@@ -170,15 +170,20 @@ def actor_opt_point(system, mode, cs, N, E, state_scale=1.0, max_iter=300, iters
     nf = torch.zeros((E,), device="cuda", dtype=torch.int32)
     sqn = init.clone()
 
+    import rcognita_b200
+    rcognita_b200.actor_opt_lanes(lanes)                  # 0 = default (four lanes per problem where instantiated), 1 = one lane
+
     def fn():
         sqn.copy_(init)
         ops.actor_opt(sysd, obj, x, x, sqn, w_critic=w, max_iter=max_iter, workspace=ws, J_out=J, iters_out=it, nfev_out=nf)
     ms = time_it(fn, iters, warm=2)
+    variant = rcognita_b200.last_actor_opt_kernel()
+    rcognita_b200.actor_opt_lanes(0)
     ms_copy = time_it(lambda: sqn.copy_(init), iters, warm=1)
     ms -= ms_copy
     itc, nfc = it.cpu().numpy(), nf.cpu().numpy()
     J0, _ = ops.actor_grad(sysd, obj, x, x, init, w_critic=w)
-    return {"kernel": "actor_opt", "system": system, "mode": mode, "critic": cs, "Nactor": N, "E": E,
+    return {"kernel": "actor_opt", "variant": variant, "J_mean": float(J.mean().item()), "system": system, "mode": mode, "critic": cs, "Nactor": N, "E": E,
             "state_scale": state_scale, "max_iter": max_iter, "ms": ms, "solves_per_s": E / ms * 1e3,
             "iters_mean": float(itc.mean()), "iters_p50": float(np.median(itc)), "iters_p99": float(np.percentile(itc, 99)),
             "iters_max": int(itc.max()), "linesearch_evals_mean": float(nfc.mean()),
@@ -237,13 +242,14 @@ def main():
         pts += [lambda: critic_fit_point("2tank", "quad-nomix", 262144), lambda: critic_fit_point("3wrobot", "quadratic", 1 << 20),
                 lambda: critic_fit_point("3wrobotNI", "quad-lin", 262144)]
     if a.what in ("opt", "all"):
-        pts += [lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 1.0),
-                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 0.05),
-                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 1 << 20, 0.05),
-                lambda: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 7, 65536, 0.05),        # generic (workspace) kernel
-                lambda: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 1.0),
-                lambda: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 0.05, max_iter=100),
-                lambda: actor_opt_point("2tank", "SQL", "quad-nomix", 8, 262144, 0.5)]
+        for lanes in (0, 1):                               # four lanes per problem (default) and the one-lane kernel
+            pts += [lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 1.0, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 0.05, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 1 << 20, 0.05, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 7, 65536, 0.05, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 1.0, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("3wrobot", "RQL", "quadratic", 10, 262144, 0.05, max_iter=100, lanes=lanes),
+                    lambda lanes=lanes: actor_opt_point("2tank", "SQL", "quad-nomix", 8, 262144, 0.5, lanes=lanes)]
     for p in pts:
         r = p()
         if RANK == 0:
