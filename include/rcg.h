@@ -264,7 +264,7 @@ int rcg_actor_opt(const rcg_system_t *sys, const rcg_objective_t *obj, int64_t E
                   double *J_out, int32_t *iters_out, int32_t *nfev_out, int32_t *best_out, double *Jmin_out,
                   double *action_out, double *accum, double sampling_time, void *stream);
 
-/* Kernel variant behind rcg_actor_opt.  Default (0): horizons 3..10 with diagonal R run `actor_opt_quad_kernel` -- four
+/* Kernel variant behind rcg_actor_opt.  Default (0): Sys3WRobotNI / Sys3WRobot horizons 3..10 with diagonal R run `actor_opt_quad_kernel` -- four
  * lanes per problem, quasi-Newton pairs / iterate / rollout in shared memory, distributed inner products, the line search's
  * trial points evaluated side by side; everything else runs `actor_opt_kernel` (one lane per problem, state in registers and
  * the workspace).  lanes = 1 forces the one-lane kernel, 4 or 0 restore the default; other values are ignored.  Returns the

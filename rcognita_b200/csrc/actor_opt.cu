@@ -98,11 +98,14 @@ static int launch_opt(const char *what, const rcg_system_t *sys, const rcg_objec
     L.grid = (unsigned)((threads + kOptThreads - 1) / kOptThreads);
     L.stream = (cudaStream_t)stream;
     int rc = 1;
-    if (!grad_only && !generic && g_opt_lanes != 1) {          // G lanes per problem, state in shared memory (actor_opt_quad.cuh)
+    // G lanes per problem, state in shared memory (actor_opt_quad.cuh): the two robots.  Sys2Tank (n = 2, m = 1, at most 10
+    // variables) fits the one-lane kernel's registers and its problems take 1-7 iterations: measured 0.19 ms (one lane) against
+    // 0.29 ms (four lanes) per 262,144 SQL N=8 solves, so it stays on the one-lane kernel.
+    if (!grad_only && !generic && g_opt_lanes != 1) {
         switch (sys->sys_id) {
         case RCG_SYS_3WROBOT_NI: rc = launch_optq_ni(L); break;
         case RCG_SYS_3WROBOT:    rc = launch_optq_3w(L); break;
-        default:                 rc = launch_optq_2t(L); break;
+        default:                 break;
         }
         if (rc == 0) g_last_opt_kernel = "actor_opt_quad_kernel";
     }

@@ -34,7 +34,7 @@ struct QuadCfg {
     static constexpr int PS = P + 16 / G;                    // padded problem stride (doubles): (r * PS + q) distinct mod 16
     static constexpr int RS = N + 2;                         // rollout record per stage: state, sin, cos
     static constexpr int oS = 0, oY = kOptMem * L, oX = 2 * kOptMem * L, oG = oX + L, oD = oG + L, oR = oD + L;
-    static constexpr int oA = oR + NA * RS;                  // two-loop coefficients al[kOptMem], sy[kOptMem]
+    static constexpr int oA = oR + NA * RS;                  // two-loop coefficients al[kOptMem], 1 / (s.y)[kOptMem]
     static constexpr int TOT = oA + 2 * kOptMem;
     static constexpr int smem_bytes = TOT * PS * (int)sizeof(double);
     static constexpr int fit = (228 * 1024) / (smem_bytes + 1024);
@@ -357,7 +357,9 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
                 T dv[LPL];
 #pragma unroll
                 for (int j = 0; j < LPL; ++j) dv[j] = ((fr >> j) & 1u) ? gv[j] : T(0);
-                T scale = step0 / pg;
+                // (al_j = (s_j.q) / (s_j.y_j) and the second loop's (y_j.r) / (s_j.y_j) are formed with one reciprocal per pair,
+                // the initial scaling (s.y) / (y.y) of the newest usable pair with one division after the loop)
+                T a_first = T(0), yy_first = T(1);
                 bool have_scale = false;
 #pragma unroll 1
                 for (int jj = 0; jj < npairs; ++jj) {
@@ -376,25 +378,26 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
                         }
                     }
                     a = qsum(a); ss = qsum(ss); yy = qsum(yy); sq = qsum(sq);
-                    T alv = T(0), syv = T(0);
+                    T alv = T(0), rho = T(0);
                     if (a > T(1e-10) * sqrt(ss * yy)) {
-                        syv = a;
-                        alv = sq / a;
+                        rho = T(1) / a;
+                        alv = sq * rho;
 #pragma unroll
                         for (int j = 0; j < LPL; ++j)
                             if ((fr >> j) & 1u) dv[j] -= alv * yv[j];
-                        if (!have_scale) { scale = a / yy; have_scale = true; }
+                        if (!have_scale) { a_first = a; yy_first = yy; have_scale = true; }
                     }
-                    // every lane of the quad holds the same (al, sy) bit for bit (xor-butterfly sums) and reads back its own write
+                    // every lane of the quad holds the same (al, rho) bit for bit (xor-butterfly sums) and reads back its own write
                     at(oA + jj) = alv;
-                    at(oA + kOptMem + jj) = syv;
+                    at(oA + kOptMem + jj) = rho;
                 }
+                const T scale = have_scale ? a_first / yy_first : step0 / pg;
 #pragma unroll
                 for (int j = 0; j < LPL; ++j) dv[j] *= scale;
 #pragma unroll 1
                 for (int jj = npairs - 1; jj >= 0; --jj) {
-                    const T syv = at(oA + kOptMem + jj);
-                    if (!(syv > T(0))) continue;
+                    const T rho = at(oA + kOptMem + jj);
+                    if (!(rho > T(0))) continue;
                     int slot = head - 1 - jj;
                     slot += (slot < 0) ? kOptMem : 0;
                     const T *sp = col + (oS + slot * L + r) * PS, *yp = col + (oY + slot * L + r) * PS;
@@ -409,7 +412,7 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
                         }
                     }
                     yr = qsum(yr);
-                    const T c = at(oA + jj) - yr / syv;
+                    const T c = at(oA + jj) - yr * rho;
 #pragma unroll
                     for (int j = 0; j < LPL; ++j)
                         if ((fr >> j) & 1u) dv[j] += c * sv[j];
@@ -540,9 +543,8 @@ static int launch_optq_sys(const OptLaunch<double> &L)
     return RCG_EINVAL;
 }
 
-// one translation unit per system: actor_optq_ni.cu, actor_optq_3w.cu, actor_optq_2t.cu
+// one translation unit per system: actor_optq_ni.cu, actor_optq_3w.cu
 int launch_optq_ni(const OptLaunch<double> &L);
 int launch_optq_3w(const OptLaunch<double> &L);
-int launch_optq_2t(const OptLaunch<double> &L);
 
 }  // namespace rcg

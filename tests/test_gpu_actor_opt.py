@@ -79,6 +79,7 @@ def test_actor_opt_reaches_the_reference_slsqp_minimum(rb, idx, lanes):
     J0, _ = ops.actor_grad(sysd, obj, state, obs, sqn, w_critic=w)
     J, iters, nfev = ops.actor_opt(sysd, obj, state, obs, sqn, w_critic=w, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
     specialised = 3 <= c["N"] <= 10 and np.count_nonzero(np.array(c["R1"]) - np.diag(np.diagonal(np.array(c["R1"])))) == 0
+    specialised = specialised and c["system"] != "2tank"     # Sys2Tank stays on the one-lane kernel
     assert rcg.last_actor_opt_kernel() == ("actor_opt_quad_kernel" if lanes == 4 and specialised else "actor_opt_kernel")
     J, x = J.cpu().numpy(), sqn.cpu().numpy()
     assert abs(J0[0].item() - c["J_init"]) <= 1e-9 * max(abs(c["J_init"]), 1.0)
@@ -326,8 +327,8 @@ def test_closed_loop_with_optimizer_vs_oracle(rb, lanes):
 @pytest.mark.parametrize("name,mode,cs,N,scale", [
     ("3wrobotNI", "MPC", "quad-nomix", 6, 1.0), ("3wrobotNI", "MPC", "quad-nomix", 6, 0.01), ("3wrobotNI", "SQL", "quad-lin", 5, 0.3),
     ("3wrobotNI", "RQL", "quad-mix", 9, 0.3), ("3wrobot", "RQL", "quadratic", 10, 1.0), ("3wrobot", "MPC", "quad-nomix", 7, 0.1),
-    ("3wrobot", "SQL", "quad-nomix", 4, 1.0), ("2tank", "SQL", "quad-nomix", 8, 1.0), ("2tank", "RQL", "quadratic", 3, 1.0),
-    ("2tank", "MPC", "quad-nomix", 10, 0.2)])
+    ("3wrobot", "SQL", "quad-nomix", 4, 1.0), ("3wrobot", "SQL", "quadratic", 8, 0.3), ("3wrobotNI", "RQL", "quadratic", 3, 1.0),
+    ("3wrobotNI", "MPC", "quad-nomix", 10, 0.2)])
 def test_four_lane_kernel_equals_one_lane_kernel(rb, name, mode, cs, N, scale):
     """The two kernels behind rcg_actor_opt run the same iteration (the parallel line search accepts the point sequential
     halving would have accepted; only the summation order of the inner products differs): on identical inputs -- distinct
@@ -342,7 +343,7 @@ def test_four_lane_kernel_equals_one_lane_kernel(rb, name, mode, cs, N, scale):
     rng = np.random.default_rng(zlib.crc32(f"{name}/{mode}/{cs}/{N}".encode()))
     sysd = _C.make_system(name, p["pars"], p["bnds"])
     obj = _C.make_objective(n, m, mode=mode, Nactor=N, pred_step_size=0.02, gamma=0.97, critic_struct=cs, R1=np.diag(p["R1_diag"]).astype(float))
-    box = {"3wrobotNI": [10, 10, np.pi], "3wrobot": [10, 10, np.pi, 1, 1], "2tank": [2, 2]}[name]
+    box = {"3wrobotNI": [10, 10, np.pi], "3wrobot": [10, 10, np.pi, 1, 1]}[name]
     x = rng.uniform(-1, 1, size=(E, n)) * np.array(box) * scale
     st = dev(x.T.copy())
     ob = dev((x + 1e-3 * rng.standard_normal(x.shape)).T.copy())

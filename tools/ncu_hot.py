@@ -40,3 +40,9 @@ for k, r in enumerate(data):
         st = {h: int(r[ix[h]]) for h in hdr if h.startswith("stall_") and "Not" not in h and r[ix[h]] not in ("", "0")}
         top = sorted(st.items(), key=lambda x: -x[1])[:3]
         print(f"{k:4d} {n:5d} {100 * n / tot:4.1f}%  {r[ix['Source']].strip()[:64]:64s} {top}")
+if len(sys.argv) > 5:                          # full per-SASS-line table: index, address, samples, warp instructions, thread instructions
+    tix = ix.get("Thread Instructions Executed")
+    with open(sys.argv[5], "w") as fh:
+        fh.write("idx,address,samples,inst,thread_inst,sass\n")
+        for k, r in enumerate(data):
+            fh.write(f"{k},{r[0]},{r[ix['# Samples']]},{r[ix['Instructions Executed']]},{r[tix] if tix is not None else ''},\"{r[ix['Source']].strip()}\"\n")
