@@ -12,8 +12,9 @@
 //     iterates are those of the one-lane kernel up to the summation order of the distributed inner products; the quads of a
 //     warp therefore stay in the same phase (one line-search pass, one gradient pass, one two-loop recursion per
 //     iteration) instead of waiting for each other's rejected trial points;
-//   * the value-and-gradient pass at the accepted point (forward sweep that keeps the rollout, reverse sweep) is executed
-//     by every lane of the quad redundantly (it is a serial recurrence over the horizon); lane 0 publishes the results.
+//   * lane 0 of the quad keeps the rollout of its trial point; when a shorter step wins, one more pass re-evaluates it on
+//     lane 0.  The reverse sweep at the accepted point is a serial recurrence over the horizon: lane 0 runs it alone and
+//     publishes x+, g+ and the new pair.
 // A persistent grid pulls problems from the work-queue counter in the workspace header like the one-lane kernel.
 // Costs come from the same device functions as rcg_actor_cost (stage_obj, critic, euler_step), in the same order.
 #pragma once
@@ -179,8 +180,8 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
         return Jc;
     };
 
-    // ---- reverse sweep at clip(x + lam d) over the stored rollout; lane 0 publishes: the new (s, y) pair into `slot`
-    //      (when have_prev), x <- x+, g <- gradient ----
+    // ---- reverse sweep at clip(x + lam d) over the stored rollout (called by lane 0 of the quad only); publishes the new
+    //      (s, y) pair into `slot` (when have_prev), x <- x+, g <- gradient ----
     auto backward = [&](T lam, bool have_prev, int slot) {
         T lamv[N];
 #pragma unroll
@@ -211,17 +212,15 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
             if constexpr (MODE != RCG_MODE_SQL) {
                 if (!done) stage_obj_grad<T, N, M, RDIAG>(O, ob, a, O.gamma_pow[k], gobs, gact);
             }
-            if (r == 0) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const T gt = ga[j] + gact[j];
-                    if (have_prev) {
-                        sp[j * PS] = a[j] - xo[j];
-                        yp[j * PS] = gt - gp[j * PS];
-                    }
-                    xp[j * PS] = a[j];
-                    gp[j * PS] = gt;
+            for (int j = 0; j < M; ++j) {
+                const T gt = ga[j] + gact[j];
+                if (have_prev) {
+                    sp[j * PS] = a[j] - xo[j];
+                    yp[j * PS] = gt - gp[j * PS];
                 }
+                xp[j * PS] = a[j];
+                gp[j * PS] = gt;
             }
             if (k > 0) {
 #pragma unroll
@@ -317,8 +316,9 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
         }
 
         if (!finished) {
-            // ---- gradient at the accepted point ----
-            backward(lam_acc, !first, head);
+            // ---- gradient at the accepted point: a serial recurrence over the horizon, run by lane 0 alone (it reads and
+            //      rewrites x and g stage by stage; the other lanes wait at the barrier) ----
+            if (r == 0) backward(lam_acc, !first, head);
             __syncwarp(qmask);
             bool stop = false;
             if (!first) {
@@ -387,10 +387,14 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
                             if ((fr >> j) & 1u) dv[j] -= alv * yv[j];
                         if (!have_scale) { a_first = a; yy_first = yy; have_scale = true; }
                     }
-                    // every lane of the quad holds the same (al, rho) bit for bit (xor-butterfly sums) and reads back its own write
-                    at(oA + jj) = alv;
-                    at(oA + kOptMem + jj) = rho;
+                    // every lane of the quad holds the same (al, rho) bit for bit (xor-butterfly sums); lane 0 keeps them for
+                    // the second loop
+                    if (r == 0) {
+                        at(oA + jj) = alv;
+                        at(oA + kOptMem + jj) = rho;
+                    }
                 }
+                __syncwarp(qmask);
                 const T scale = have_scale ? a_first / yy_first : step0 / pg;
 #pragma unroll
                 for (int j = 0; j < LPL; ++j) dv[j] *= scale;
