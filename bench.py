@@ -499,6 +499,7 @@ def run_b200(args):
         actor_opt = {"ms_per_step": ms_opt / K2, "steps": K2,
                      "solves_per_s": (int(eng2.nsamples.sum().item()) - n0) / (ms_opt * 1e-3),
                      "env_steps_per_s": (int(eng2.nsteps.sum().item()) - st0) / (ms_opt * 1e-3),
+                     "kernel": rcognita_b200.last_actor_opt_kernel(),      # variant rcg_actor_opt dispatched to (rcg_last_actor_opt_kernel)
                      "api": "ClosedLoopEngine(actor='opt', opt_start='init', opt_pg_tol=1e-4, opt_f_tol=1e-8): rcg_rk45_advance + "
                             "rcg_actor_opt (exact adjoint gradient, projected L-BFGS from action_sqn_init, one bounded "
                             "minimisation of _actor_cost per environment and control interval)"}

@@ -504,10 +504,9 @@ static bool launch_opt_quad(const OptLaunch<double> &L)
 
 // Dispatch over mode / critic structure / horizon for one system.  Returns 0 when a quad kernel (and, for S > 1, the
 // select kernel) was launched, 1 when this problem shape has no quad instantiation (the caller runs the one-lane kernel).
-template <int SYS, int MODE, int CS>
-static int launch_optq_mc(const OptLaunch<double> &L)
+template <int SYS, int MODE, int CS, int G>
+static int launch_optq_g(const OptLaunch<double> &L)
 {
-    constexpr int G = 4;
     bool ok = false;
     switch (L.O.Nactor) {
     case 3:  ok = launch_opt_quad<SYS, MODE, CS, 3, G>(L); break;
@@ -526,6 +525,14 @@ static int launch_optq_mc(const OptLaunch<double> &L)
             L.O, L.A.E, L.A.S, L.obs, L.sqn, L.ws + kOptWsHeader, L.mask, L.best, L.Jmin, L.action, L.accum, L.sampling_time);
     }
     return 0;
+}
+
+template <int SYS, int MODE, int CS>
+static int launch_optq_mc(const OptLaunch<double> &L)
+{
+    // eight lanes per problem (twice the resident warps at 128 registers, three weights per lane) were measured slower on
+    // every bench point: Sys3WRobot N=10 7.35 against 5.90 ms per 262,144 solves, Sys3WRobotNI N=6 1.45 against 0.95 ms
+    return launch_optq_g<SYS, MODE, CS, 4>(L);
 }
 
 template <int SYS>

@@ -242,7 +242,7 @@ def main():
         pts += [lambda: critic_fit_point("2tank", "quad-nomix", 262144), lambda: critic_fit_point("3wrobot", "quadratic", 1 << 20),
                 lambda: critic_fit_point("3wrobotNI", "quad-lin", 262144)]
     if a.what in ("opt", "all"):
-        for lanes in (0, 1):                               # four lanes per problem (default) and the one-lane kernel
+        for lanes in tuple(int(v) for v in os.environ.get('RCG_BENCH_LANES', '0,1').split(',')):   # 0 = default (four lanes per problem), 1 = one lane
             pts += [lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 1.0, lanes=lanes),
                     lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 65536, 0.05, lanes=lanes),
                     lambda lanes=lanes: actor_opt_point("3wrobotNI", "MPC", "quad-nomix", 6, 1 << 20, 0.05, lanes=lanes),
