@@ -581,6 +581,55 @@ def test_actor_opt_edge_cases(rb):
     ops.actor_opt(sysd, obj, e0, e0, torch.zeros((N * m, 0), dtype=torch.float64, device="cuda"), max_iter=5)
 
 
+@pytest.mark.timeout(120)
+def test_four_lane_kernel_degenerate_inputs(rb):
+    """The four-lane kernel on the inputs that must not hang or leak into their neighbours: a non-finite state in one
+    environment (its line search gives up, everybody else's result is bit-identical to the batch without it), an all-zero
+    mask (nothing is touched), an unbounded box (has_bnds = 0: strictly convex objective, interior minimiser equal to the
+    one-lane kernel's), one single problem."""
+    rcg, _C, ops = rb
+    name, N = "3wrobot", 10
+    n, m = DIMS[name]
+    p = PRESET[name]
+    rng = np.random.default_rng(3)
+    E = 97
+    R1 = np.diag([1.0, 10.0, 1.0, 0.1, 0.1, 1e-4, 1e-3])
+    obj = _C.make_objective(n, m, mode="MPC", Nactor=N, pred_step_size=0.05, R1=R1)
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    x = rng.uniform(-1, 1, size=(E, n)) * np.array([3, 3, np.pi, 1, 1])
+    start = np.zeros((N * m, E))
+    st = dev(x.T.copy())
+    sq = dev(start)
+    J, it, nf = ops.actor_opt(sysd, obj, st, st, sq, max_iter=60)
+    assert rcg.last_actor_opt_kernel() == "actor_opt_quad_kernel"
+    xb = x.copy()
+    xb[40, 1] = np.nan
+    xb[41, 3] = np.inf
+    stb = dev(xb.T.copy())
+    sqb = dev(start)
+    Jb, itb, nfb = ops.actor_opt(sysd, obj, stb, stb, sqb, max_iter=60)
+    keep = np.ones(E, dtype=bool)
+    keep[[40, 41]] = False
+    assert torch.equal(sqb[:, keep], sq[:, keep]) and torch.equal(Jb[keep], J[keep]) and torch.equal(itb[keep], it[keep])
+    assert not np.isfinite(Jb.cpu().numpy()[[40, 41]]).any() and np.array_equal(sqb.cpu().numpy()[:, [40, 41]], start[:, [40, 41]])
+    # nothing selected: nothing written
+    sq0 = dev(start + 0.25)
+    J0 = torch.full((E,), -7.0, dtype=torch.float64, device="cuda")
+    ops.actor_opt(sysd, obj, st, st, sq0, mask=torch.zeros(E, dtype=torch.int32, device="cuda"), J_out=J0, max_iter=60)
+    assert bool((sq0 == 0.25).all()) and bool((J0 == -7.0).all())
+    # unbounded box, one problem
+    free = _C.make_system(name, p["pars"], None)
+    one = dev(x[:1].T.copy())
+    res = {}
+    for lanes in (4, 1):
+        rcg.actor_opt_lanes(lanes)
+        sq1 = dev(start[:, :1])
+        J1, it1, _ = ops.actor_opt(free, obj, one, one, sq1, max_iter=300)
+        res[lanes] = (J1[0].item(), sq1.cpu().numpy()[:, 0], it1[0].item())
+    assert abs(res[4][0] - res[1][0]) <= 1e-9 * max(abs(res[1][0]), 1.0) and res[4][0] < J[0].item() + 1e-9
+    assert np.max(np.abs(res[4][1] - res[1][1])) <= 1e-5 * max(np.max(np.abs(res[1][1])), 1.0)
+
+
 # ---- Gauss-Newton (iLQR) pre-pass: rcg_actor_ilqr --------------------------------------------------------------------
 def test_ilqr_presweeps_then_opt_reach_the_slsqp_minimum_without_a_tail(rb):
     """rcg_actor_ilqr followed by rcg_actor_opt on the 72 problems recorded from the live reference: at or below SLSQP's
