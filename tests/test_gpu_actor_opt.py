@@ -540,6 +540,68 @@ def test_closed_loop_with_optimizer_vs_oracle_2tank_sql(rb):
         assert abs(got["accum"][e] - accum) <= 1e-6 * abs(accum)
 
 
+def test_closed_loop_with_optimizer_sample_by_sample_3wrobot_rql(rb):
+    """Sys3WRobot, RQL with a fixed 'quadratic' critic, Nactor = 10 (BASELINE config 3's shapes; the four-lane kernel): every
+    solve of a closed-loop episode with actor='opt' is repeated by the oracle's restatement on the engine's own inputs --
+    cost to 1e-8, first action to 1e-4 of the box -- and the engine's bookkeeping around the solves (which environments
+    sample, what reaches `action` and `accum`) is checked against the recorded solves."""
+    rcg, _C, ops = rb
+    from rcognita_b200.engine import ClosedLoopEngine
+    name, N, t1 = "3wrobot", 10, 0.25
+    n, m = DIMS[name]
+    P = PRESET[name]
+    dt = P["dt"]
+    rng = np.random.default_rng(17)
+    E = 4
+    x0 = rng.uniform(-1, 1, size=(E, n)) * np.array([3.0, 3.0, 2.0, 0.5, 0.5])
+    dimc = oracle.dim_critic("quadratic", n, m)
+    Wm = rng.uniform(0.0, 1.0, size=(n + m, n + m))
+    Wm = Wm @ Wm.T + np.diag([1.0, 1.0, 1.0, 0.5, 0.5, 1e-3, 1e-2])       # positive definite critic: well-conditioned solves
+    w = np.array([Wm[i, j] * (1.0 if i == j else 2.0) for i in range(n + m) for j in range(i, n + m)])
+    assert w.size == dimc
+    R1 = [1.0, 10.0, 1.0, 0.1, 0.1, 1e-4, 1e-3]
+    kw = dict(mode="RQL", Nactor=N, pred_step_size=dt * P["psm"], critic_struct="quadratic", R1=R1)
+    a_init = list(np.array(P["bnds"], dtype=float)[:, 0] / 10)
+    eng = ClosedLoopEngine(name, x0, None, pars=P["pars"], ctrl_bnds=P["bnds"], dt=dt, t1=t1, w_critic=w, action_init=a_init,
+                           actor="opt", opt_start="init", opt_iters=300, **kw)
+    solves = []
+    real = ops.actor_opt
+
+    def recording(sysd, obj, state_sys, obs, sqn, **k):
+        rec = {"state_sys": state_sys.clone(), "obs": obs.clone(), "mask": k["mask"].clone(), "accum0": k["accum"].clone()}
+        out = real(sysd, obj, state_sys, obs, sqn, **k)
+        rec.update(action=k["action_out"].clone(), Jmin=k["Jmin_out"].clone(), accum1=k["accum"].clone())
+        solves.append(rec)
+        return out
+    ops.actor_opt = recording
+    try:
+        eng.run()
+    finally:
+        ops.actor_opt = real
+    assert rcg.last_actor_opt_kernel() == "actor_opt_quad_kernel"
+    got = eng.results()
+    s = oracle.make_sys(name, P["pars"], P["bnds"])
+    ct = oracle.make_ctrl(n, m, **kw)
+    rngbox = np.array(P["bnds"], dtype=float)
+    checked = np.zeros(E, dtype=int)
+    for rec in solves:
+        for e in range(E):
+            if rec["mask"][e].item() == 0:
+                assert rec["accum1"][e].item() == rec["accum0"][e].item()
+                continue
+            ob, st = rec["obs"][:, e].cpu().numpy(), rec["state_sys"][:, e].cpu().numpy()
+            xo, Jo, _, _ = oracle.actor_opt(ct, s, np.tile(a_init, N), ob, st, w, max_iter=300, pg_tol=1e-7, f_tol=1e-12)
+            assert abs(rec["Jmin"][e].item() - Jo) <= 1e-8 * max(abs(Jo), 1.0), (checked, rec["Jmin"][e].item(), Jo)
+            act = rec["action"][:, e].cpu().numpy()
+            # (the cost pins the solve; along the flat directions of the double integrator the stop test |P(x - g) - x| <= 1e-7
+            #  leaves the first action free to a few 1e-6 of the box: measured 4e-6)
+            assert np.max(np.abs(act - xo[:m]) / (rngbox[:, 1] - rngbox[:, 0])) <= 1e-4, (checked, act, xo[:m])
+            so = oracle.stage_obj(ct, n, m, ob, act)
+            assert abs((rec["accum1"][e].item() - rec["accum0"][e].item()) - so * dt) <= 1e-12 * max(abs(so * dt), 1.0)
+            checked[e] += 1
+    assert np.array_equal(checked, got["nsamples"]) and checked.min() >= 20
+
+
 def test_actor_opt_edge_cases(rb):
     """Nactor = 1 (no Euler step at all), one environment with 32 starts, max_iter = 0 (the clipped start point and
     its cost come back), starts outside the box (projected first), and an empty batch."""
