@@ -32,7 +32,6 @@ SOURCES = {
     "nominal.cu": ["-fmad=false"],
     "critic_fit.cu": [],
 }
-HEADERS = ["rcg_device.cuh", "rcg_host.h", "actor_impl.cuh", "actor_opt_impl.cuh", "actor_opt_quad.cuh", "actor_ilqr_core.cuh", os.path.join(INCLUDE, "rcg.h")]
 
 
 def _nvcc() -> str:
@@ -49,16 +48,36 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _includes(path: str, seen=None) -> set:
+    """Project headers a source reaches through `#include "..."` (csrc/ and include/), transitively."""
+    seen = set() if seen is None else seen
+    try:
+        with open(path) as fh:
+            text = fh.read()
+    except OSError:
+        return seen
+    for line in text.splitlines():
+        line = line.strip()
+        if line.startswith('#include "'):
+            name = line.split('"')[1]
+            for base in (CSRC, INCLUDE):
+                cand = os.path.join(base, name)
+                if os.path.exists(cand) and cand not in seen:
+                    seen.add(cand)
+                    _includes(cand, seen)
+    return seen
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
-    hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
     objs = []
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(o)
+        hdrs = sorted(_includes(s)) + [os.path.abspath(__file__)]        # only the headers this source actually includes
         if force or _stale(o, [s] + hdrs):
             jobs.append((src, [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]))
 
