@@ -38,6 +38,13 @@ struct QuadCfg {
     static constexpr int oA = oR + NA * RS;                  // two-loop coefficients al[kOptMem], 1 / (s.y)[kOptMem]
     static constexpr int TOT = oA + 2 * kOptMem;
     static constexpr int smem_bytes = TOT * PS * (int)sizeof(double);
+    // Partial unrolling of the sweeps (measured, Sys3WRobot N=10, 262,144 solves): rolled 5.88 ms; forward sweep x2 5.50, x5
+    // 5.23, FULLY unrolled 6.63 ms (the instruction-fetch cliff again); reverse sweep x2 on top of forward x2: 5.35; pair loops
+    // x2: slower (5.71).  Hence: the largest divisor of the horizon within a per-system stage budget for the forward sweep
+    // (a Sys3WRobot stage is ~1.6x a Sys3WRobotNI stage), two stages of the reverse sweep, pair loops rolled.
+    static constexpr int largest_divisor(int n, int cap) { int d = 1; for (int c = 2; c <= cap && c <= n; ++c) if (n % c == 0) d = c; return d; }
+    static constexpr int unroll_fwd = largest_divisor(NA, N >= 5 ? 5 : 7);
+    static constexpr int unroll_bwd = (NA % 2 == 0) ? 2 : 1;
     static constexpr int fit = (228 * 1024) / (smem_bytes + 1024);
     static constexpr int min_blocks = fit < 1 ? 1 : (fit > 4 ? 4 : fit);
     static_assert(G == 2 || G == 4 || G == 8, "lanes per problem");
@@ -152,7 +159,7 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
         for (int i = 0; i < N; ++i) { st[i] = x0[i]; ob[i] = ob0[i]; }
         const T *xp = col + oX * PS, *dp = col + oD * PS, *gp = col + oG * PS;
         T *rp = col + oR * PS;
-#pragma unroll 1
+#pragma unroll Q::unroll_fwd
         for (int k = 0; k < NA; ++k) {
             T a[M];
 #pragma unroll
@@ -189,7 +196,7 @@ actor_opt_quad_kernel(const __grid_constant__ SysDev<double> Sd, const __grid_co
         T *xp = col + (oX + (NA - 1) * M) * PS, *gp = col + (oG + (NA - 1) * M) * PS;
         const T *dp = col + (oD + (NA - 1) * M) * PS, *rp = col + (oR + (NA - 1) * RS) * PS;
         T *sp = col + (oS + slot * L + (NA - 1) * M) * PS, *yp = col + (oY + slot * L + (NA - 1) * M) * PS;
-#pragma unroll 1
+#pragma unroll Q::unroll_bwd
         for (int k = NA - 1; k >= 0; --k) {
             T a[M], xo[M], ga[M], xk[N], ob[N], gobs[N], gact[M];
 #pragma unroll
