@@ -26,6 +26,7 @@ SOURCES = {
     "actor.cu": [],
     "actor_ni_f64.cu": [], "actor_3w_f64.cu": [], "actor_2t_f64.cu": [],
     "actor_ni_f32.cu": [], "actor_3w_f32.cu": [], "actor_2t_f32.cu": [],
+    "actor_tab_ni.cu": [], "actor_tab_3w.cu": [],
     "actor_opt.cu": [], "actor_opt_ni.cu": [], "actor_opt_3w.cu": [], "actor_opt_2t.cu": [], "actor_ilqr.cu": [],
     "actor_optq_ni.cu": [], "actor_optq_3w.cu": [],
     "critic.cu": ["-fmad=false"],

@@ -2,8 +2,9 @@
 // and dispatch to the per-system kernel instantiations (actor_impl.cuh, actor_{ni,3w,2t}_{f64,f32}.cu).
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
-#include "actor_impl.cuh"
+#include "actor_tab.cuh"
 
 namespace rcg {
 
@@ -58,6 +59,56 @@ static int make_cand_tensor_map(CUtensorMap *tm, const void *base, size_t elem, 
     next = (next + 1) % kCache;
     if (used < kCache) ++used;
     return 0;
+}
+
+// Scratch of the shared-table path (actor_tab.cuh: Nactor * F * C doubles + C flags), one buffer per (thread, stream), grown
+// on demand and kept.  Returns nullptr when none can be had without side effects: the stream is being captured (a captured
+// graph must not depend on a buffer a later, larger call would replace) or the allocation fails.
+static void *actor_tab_scratch(cudaStream_t stream, size_t bytes)
+{
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    struct Slot { cudaStream_t stream; int dev; void *ptr; size_t bytes; };
+    constexpr int kSlots = 16;
+    static thread_local Slot slots[kSlots];
+    static thread_local int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Slot *s = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (slots[i].stream == stream && slots[i].dev == dev) { s = &slots[i]; break; }
+    if (!s) {
+        if (used == kSlots) return nullptr;
+        s = &slots[used++];
+        *s = Slot{stream, dev, nullptr, 0};
+    }
+    if (s->bytes < bytes) {
+        if (s->ptr) {
+            cudaStreamSynchronize(stream);                   // the previous launch on this stream may still read it
+            cudaFree(s->ptr);
+        }
+        s->ptr = nullptr;
+        s->bytes = 0;
+        if (cudaMalloc(&s->ptr, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            s->ptr = nullptr;
+            return nullptr;
+        }
+        s->bytes = bytes;
+    }
+    return s->ptr;
+}
+
+// Smallest batch that takes the table path: RCG_ACTOR_TABLE_MIN_E (default 1024; 1 forces it for tests, a huge value or
+// RCG_ACTOR_NO_TABLE=1 turns it off).
+static int64_t actor_tab_min_envs()
+{
+    if (getenv("RCG_ACTOR_NO_TABLE")) return INT64_MAX;
+    const char *v = getenv("RCG_ACTOR_TABLE_MIN_E");
+    return v ? atoll(v) : 1024;
 }
 
 template <typename T>
@@ -133,6 +184,22 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     }
     L.stream = (cudaStream_t)stream;
     g_last_actor_kernel = L.use_tma ? "actor_cost_tma_kernel" : L.use_tma_rt ? "actor_cost_tma_rt_kernel" : "actor_cost_kernel";
+    // Shared candidate table on a robot with the presets' (lean) objective, MPC / RQL, horizons 3..10, fp64: the candidate
+    // part of the heading is tabulated once per launch (actor_tab.cuh).  Not for small batches (one more launch), not while
+    // the stream is being captured.
+    if constexpr (std::is_same<T, double>::value) {
+        const int na = obj->Nactor;
+        if (!cand_per_env && C % 32 == 0 && L.lean && L.rdiag && na >= 3 && na <= 10 && sys->sys_id != RCG_SYS_2TANK &&
+            (obj->mode == RCG_MODE_MPC || obj->mode == RCG_MODE_RQL) && E >= actor_tab_min_envs()) {
+            if (void *scratch = actor_tab_scratch(L.stream, actor_tab_bytes(sys->sys_id, na, C))) {
+                const int rt = (sys->sys_id == RCG_SYS_3WROBOT_NI) ? launch_actor_tab_ni(L, scratch) : launch_actor_tab_3w(L, scratch);
+                if (rt == 0) {
+                    g_last_actor_kernel = "actor_cost_tab_kernel";
+                    return check_launch(what);
+                }
+            }
+        }
+    }
     int rc;
     switch (sys->sys_id) {
     case RCG_SYS_3WROBOT_NI: rc = launch_actor_ni(L); break;

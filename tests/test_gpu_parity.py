@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): _actor_cost / _critic_cost 1e-9 relative 
 RK45 closed-loop trajectories 1e-6 relative (we assert 1e-9, and exact step times / counts);
 arg-min indices bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -210,6 +212,78 @@ def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
         assert Jmin[e] == J[e, am[e]]
         assert np.array_equal(action_out[e], tab[am[e], :m])
         assert rel_err(accum[e], 0.5 + oracle.stage_obj(c, n, m, obs[e], tab[am[e], :m]) * 0.01) <= COST_RTOL
+
+
+@pytest.mark.parametrize("name,mode,cs,N,C_", [
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 256), ("3wrobotNI", "RQL", "quad-lin", 5, 96), ("3wrobotNI", "RQL", "quad-mix", 10, 32),
+    ("3wrobot", "RQL", "quadratic", 10, 256), ("3wrobot", "MPC", "quad-nomix", 7, 64), ("3wrobot", "RQL", "quad-nomix", 3, 160),
+])
+def test_actor_cost_shared_table_kernel(rb, name, mode, cs, N, C_):
+    """actor_cost_tab_kernel (shared candidate table on a robot, the presets' lean objective: the candidate part of the
+    heading is tabulated once per launch, csrc/actor_tab.cuh) against the oracle and against actor_cost_kernel on the same
+    inputs: costs to 1e-12 relative (the sums of the heading are formed in a different order, ~1e-15), arg-min of the
+    kernel's own costs, action hand-over, accumulated objective, masked environments untouched, a candidate with a non-finite
+    action costs NaN and wins the arg-min like np.argmin -- and the dispatch rule (batches of >= 1,024 environments)."""
+    rcg, _C, ops = rb
+    n, m = DIMS[name]
+    p = PRESET[name]
+    E = 1100
+    sysd = _C.make_system(name, p["pars"], p["bnds"])
+    kw = dict(mode=mode, Nactor=N, pred_step_size=p["dt"] * p["psm"], gamma=1.0, critic_struct=cs, R1=p["R1_diag"])
+    obj = _C.make_objective(n, m, **kw)
+    s = oracle.make_sys(name, p["pars"], p["bnds"])
+    c = oracle.make_ctrl(n, m, **kw)
+    obs = random_states(name, E, 13)
+    xs = obs + 0.01 * np.random.default_rng(14).normal(size=obs.shape)
+    cand = random_cands(name, (C_,), N, 15)
+    dimc = _C.dim_critic(cs, n, m)
+    w = np.random.default_rng(16).uniform(0, 2, size=(E, dimc))
+    mask = np.ones(E, dtype=np.int32)
+    mask[[5, 700, E - 1]] = 0
+
+    def run(table):
+        cdev = dev(table.T.copy())
+        action_out = torch.full((m, E), -777.0, device="cuda", dtype=torch.float64)
+        accum = torch.full((E,), 0.5, device="cuda", dtype=torch.float64)
+        J, am, Jmin = ops.actor_cost(sysd, obj, soa(xs), soa(obs), cdev, False, C_, w_critic=dev(w.T.copy()), w_per_env=True,
+                                     mask=dev(mask, torch.int32), action_out=action_out, accum=accum, sampling_time=0.01)
+        return J.cpu().numpy(), am.cpu().numpy(), Jmin.cpu().numpy(), action_out.T.cpu().numpy(), accum.cpu().numpy()
+
+    J, am, Jmin, act, accum = run(cand)
+    assert rcg.last_actor_kernel() == "actor_cost_tab_kernel"
+    os.environ["RCG_ACTOR_NO_TABLE"] = "1"
+    try:
+        J2, am2, Jmin2, act2, accum2 = run(cand)
+        assert rcg.last_actor_kernel() == "actor_cost_kernel"
+    finally:
+        os.environ.pop("RCG_ACTOR_NO_TABLE", None)
+    live = mask != 0
+    assert np.max(np.abs(J[live] - J2[live]) / np.maximum(np.abs(J2[live]), 1e-300)) <= 1e-12
+    assert np.mean(am[live] == am2[live]) >= 0.999                                   # a flip needs a 1e-15 near-tie
+    for e in list(range(0, E, 97)) + [5, 700, E - 1]:
+        if not mask[e]:
+            assert am[e] == -1 and np.isnan(Jmin[e]) and np.all(act[e] == -777.0) and accum[e] == 0.5
+            continue
+        Jr, ar = oracle.actor_cost_table(c, s, cand, obs[e], xs[e], w[e])
+        assert rel_err(J[e], Jr) <= COST_RTOL
+        assert am[e] == int(np.argmin(J[e])) and Jmin[e] == J[e, am[e]]
+        if am[e] != ar:
+            assert abs(Jr[am[e]] - Jr[ar]) <= COST_RTOL * abs(Jr[ar])
+        assert np.array_equal(act[e], cand[am[e], :m])
+        assert rel_err(accum[e], 0.5 + oracle.stage_obj(c, n, m, obs[e], cand[am[e], :m]) * 0.01) <= COST_RTOL
+    # a non-finite action anywhere in a sequence -- also in the last stage, which never enters the rollout -- costs NaN
+    bad = cand.copy()
+    bad[3, (N - 1) * m] = np.inf
+    bad[C_ - 2, 1] = np.nan
+    Jb, amb, _, _, _ = run(bad)
+    assert np.isnan(Jb[live][:, 3]).all() and np.isnan(Jb[live][:, C_ - 2]).all() and np.all(amb[live] == 3)
+    keep = np.ones(C_, dtype=bool)
+    keep[[3, C_ - 2]] = False
+    assert np.array_equal(Jb[live][:, keep], J[live][:, keep])
+    # small batches stay on the direct kernel (one launch instead of two)
+    few = soa(xs[:64])
+    ops.actor_cost(sysd, obj, few, few, dev(cand.T.copy()), False, C_, w_critic=dev(w[:64].T.copy()), w_per_env=True, want_J=False)
+    assert rcg.last_actor_kernel() == "actor_cost_kernel"
 
 
 @pytest.mark.parametrize("name,mode,cs,N,E,C_", [
