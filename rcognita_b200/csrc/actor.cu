@@ -189,7 +189,7 @@ static int launch_actor(const char *what, const rcg_system_t *sys, const rcg_obj
     // the stream is being captured.
     if constexpr (std::is_same<T, double>::value) {
         const int na = obj->Nactor;
-        if (!cand_per_env && C % 32 == 0 && L.lean && L.rdiag && na >= 3 && na <= 10 && sys->sys_id != RCG_SYS_2TANK &&
+        if (!cand_per_env && ((C % 32 == 0) || (C < 32 && (C & (C - 1)) == 0)) && L.lean && L.rdiag && na >= 3 && na <= 10 && sys->sys_id != RCG_SYS_2TANK &&
             (obj->mode == RCG_MODE_MPC || obj->mode == RCG_MODE_RQL) && E >= actor_tab_min_envs()) {
             if (void *scratch = actor_tab_scratch(L.stream, actor_tab_bytes(sys->sys_id, na, C))) {
                 const int rt = (sys->sys_id == RCG_SYS_3WROBOT_NI) ? launch_actor_tab_ni(L, scratch) : launch_actor_tab_3w(L, scratch);

@@ -17,7 +17,7 @@
 // The sums of the heading are formed in a different order than the reference's step-by-step update (theta_0 + (d_0 + d_1 +
 // ...) instead of ((theta_0 + d_0) + d_1) + ...): costs agree with the other kernels and the oracle to ~1e-15 relative, not
 // bit for bit.  Lean objective only (diagonal R1 with zero action weights, no target, gamma = 1: every preset), MPC and RQL,
-// fp64, horizons 3..10, C a multiple of 32, batches of >= 1,024 environments (one more launch), table within the block's
+// fp64, horizons 3..10, C a multiple of 32 (Sys3WRobotNI: or a power of two below 32), batches of >= 1,024 environments (one more launch), table within the block's
 // shared memory; everything else runs actor_cost_kernel.  A candidate with a non-finite action costs NaN like in the
 // reference (0 * a * a = NaN): one flag per candidate.
 #pragma once
@@ -89,8 +89,10 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
     static_assert(MODE == RCG_MODE_MPC || MODE == RCG_MODE_RQL, "lean objective: MPC and RQL");
     extern __shared__ double tab_s[];
     const int64_t E = A.E;
-    const int C = A.C;                                        // a multiple of 32 (one environment per warp)
+    const int C = A.C, seg = A.seg;                           // Sys3WRobot: seg == 32 (one environment per warp, host-checked)
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int slot = lane >> A.seg_shift, cl = lane & (seg - 1);
+    const int epw = 32 >> A.seg_shift;                        // environments per warp (C < 32: one power-of-two lane segment each)
     const int64_t warp0 = (int64_t)blockIdx.x * kActorWarps + wi;
     const int64_t nwarps = (int64_t)gridDim.x * kActorWarps;
     const T h = O.pred_step_size;
@@ -101,8 +103,9 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
     T *envp = tab_s + (size_t)NA * F * C + (size_t)wi * NA * 3;
     __syncthreads();
 
-    for (int64_t e = warp0; e < A.num_groups; e += nwarps) {
-        const bool active = e < E && (mask_g == nullptr || mask_g[e] != 0);     // warp-uniform
+    for (int64_t g = warp0; g < A.num_groups; g += nwarps) {
+        const int64_t e = g * epw + slot;
+        const bool active = e < E && (mask_g == nullptr || mask_g[e] != 0);     // Sys3WRobot: warp-uniform
         T bestJ = T(0);
         int bestI = kNone;
         if (active) {
@@ -129,7 +132,7 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
             } else {
                 sincos_t(x0[2], &s0, &c0);
             }
-            for (int c = lane; c < C; c += 32) {
+            for (int c = cl; c < C; c += seg) {
                 const T *t = tab_s + c;
                 T x = x0[0], y = x0[1], J = T(0);
 #pragma unroll
@@ -174,12 +177,12 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
                 if (bestI == kNone || argmin_better(J, c, bestJ, bestI)) { bestJ = J; bestI = c; }
             }
         }
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = seg >> 1; off > 0; off >>= 1) {
             const T oJ = __shfl_xor_sync(0xffffffffu, bestJ, off);
             const int oI = __shfl_xor_sync(0xffffffffu, bestI, off);
             if (oI != kNone && (bestI == kNone || argmin_better(oJ, oI, bestJ, bestI))) { bestJ = oJ; bestI = oI; }
         }
-        if (active && lane == 0 && bestI != kNone) {
+        if (active && cl == 0 && bestI != kNone) {
             if (argmin_g) argmin_g[e] = bestI;
             if (Jmin_g) Jmin_g[e] = bestJ;
             if (action_g || accum_g) {
@@ -213,8 +216,10 @@ static int launch_actor_tab_one(const ActorLaunch<double> &L, void *scratch)
     constexpr int F = TabFields<SYS>::F;
     const int C = L.A.C, na = NA;
     const size_t smem = actor_tab_smem_bytes<SYS, NA>(C);
-    // the table must fit the block's shared memory at the residency the register allocation is held to
+    // the table must fit the block's shared memory at the residency the register allocation is held to; Sys3WRobot keeps one
+    // environment part per warp, i.e. one environment per warp
     if (smem > (size_t)(225 * 1024) / actor_min_blocks(SYS, NA, true) - 1024) return 1;
+    if (SYS == RCG_SYS_3WROBOT && L.A.seg != 32) return 1;
     auto kern = actor_cost_tab_kernel<SYS, MODE, CS, NA>;
     static unsigned long long configured = 0;                 // per instantiation, one bit per device
     if (smem > 48 * 1024) {

@@ -217,6 +217,7 @@ def test_actor_cost_vs_oracle(rb, name, mode, cs, N, C_, per_env, w_per_env):
 @pytest.mark.parametrize("name,mode,cs,N,C_", [
     ("3wrobotNI", "MPC", "quad-nomix", 6, 256), ("3wrobotNI", "RQL", "quad-lin", 5, 96), ("3wrobotNI", "RQL", "quad-mix", 10, 32),
     ("3wrobot", "RQL", "quadratic", 10, 256), ("3wrobot", "MPC", "quad-nomix", 7, 64), ("3wrobot", "RQL", "quad-nomix", 3, 160),
+    ("3wrobotNI", "MPC", "quad-nomix", 6, 16), ("3wrobotNI", "RQL", "quadratic", 4, 8),      # several environments per warp
 ])
 def test_actor_cost_shared_table_kernel(rb, name, mode, cs, N, C_):
     """actor_cost_tab_kernel (shared candidate table on a robot, the presets' lean objective: the candidate part of the
