@@ -66,10 +66,15 @@ cand_table_kernel(const __grid_constant__ SysDev<double> S, double h, int C, int
 // immediate offsets from one per-lane base: no address arithmetic, no global-load latency -- the first version read the table
 // through L1 and spent 24 % of its instructions on 64-bit addresses) + per warp the environment part of the heading
 // [Nactor][3] (Sys3WRobot: theta_0 + k h omega_0 and its sin / cos, computed once per environment by lanes 0 .. Nactor-1).
+// In shared memory a candidate's entries are one ROW ([c][k * F + f], row stride odd: consecutive candidates fall into distinct
+// 8-byte banks), so every read is an immediate offset from the lane's row pointer (the [k][f][C] layout of the global table
+// cost an integer multiply-add per read: 13 % of the instructions).
+template <int SYS, int NA>
+__host__ __device__ constexpr int actor_tab_row() { return (NA * TabFields<SYS>::F) | 1; }
 template <int SYS, int NA>
 __host__ __device__ constexpr size_t actor_tab_smem_bytes(int C)
 {
-    return ((size_t)NA * TabFields<SYS>::F * C + (size_t)kActorWarps * NA * 3) * sizeof(double);
+    return ((size_t)actor_tab_row<SYS, NA>() * C + (size_t)kActorWarps * NA * 3) * sizeof(double);
 }
 
 template <int SYS, int MODE, int CS, int NA>
@@ -99,8 +104,12 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
     T r[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) r[i] = O.R1[i * P + i];
-    for (int i = threadIdx.x; i < NA * F * C; i += kActorThreads) tab_s[i] = tab_g[i];
-    T *envp = tab_s + (size_t)NA * F * C + (size_t)wi * NA * 3;
+    constexpr int ROW = actor_tab_row<SYS, NA>();
+    for (int i = threadIdx.x; i < NA * F * C; i += kActorThreads) {           // coalesced read of [k * F + f][c], transposed write
+        const int j = i / C, c = i - j * C;
+        tab_s[c * ROW + j] = tab_g[i];
+    }
+    T *envp = tab_s + (size_t)ROW * C + (size_t)wi * NA * 3;
     __syncthreads();
 
     for (int64_t g = warp0; g < A.num_groups; g += nwarps) {
@@ -133,11 +142,11 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
                 sincos_t(x0[2], &s0, &c0);
             }
             for (int c = cl; c < C; c += seg) {
-                const T *t = tab_s + c;
+                const T *t = tab_s + c * ROW;
                 T x = x0[0], y = x0[1], J = T(0);
 #pragma unroll
                 for (int k = 0; k < NA; ++k) {
-                    const T sp = t[(k * F + 0) * C], cp = t[(k * F + 1) * C], phi = t[(k * F + 2) * C];
+                    const T sp = t[k * F + 0], cp = t[k * F + 1], phi = t[k * F + 2];
                     T sE = s0, cE = c0, thE = x0[2];
                     if constexpr (SYS == RCG_SYS_3WROBOT) { sE = envp[k * 3 + 0]; cE = envp[k * 3 + 1]; thE = envp[k * 3 + 2]; }
                     const T sn = fma(sE, cp, cE * sp), cs = fma(cE, cp, -(sE * sp));          // sin / cos (theta_k)
@@ -145,11 +154,11 @@ actor_cost_tab_kernel(const __grid_constant__ SysDev<double> S, const __grid_con
                     ob[0] = x; ob[1] = y; ob[2] = thE + phi;
                     T vk;
                     if constexpr (SYS == RCG_SYS_3WROBOT) {
-                        vk = x0[3] + t[(k * F + 3) * C];
+                        vk = x0[3] + t[k * F + 3];
                         ob[3] = vk;
-                        ob[4] = x0[4] + t[(k * F + 4) * C];
+                        ob[4] = x0[4] + t[k * F + 4];
                     } else {
-                        vk = t[(k * F + 3) * C];                                                // the action v_k itself
+                        vk = t[k * F + 3];                                                      // the action v_k itself
                     }
                     if (k == 0) {
 #pragma unroll
