@@ -474,53 +474,63 @@ def run_b200(args):
 
     extra = None
     if not args.no_extra:
-        extra = {"env_steps": extra_env_steps(args, rank, world, dev, barrier, allreduce_max, allreduce_sum),
-                 "config3_strong": extra_config3_strong(args, rank, world, dev, barrier, allreduce_max, allreduce_sum)}
+        # (an optional block that fails on every rank -- out of memory on a smaller device, say -- must not take the headline
+        #  line down with it; its entry then says why)
+        extra = {}
+        for key, fn in (("env_steps", extra_env_steps), ("config3_strong", extra_config3_strong)):
+            try:
+                extra[key] = fn(args, rank, world, dev, barrier, allreduce_max, allreduce_sum)
+            except Exception as exc:
+                extra[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.empty_cache()
 
     # ---- extra (N = 1): the same closed loop with the batched bounded minimiser standing in for the SLSQP
     #      _actor_optimizer instead of enumerate-and-argmin; reported beside the headline, not part of it
     actor_opt = None
     if world == 1 and not args.no_opt:
-        K2 = min(K, 200)
-        eng2 = ClosedLoopEngine(SYSTEM, x0, None, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
-                                action_init=ACTION_INIT, device=dev, actor="opt", opt_start="init", opt_pg_tol=1e-4,
-                                opt_f_tol=1e-8)
-        for _ in range(W):
-            eng2.run_interval()
-        torch.cuda.synchronize()
-        n0, st0 = int(eng2.nsamples.sum().item()), int(eng2.nsteps.sum().item())
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(K2):
-            eng2.run_interval()
-        a1.record()
-        torch.cuda.synchronize()
-        ms_opt = a0.elapsed_time(a1)
-        actor_opt = {"ms_per_step": ms_opt / K2, "steps": K2,
-                     "solves_per_s": (int(eng2.nsamples.sum().item()) - n0) / (ms_opt * 1e-3),
-                     "env_steps_per_s": (int(eng2.nsteps.sum().item()) - st0) / (ms_opt * 1e-3),
-                     "kernel": rcognita_b200.last_actor_opt_kernel(),      # variant rcg_actor_opt dispatched to (rcg_last_actor_opt_kernel)
-                     "api": "ClosedLoopEngine(actor='opt', opt_start='init', opt_pg_tol=1e-4, opt_f_tol=1e-8): rcg_rk45_advance + "
-                            "rcg_actor_opt (exact adjoint gradient, projected L-BFGS from action_sqn_init, one bounded "
-                            "minimisation of _actor_cost per environment and control interval)"}
-        del eng2
-        if not args.no_cpu_baseline:
-            # the checker's restatement of the same minimiser on the host cores (bounded sample), like cpu_baseline
-            import oracle
-            if prev_affinity:
-                os.sched_setaffinity(0, prev_affinity)          # all host cores, like the cpu_baseline leg below
-            ns = min(E, 32768)
-            so = oracle.make_sys(SYSTEM, [], BNDS)
-            co = oracle.make_ctrl(3, 2, mode="MPC", Nactor=N, pred_step_size=DT, R1=R1_DIAG)
-            xs = np.ascontiguousarray(np.asarray(x0[:ns], dtype=np.float64))
-            sq0 = np.tile(np.asarray(ACTION_INIT, dtype=np.float64), N)
-            oracle.actor_opt_batch(co, so, sq0, xs[:1024], pg_tol=1e-4, f_tol=1e-8)            # thread pool warm-up
-            tc = time.time()
-            oracle.actor_opt_batch(co, so, sq0, xs, pg_tol=1e-4, f_tol=1e-8)
-            tc = time.time() - tc
-            actor_opt["cpu_port"] = {"solves_per_s": ns / tc, "cores": oracle.num_threads(), "kind": "port",
-                                     "sample": f"{ns} minimisations from action_sqn_init at the initial states "
-                                               "(oracle/rcg_oracle_opt.c, C + OpenMP)"}
+        try:
+            K2 = min(K, 200)
+            eng2 = ClosedLoopEngine(SYSTEM, x0, None, ctrl_bnds=BNDS, mode="MPC", Nactor=N, dt=DT, t1=t1, R1=R1_DIAG,
+                                    action_init=ACTION_INIT, device=dev, actor="opt", opt_start="init", opt_pg_tol=1e-4,
+                                    opt_f_tol=1e-8)
+            for _ in range(W):
+                eng2.run_interval()
+            torch.cuda.synchronize()
+            n0, st0 = int(eng2.nsamples.sum().item()), int(eng2.nsteps.sum().item())
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(K2):
+                eng2.run_interval()
+            a1.record()
+            torch.cuda.synchronize()
+            ms_opt = a0.elapsed_time(a1)
+            actor_opt = {"ms_per_step": ms_opt / K2, "steps": K2,
+                         "solves_per_s": (int(eng2.nsamples.sum().item()) - n0) / (ms_opt * 1e-3),
+                         "env_steps_per_s": (int(eng2.nsteps.sum().item()) - st0) / (ms_opt * 1e-3),
+                         "kernel": rcognita_b200.last_actor_opt_kernel(),      # variant rcg_actor_opt dispatched to (rcg_last_actor_opt_kernel)
+                         "api": "ClosedLoopEngine(actor='opt', opt_start='init', opt_pg_tol=1e-4, opt_f_tol=1e-8): rcg_rk45_advance + "
+                                "rcg_actor_opt (exact adjoint gradient, projected L-BFGS from action_sqn_init, one bounded "
+                                "minimisation of _actor_cost per environment and control interval)"}
+            del eng2
+            if not args.no_cpu_baseline:
+                # the checker's restatement of the same minimiser on the host cores (bounded sample), like cpu_baseline
+                import oracle
+                if prev_affinity:
+                    os.sched_setaffinity(0, prev_affinity)          # all host cores, like the cpu_baseline leg below
+                ns = min(E, 32768)
+                so = oracle.make_sys(SYSTEM, [], BNDS)
+                co = oracle.make_ctrl(3, 2, mode="MPC", Nactor=N, pred_step_size=DT, R1=R1_DIAG)
+                xs = np.ascontiguousarray(np.asarray(x0[:ns], dtype=np.float64))
+                sq0 = np.tile(np.asarray(ACTION_INIT, dtype=np.float64), N)
+                oracle.actor_opt_batch(co, so, sq0, xs[:1024], pg_tol=1e-4, f_tol=1e-8)            # thread pool warm-up
+                tc = time.time()
+                oracle.actor_opt_batch(co, so, sq0, xs, pg_tol=1e-4, f_tol=1e-8)
+                tc = time.time() - tc
+                actor_opt["cpu_port"] = {"solves_per_s": ns / tc, "cores": oracle.num_threads(), "kind": "port",
+                                         "sample": f"{ns} minimisations from action_sqn_init at the initial states "
+                                                   "(oracle/rcg_oracle_opt.c, C + OpenMP)"}
+        except Exception as exc:                               # optional block: never take the headline line down
+            actor_opt = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:
